@@ -1,0 +1,1 @@
+"""Empty import stub (test infrastructure)."""
