@@ -1,0 +1,119 @@
+// TEST-ONLY: compiles the device-agnostic (VI_HD) scalar routines of
+// volumetricinterp_b200/csrc for the CPU so that their arithmetic can be checked
+// against scipy / LAPACK in the GPU-less build container.  This shared object is
+// never loaded by the product package; the product path fails loudly without the
+// CUDA library (volumetricinterp_b200/_native.py).
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include "../volumetricinterp_b200/csrc/vi_math.h"
+#include "../volumetricinterp_b200/csrc/vi_tql.h"
+#include "../volumetricinterp_b200/csrc/vi_brent.h"
+#include "../volumetricinterp_b200/csrc/vi_tridiag.h"
+
+extern "C" {
+
+void h_shl_rows(const vi_shl_params* P, const double* lat, const double* lon, const double* alt,
+                int64_t npts, double* A) {
+  const int N = P->maxk * P->maxl * P->maxl;
+  for (int64_t p = 0; p < npts; ++p) {
+    double* row = A + p * N;
+    vi_shl_row(*P, lat[p], lon[p], alt[p], [&](int n, double v) { row[n] = v; });
+  }
+}
+
+void h_shl_coords(const vi_shl_params* P, const double* lat, const double* lon, const double* alt,
+                  int64_t npts, double* z, double* th, double* ph) {
+  for (int64_t p = 0; p < npts; ++p) vi_shl_coords(*P, lat[p], lon[p], alt[p], z + p, th + p, ph + p);
+}
+
+double h_lpmv_pos(double v, int m, double x) { return vi_lpmv_pos(v, m, x); }
+
+void h_rbf_rows(const double* lat, const double* lon, const double* alt, int64_t npts,
+                const double* centers, int N, double eps, double* A) {
+  for (int64_t p = 0; p < npts; ++p) {
+    double x, y, z;
+    vi_geodetic2ecef(lat[p], lon[p], alt[p], &x, &y, &z);
+    for (int n = 0; n < N; ++n)
+      A[p * N + n] = vi_rbf_value(x, y, z, centers[3 * n], centers[3 * n + 1], centers[3 * n + 2], eps);
+  }
+}
+
+// Truncated pseudo-inverse solve of a symmetric tridiagonal system:
+// w = Z L^+ Z^T g0 ; lam <- eigenvalues ; returns status, *rank, *nrot.
+int h_tql_solve(int n, const double* d0, const double* e0, const double* g0, double rcond,
+                double* w, double* lam, int* rank, int* nrot) {
+  std::vector<double> d(d0, d0 + n), e(n, 0.0), g(g0, g0 + n);
+  for (int i = 0; i + 1 < n; ++i) e[i] = e0[i];
+  int cap = 4 * n * n + 64;
+  std::vector<double> tc(cap), ts(cap);
+  std::vector<int32_t> ti(cap);
+  vi_tape tape{{tc.data(), 1}, {ts.data(), 1}, {ti.data(), 1}, cap};
+  int32_t nr = 0;
+  int st = vi_tql(n, {d.data(), 1}, {e.data(), 1}, {g.data(), 1}, tape, &nr);
+  std::memcpy(lam, d.data(), n * sizeof(double));
+  *rank = vi_spectral_divide(n, {d.data(), 1}, {g.data(), 1}, rcond);
+  vi_tape_apply_z({g.data(), 1}, tape, nr);
+  std::memcpy(w, g.data(), n * sizeof(double));
+  *nrot = nr;
+  return st;
+}
+
+typedef double (*h_fn)(double);
+// brentq driven through the state machine; xs receives every abscissa evaluated.
+int h_brentq(h_fn f, double xa, double xb, double* root, double* xs, int* nfev) {
+  vi_brent b;
+  int n = 0;
+  double fa = f(xa), fb = f(xb);
+  xs[n++] = xa; xs[n++] = xb;
+  vi_brent_init(b, xa, fa, xb, fb);
+  while (!vi_brent_propose(b)) {
+    xs[n++] = b.xcur;
+    vi_brent_feed(b, f(b.xcur));
+  }
+  *root = b.root;
+  *nfev = n;
+  return b.done;
+}
+
+void h_chi2_bracket(const double* table, int npts, int* status, int* k_lo, double* nu) {
+  vi_bracket br = vi_chi2_bracket(table, 1, npts);
+  *status = br.status; *k_lo = br.k_lo; *nu = br.nu;
+}
+
+// The complete per-system pipeline of kernels k_tridiag + k_tql (csrc/fit.cu) executed on the CPU
+// with the phase bodies of vi_tridiag.h run for tid = 0..nt-1 in turn:
+//   X = 2^-ex (sym(G) + sum lam_r Reg_r) -> T = Q^T X Q -> QL with tape -> truncated solve -> C = Q c~.
+// Returns the QL status; *bad = 1 if a non-finite entry was met.
+int h_system_solve(int n, const double* G, const double* y, const double* regs, const double* lam, int nreg,
+                   int nt, double rcond, double* C, int* rank, double* dd, double* ee, int* bad) {
+  const int ld = vi_tri_ld(n);
+  std::vector<double> X((size_t)n * ld), aux(vi_tri_aux_doubles(n, nt) + 16), V((size_t)n * n, 0.0);
+  vi_tri_ws S;
+  double* a = aux.data();
+  S.X = X.data(); S.ld = ld;
+  S.v = a; S.w = a + n; S.yv = a + 2 * n; S.red2 = a + 3 * n; S.d = a + 4 * n; S.e = a + 5 * n;
+  S.tau = a + 6 * n; S.sc = a + 7 * n; S.red1 = a + 7 * n + 8; S.psum = S.red1 + (nt > n ? nt : n);
+  vi_tri_load(S, n, G, y, regs, lam, nreg, 0, nt);
+  *bad = S.sc[1] != 0.0;
+  if (*bad) return 0;
+  vi_tri_reduce(S, n, V.data(), 0, nt);
+  for (int i = 0; i < n; ++i) { dd[i] = S.d[i]; ee[i] = S.e[i]; }
+  std::vector<double> d(S.d, S.d + n), e(S.e, S.e + n), g(S.yv, S.yv + n), tau(S.tau, S.tau + n);
+  int cap = n * n + 64;
+  std::vector<double> tc(cap), ts(cap);
+  std::vector<int32_t> ti(cap);
+  vi_tape tape{{tc.data(), 1}, {ts.data(), 1}, {ti.data(), 1}, cap};
+  int32_t nr = 0;
+  int st = vi_tql(n, {d.data(), 1}, {e.data(), 1}, {g.data(), 1}, tape, &nr);
+  if (st != 0) return st;
+  *rank = vi_spectral_divide(n, {d.data(), 1}, {g.data(), 1}, rcond);
+  vi_tape_apply_z({g.data(), 1}, tape, nr);
+  for (int i = 0; i < n; ++i) g[i] *= S.sc[0];
+  vi_tri_backtransform(n, V.data(), tau.data(), 1, g.data(), 1);
+  std::memcpy(C, g.data(), n * sizeof(double));
+  return 0;
+}
+
+int h_sizeof_shl_params() { return (int)sizeof(vi_shl_params); }
+}

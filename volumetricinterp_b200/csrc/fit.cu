@@ -1,0 +1,684 @@
+// K3 — per-record solve and regularisation-parameter search, batched over records.
+//
+// Replaces, for R records at once, the body of the reference's record loop after the normal
+// equations (interpolate.py:555-569):
+//   find_reg_param -> chi2 -> chi2objfunct -> eval_C      interpolate.py:97-147, 152-261, 432-469
+//   NaN-record rule                                         interpolate.py:558-563
+//   final eval_C and chi^2                                  interpolate.py:566, 569
+//
+// The reference re-solves (A^T W A + 10^alpha R) C = A^T W b with scipy.linalg.lstsq (LAPACK
+// gelsd, rcond = eps) ~400-500 times per record, recomputing A^T W A each time.  Here the normal
+// equations come from K2 once per record, and every trial is one "system":
+//   k_tridiag  one CTA per system: X = sym(G) + sum lambda R in shared memory, Householder
+//              tridiagonalisation, g = Q^T y                                  (vi_tridiag.h)
+//   k_tql      one THREAD per system: implicit QL with a rotation tape, truncated spectral
+//              solve (|eig| > eps*max|eig| == gelsd's rcond rule), back-transform with the
+//              stored reflectors                                              (vi_tql.h)
+//   k_chi2     chi^2 = sum_j W_j ((A C)_j - b_j)^2 exactly as chi2objfunct does (residual form),
+//              16 systems per CTA so the design matrix is streamed once per 16 systems
+// chi2objfunct(alpha) - nu depends on the scale factor only through nu, so the decade walk of
+// interpolate.py:180-207 runs on a table chi2(10^-k), k = 0..101, evaluated ONCE per record
+// (all its systems are independent -> one big batch); Brent's iterations are then advanced for
+// all records in lock step (vi_brent.h state machine), one batch of systems per iteration.
+#include "common.cuh"
+#include <math.h>
+#include <vector>
+#include "vi_brent.h"
+#include "vi_tql.h"
+#include "vi_tridiag.h"
+
+namespace {
+
+constexpr int kSkip = -1;          // system slot not in use this round
+constexpr int kChiSB = 16;         // systems per CTA in k_chi2
+constexpr int kChiThreads = 256;
+
+// ------------------------------------------------------------------------------------------
+// workspace carving (identical arithmetic in vi_fit_workspace_bytes and the entry points)
+// ------------------------------------------------------------------------------------------
+struct Bump {
+  char* base; int64_t off; int64_t cap;
+  template <class T> T* take(int64_t count) {
+    off = vi_align_up(off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * (int64_t)sizeof(T);
+    return p;
+  }
+};
+
+struct SysBuf {
+  int64_t cap;         // systems held at once (multiple of 32)
+  int n, nreg, tapecap, nt, use_gx, ld;
+  size_t smem;
+  double *V, *d, *e, *g, *tau, *scl, *tc, *ts, *lam, *Csys, *chi2, *Xg;
+  int32_t *tix, *st, *rec, *rank;
+};
+
+int tri_threads(int n) {
+  int ng = 1024 / n;
+  if (ng > 4) ng = 4;
+  if (ng < 1) ng = 1;
+  int nt = (ng * n + 31) / 32 * 32;
+  if (nt > 1024) nt = 1024;
+  return nt;
+}
+
+void sysbuf_carve(Bump& b, SysBuf& S, int64_t cap, int n, int nreg) {
+  S.cap = cap; S.n = n; S.nreg = nreg;
+  S.tapecap = n * n + 64;
+  S.nt = tri_threads(n);
+  S.ld = vi_tri_ld(n);
+  size_t smem_x = (size_t)n * S.ld * sizeof(double);
+  size_t smem_aux = (size_t)vi_tri_aux_doubles(n, S.nt) * sizeof(double);
+  S.use_gx = (smem_x + smem_aux > 227 * 1024) ? 1 : 0;
+  S.smem = S.use_gx ? smem_aux : smem_x + smem_aux;
+  S.V = b.take<double>(cap * n * n);
+  S.d = b.take<double>(cap * n);
+  S.e = b.take<double>(cap * n);
+  S.g = b.take<double>(cap * n);
+  S.tau = b.take<double>(cap * n);
+  S.scl = b.take<double>(cap);
+  S.tc = b.take<double>(cap * S.tapecap);
+  S.ts = b.take<double>(cap * S.tapecap);
+  S.tix = b.take<int32_t>(cap * S.tapecap);
+  S.lam = b.take<double>(cap * (nreg > 0 ? nreg : 1));
+  S.Csys = b.take<double>(cap * n);
+  S.chi2 = b.take<double>(cap);
+  S.st = b.take<int32_t>(cap);
+  S.rec = b.take<int32_t>(cap);
+  S.rank = b.take<int32_t>(cap);
+  S.Xg = S.use_gx ? b.take<double>(cap * n * S.ld) : nullptr;
+}
+
+struct UnitBuf {      // one search unit = (record, regulariser)
+  double* table;      // U x VI_NALPHA
+  vi_brent* br;       // U
+  double* nu;         // U
+  int32_t* status;    // U
+  int32_t* active;    // U
+  int32_t* tabbad;    // U
+  int32_t* count;     // 1
+};
+
+void unit_carve(Bump& b, UnitBuf& Ub, int64_t U) {
+  Ub.table = b.take<double>(U * VI_NALPHA);
+  Ub.br = b.take<vi_brent>(U);
+  Ub.nu = b.take<double>(U);
+  Ub.status = b.take<int32_t>(U);
+  Ub.active = b.take<int32_t>(U);
+  Ub.tabbad = b.take<int32_t>(U);
+  Ub.count = b.take<int32_t>(8);
+}
+
+int64_t per_system_bytes(int n, int nreg) {
+  Bump b{nullptr, 0, 0};
+  SysBuf S;
+  sysbuf_carve(b, S, 32, n, nreg);
+  return (b.off + 32 * 256) / 32;
+}
+
+int64_t default_system_cap(int64_t wanted, int n, int nreg) {
+  int64_t per = per_system_bytes(n, nreg);
+  int64_t budget = (int64_t)16 << 30;   // 16 GiB of scratch by default
+  int64_t cap = budget / per;
+  if (cap > wanted) cap = wanted;
+  if (cap < 32) cap = 32;
+  return vi_align_up(cap, 32);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t ileave(int64_t s, int n) { return (s >> 5) * 32 * (int64_t)n + (s & 31); }
+
+__global__ void __launch_bounds__(1024)
+k_tridiag(const double* __restrict__ G, const double* __restrict__ y, const double* __restrict__ regs, SysBuf B) {
+  extern __shared__ __align__(16) double sm[];
+  const int64_t s = blockIdx.x;
+  const int r = B.rec[s];
+  if (r < 0) { if (threadIdx.x == 0) B.st[s] = kSkip; return; }
+  const int n = B.n, nt = blockDim.x, tid = threadIdx.x;
+  vi_tri_ws S;
+  double* aux = sm;
+  S.ld = B.ld;
+  if (B.use_gx) S.X = B.Xg + s * (int64_t)n * S.ld;
+  else { S.X = sm; aux = sm + (size_t)n * S.ld; }
+  const int ng = (nt / n) < 1 ? 1 : (nt / n);
+  S.v = aux; S.w = aux + n; S.yv = aux + 2 * n; S.red2 = aux + 3 * n; S.d = aux + 4 * n; S.e = aux + 5 * n;
+  S.tau = aux + 6 * n; S.sc = aux + 7 * n; S.red1 = aux + 7 * n + 8; S.psum = S.red1 + (nt > n ? nt : n);
+  (void)ng;
+  vi_tri_load(S, n, G + (int64_t)r * n * n, y + (int64_t)r * n, regs, B.lam + s * (B.nreg > 0 ? B.nreg : 1), B.nreg, tid, nt);
+  const bool bad = S.sc[1] != 0.0;
+  if (!bad) vi_tri_reduce(S, n, B.V + s * (int64_t)n * n, tid, nt);
+  const int64_t base = ileave(s, n);
+  if (!bad)
+    for (int i = tid; i < n; i += nt) {
+      B.d[base + (int64_t)i * 32] = S.d[i];
+      B.e[base + (int64_t)i * 32] = S.e[i];
+      B.g[base + (int64_t)i * 32] = S.yv[i];
+      B.tau[base + (int64_t)i * 32] = S.tau[i];
+    }
+  if (tid == 0) { B.scl[s] = S.sc[0]; B.st[s] = bad ? VI_ST_NONFINITE : VI_ST_OK; }
+}
+
+__global__ void __launch_bounds__(64)
+k_tql(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, int32_t* __restrict__ rank_out) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nsys) return;
+  const int st = B.st[s];
+  if (st == kSkip) return;
+  const int n = B.n;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  double* Cs = Cout + s * (int64_t)n;
+  if (st != VI_ST_OK) {
+    for (int i = 0; i < n; ++i) Cs[i] = nan;
+    rank_out[s] = 0;
+    return;
+  }
+  const int64_t base = ileave(s, n);
+  vi_svec d{B.d + base, 32}, e{B.e + base, 32}, g{B.g + base, 32};
+  const int64_t tb = ileave(s, B.tapecap);
+  vi_tape tape{{B.tc + tb, 32}, {B.ts + tb, 32}, {B.tix + tb, 32}, B.tapecap};
+  int32_t nrot = 0;
+  const int q = vi_tql(n, d, e, g, tape, &nrot);
+  if (q != 0) {
+    B.st[s] = VI_ST_NOCONV;
+    for (int i = 0; i < n; ++i) Cs[i] = nan;
+    rank_out[s] = 0;
+    return;
+  }
+  const int rank = vi_spectral_divide(n, d, g, rcond);
+  vi_tape_apply_z(g, tape, nrot);
+  const double scl = B.scl[s];
+  for (int i = 0; i < n; ++i) g[i] = g[i] * scl;
+  vi_tri_backtransform(n, B.V + s * (int64_t)n * n, B.tau + base, 32, g.p, 32);
+  for (int i = 0; i < n; ++i) Cs[i] = g[i];
+  rank_out[s] = rank;
+}
+
+// chi2[s] = sum_j Wm[r][j] * (sum_n At[n][j] C_s[n] - bm[r][j])^2   (chi2objfunct, interpolate.py:258-259)
+__global__ void __launch_bounds__(kChiThreads)
+k_chi2(const double* __restrict__ At, const double* __restrict__ Wm, const double* __restrict__ bm, int P, int n,
+       int64_t nsys, const int32_t* __restrict__ rec, const int32_t* __restrict__ st, const double* __restrict__ Csys,
+       double* __restrict__ chi2) {
+  extern __shared__ __align__(16) double sm[];
+  double* Cs = sm;                         // n x kChiSB  (n-major so one LDS.128 serves two systems)
+  double* red = sm + (size_t)n * kChiSB;   // kChiThreads/32 x kChiSB
+  __shared__ int srec[kChiSB];
+  const int64_t s0 = (int64_t)blockIdx.x * kChiSB;
+  const int tid = threadIdx.x;
+  if (tid < kChiSB) {
+    int64_t s = s0 + tid;
+    int r = kSkip;
+    if (s < nsys && st[s] == VI_ST_OK) r = rec[s];
+    srec[tid] = r;
+  }
+  __syncthreads();
+  bool any = false;
+  for (int q = 0; q < kChiSB; ++q) any = any || (srec[q] >= 0);
+  if (!any) return;
+  for (int e = tid; e < n * kChiSB; e += kChiThreads) {
+    int i = e / kChiSB, q = e - i * kChiSB;
+    Cs[e] = (srec[q] >= 0) ? Csys[(s0 + q) * (int64_t)n + i] : 0.0;
+  }
+  __syncthreads();
+  bool same = true;
+  for (int q = 1; q < kChiSB; ++q) same = same && (srec[q] == srec[0]);
+  double csum[kChiSB];
+#pragma unroll
+  for (int q = 0; q < kChiSB; ++q) csum[q] = 0.0;
+  for (int j = tid; j < P; j += kChiThreads) {
+    double acc[kChiSB];
+#pragma unroll
+    for (int q = 0; q < kChiSB; ++q) acc[q] = 0.0;
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+      const double a = At[(int64_t)i * P + j];
+      const double2* c2 = reinterpret_cast<const double2*>(Cs + i * kChiSB);
+#pragma unroll
+      for (int q = 0; q < kChiSB / 2; ++q) {
+        double2 c = c2[q];
+        acc[2 * q] = fma(a, c.x, acc[2 * q]);
+        acc[2 * q + 1] = fma(a, c.y, acc[2 * q + 1]);
+      }
+    }
+    if (same) {
+      const int r = srec[0];
+      const double w = Wm[(int64_t)r * P + j], b = bm[(int64_t)r * P + j];
+#pragma unroll
+      for (int q = 0; q < kChiSB; ++q) { double t = acc[q] - b; csum[q] += (t * t) * w; }
+    } else {
+#pragma unroll
+      for (int q = 0; q < kChiSB; ++q) {
+        const int r = srec[q];
+        if (r >= 0) {
+          const double w = Wm[(int64_t)r * P + j], b = bm[(int64_t)r * P + j];
+          double t = acc[q] - b;
+          csum[q] += (t * t) * w;
+        }
+      }
+    }
+  }
+  // deterministic reduction: warp shuffle tree, then the 8 warp sums in order
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int q = 0; q < kChiSB; ++q) {
+    double v = csum[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp * kChiSB + q] = v;
+  }
+  __syncthreads();
+  if (tid < kChiSB) {
+    int64_t s = s0 + tid;
+    if (s < nsys && srec[tid] >= 0) {
+      double v = 0.0;
+      for (int w = 0; w < kChiThreads / 32; ++w) v += red[w * kChiSB + tid];
+      chi2[s] = v;
+    }
+  }
+}
+
+// ---- system set-up for the three phases ---------------------------------------------------
+// table phase: global system index t = u*VI_NALPHA + k, chunk covers [t0, t0 + cnt)
+__global__ void k_setup_table(int64_t t0, int64_t cnt, int nreg, const int32_t* __restrict__ npts,
+                              const double* __restrict__ pow10tab, SysBuf B) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B.cap) return;
+  if (s >= cnt) { B.rec[s] = kSkip; return; }
+  int64_t t = t0 + s;
+  int64_t u = t / VI_NALPHA;
+  int k = (int)(t - u * VI_NALPHA);
+  int r = (int)(u / nreg), q = (int)(u - (int64_t)r * nreg);
+  B.rec[s] = (npts[r] > 0) ? r : kSkip;
+  for (int i = 0; i < nreg; ++i) B.lam[s * nreg + i] = (i == q) ? pow10tab[k] : 0.0;
+}
+
+__global__ void k_scatter_table(int64_t t0, int64_t cnt, SysBuf B, UnitBuf Ub) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= cnt) return;
+  int64_t t = t0 + s;
+  int64_t u = t / VI_NALPHA;
+  int st = B.st[s];
+  if (st == kSkip) return;
+  if (st != VI_ST_OK) { atomicMax(&Ub.tabbad[u], st); Ub.table[t] = __longlong_as_double(0x7ff8000000000000LL); return; }
+  Ub.table[t] = B.chi2[s];
+}
+
+__global__ void k_bracket(int64_t U, int nreg, const int32_t* __restrict__ npts, UnitBuf Ub) {
+  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  int r = (int)(u / nreg);
+  Ub.active[u] = 0;
+  Ub.nu[u] = 0.0;
+  if (npts[r] <= 0) { Ub.status[u] = VI_ST_EMPTY; return; }
+  if (Ub.tabbad[u] != 0) { Ub.status[u] = Ub.tabbad[u]; return; }
+  const double* tab = Ub.table + u * VI_NALPHA;
+  vi_bracket br = vi_chi2_bracket(tab, 1, npts[r]);
+  Ub.status[u] = br.status;
+  Ub.nu[u] = br.nu;
+  if (br.status != VI_ST_OK) return;
+  const int k = br.k_lo;
+  vi_brent b;
+  vi_brent_init(b, -(double)k, tab[k] - br.nu, -(double)(k - 1), tab[k - 1] - br.nu);
+  Ub.br[u] = b;
+  Ub.active[u] = 1;
+}
+
+// Brent: advance units [u0, u0+cnt) to their next abscissa; system slot s = u - u0
+__global__ void k_brent_propose(int64_t u0, int64_t cnt, int nreg, SysBuf B, UnitBuf Ub) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B.cap) return;
+  if (s >= cnt) { B.rec[s] = kSkip; return; }
+  int64_t u = u0 + s;
+  B.rec[s] = kSkip;
+  if (!Ub.active[u]) return;
+  vi_brent b = Ub.br[u];
+  bool fin = vi_brent_propose(b);
+  Ub.br[u] = b;
+  if (fin) {
+    Ub.active[u] = 0;
+    if (b.done != 1) Ub.status[u] = VI_ST_NOCONV;
+    return;
+  }
+  int r = (int)(u / nreg), q = (int)(u - (int64_t)r * nreg);
+  B.rec[s] = r;
+  const double lamv = exp10(b.xcur);   // np.power(10., alpha), interpolate.py:250
+  for (int i = 0; i < nreg; ++i) B.lam[s * nreg + i] = (i == q) ? lamv : 0.0;
+  atomicAdd(Ub.count, 1);
+}
+
+__global__ void k_brent_feed(int64_t u0, int64_t cnt, SysBuf B, UnitBuf Ub) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= cnt) return;
+  int64_t u = u0 + s;
+  if (!Ub.active[u] || B.rec[s] < 0) return;
+  int st = B.st[s];
+  if (st != VI_ST_OK) { Ub.active[u] = 0; Ub.status[u] = (st == VI_ST_NONFINITE) ? VI_ST_NONFINITE : VI_ST_NOCONV; return; }
+  double f = B.chi2[s] - Ub.nu[u];
+  if (!isfinite(f)) { Ub.active[u] = 0; Ub.status[u] = VI_ST_NOCONV; return; }
+  vi_brent b = Ub.br[u];
+  vi_brent_feed(b, f);
+  Ub.br[u] = b;
+}
+
+// final phase: records [r0, r0+cnt), slot s = r - r0
+__global__ void k_setup_final(int64_t r0, int64_t cnt, int nreg, int method, const int32_t* __restrict__ npts,
+                              SysBuf B, UnitBuf Ub, double* __restrict__ lam_out, int32_t* __restrict__ status_out) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B.cap) return;
+  if (s >= cnt) { B.rec[s] = kSkip; return; }
+  int64_t r = r0 + s;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  int worst = VI_ST_OK;
+  bool bad = false;
+  if (npts[r] <= 0) { worst = VI_ST_EMPTY; bad = true; }
+  if (method == VI_METHOD_CHI2) {
+    for (int q = 0; q < nreg; ++q) {
+      int64_t u = r * nreg + q;
+      int st = Ub.status[u];
+      double l;
+      if (bad) l = nan;
+      else if (st == VI_ST_OK) l = exp10(Ub.br[u].root);   // interpolate.py:216
+      else if (st == VI_ST_TOO_SMOOTH) l = 0.0;
+      else l = nan;
+      if (!bad && st != VI_ST_OK && st != VI_ST_TOO_SMOOTH) { bad = true; worst = st; }
+      else if (!bad && st == VI_ST_TOO_SMOOTH && worst == VI_ST_OK) worst = VI_ST_TOO_SMOOTH;
+      lam_out[r * nreg + q] = l;
+    }
+  } else {
+    for (int q = 0; q < nreg; ++q) lam_out[r * nreg + q] = 0.0;
+  }
+  status_out[r] = worst;
+  B.rec[s] = bad ? kSkip : (int)r;
+  for (int q = 0; q < nreg; ++q) B.lam[s * nreg + q] = bad ? 0.0 : lam_out[r * nreg + q];
+}
+
+__global__ void k_finalize(int64_t r0, int64_t cnt, int n, SysBuf B, double* __restrict__ C, double* __restrict__ chi2,
+                           int32_t* __restrict__ rank, int32_t* __restrict__ status_out) {
+  int64_t s = (int64_t)blockIdx.x;
+  if (s >= cnt) return;
+  int64_t r = r0 + s;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  int st = B.st[s];
+  bool bad = (B.rec[s] < 0) || (st != VI_ST_OK);
+  if (bad) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) C[r * n + i] = nan;
+    if (threadIdx.x == 0) {
+      chi2[r] = nan;
+      rank[r] = 0;
+      if (B.rec[s] >= 0 && st != VI_ST_OK) status_out[r] = (st == VI_ST_NONFINITE) ? VI_ST_NONFINITE : VI_ST_NOCONV;
+    }
+  } else if (threadIdx.x == 0) {
+    chi2[r] = B.chi2[s];
+    rank[r] = B.rank[s];
+  }
+}
+
+__global__ void k_setup_solve(int64_t s0, int64_t cnt, int nreg, const int32_t* __restrict__ rec,
+                              const double* __restrict__ lam, SysBuf B) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B.cap) return;
+  if (s >= cnt) { B.rec[s] = kSkip; return; }
+  B.rec[s] = rec ? rec[s0 + s] : (int)(s0 + s);
+  for (int q = 0; q < nreg; ++q) B.lam[s * nreg + q] = lam[(s0 + s) * nreg + q];
+}
+
+__global__ void k_copy_status(int64_t cnt, SysBuf B, int32_t* __restrict__ rank, int32_t* __restrict__ status) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= cnt) return;
+  int st = B.st[s];
+  status[s] = (st == kSkip) ? VI_ST_EMPTY : st;
+  rank[s] = (st == VI_ST_OK) ? B.rank[s] : 0;
+}
+
+__global__ void k_transpose(const double* __restrict__ A, int P, int N, double* __restrict__ At) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)P * N) return;
+  int j = (int)(e / N), i = (int)(e - (int64_t)j * N);
+  At[(int64_t)i * P + j] = A[e];
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side drivers
+// ------------------------------------------------------------------------------------------
+inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+int run_systems(int64_t cnt, const double* G, const double* y, const double* regs, const SysBuf& B, double rcond,
+                double* Cout, int32_t* rank_out, cudaStream_t s) {
+  if (cnt <= 0) return VI_OK;
+  VI_CUDA(cudaFuncSetAttribute(k_tridiag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
+  k_tridiag<<<(unsigned)cnt, B.nt, B.smem, s>>>(G, y, regs, B);
+  VI_LAUNCH_CHECK();
+  k_tql<<<blocks(cnt, 64), 64, 0, s>>>(cnt, B, rcond, Cout, rank_out);
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
+
+int run_chi2(int64_t cnt, const double* At, const double* Wm, const double* bm, int P, const SysBuf& B,
+             const double* Csys, double* chi2, cudaStream_t s) {
+  if (cnt <= 0) return VI_OK;
+  size_t smem = ((size_t)B.n * kChiSB + (kChiThreads / 32) * kChiSB) * sizeof(double);
+  VI_CUDA(cudaFuncSetAttribute(k_chi2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_chi2<<<blocks(cnt, kChiSB), kChiThreads, smem, s>>>(At, Wm, bm, P, B.n, cnt, B.rec, B.st, Csys, chi2);
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
+
+}  // namespace
+
+extern "C" int vi_fit_workspace_bytes(int32_t R, int32_t P, int32_t N, int32_t nreg, int64_t systems, int64_t* bytes) {
+  VI_REQUIRE(bytes != nullptr && R >= 0 && N >= 1 && nreg >= 0, "bad arguments");
+  (void)P;
+  if (N > 1024) { vi_set_error("nbasis %d > 1024 not supported", N); return VI_EUNSUPPORTED; }
+  int64_t U = (int64_t)R * (nreg > 0 ? nreg : 1);
+  int64_t wanted = U * VI_NALPHA;
+  if (wanted < R) wanted = R;
+  int64_t cap = systems > 0 ? vi_align_up(systems, 32) : default_system_cap(wanted, N, nreg);
+  Bump b{nullptr, 0, 0};
+  UnitBuf Ub;
+  unit_carve(b, Ub, U);
+  b.take<double>(VI_NALPHA);
+  *bytes = b.off + per_system_bytes(N, nreg) * (cap + 32) + 16384;
+  return VI_OK;
+}
+
+// cap actually available inside a given workspace
+static int64_t cap_for_workspace(int64_t ws_bytes, int64_t U, int n, int nreg) {
+  Bump b{nullptr, 0, 0};
+  UnitBuf Ub;
+  unit_carve(b, Ub, U);
+  b.take<double>(VI_NALPHA);
+  int64_t left = ws_bytes - b.off - 8192;
+  int64_t per = per_system_bytes(n, nreg);
+  int64_t cap = left / per;
+  cap = cap / 32 * 32;
+  return cap;
+}
+
+extern "C" int vi_solve_batched(const double* G, const double* y, const int32_t* rec, const double* regmats,
+                                const double* lam, int64_t S, int32_t N, int32_t nreg, double rcond,
+                                double* C, int32_t* rank, int32_t* status,
+                                void* workspace, int64_t workspace_bytes, void* stream) {
+  VI_REQUIRE(G && y && C && rank && status && workspace, "NULL argument");
+  VI_REQUIRE(S >= 0 && N >= 1 && N <= 1024 && nreg >= 0, "bad shape");
+  VI_REQUIRE(nreg == 0 || (regmats && lam), "regmats/lam missing");
+  if (S == 0) return VI_OK;
+  cudaStream_t st = vi_stream(stream);
+  int64_t cap = cap_for_workspace(workspace_bytes, 0, N, nreg);
+  if (cap < 32) { vi_set_error("workspace too small (%lld bytes)", (long long)workspace_bytes); return VI_EWORKSPACE; }
+  if (cap > vi_align_up(S, 32)) cap = vi_align_up(S, 32);
+  Bump b{reinterpret_cast<char*>(workspace), 0, workspace_bytes};
+  SysBuf B;
+  sysbuf_carve(b, B, cap, N, nreg);
+  for (int64_t s0 = 0; s0 < S; s0 += cap) {
+    int64_t cnt = (S - s0 < cap) ? S - s0 : cap;
+    k_setup_solve<<<blocks(cap, 256), 256, 0, st>>>(s0, cnt, nreg, rec, lam, B);
+    VI_LAUNCH_CHECK();
+    if (int rc = run_systems(cnt, G, y, regmats, B, rcond, C + s0 * N, B.rank, st)) return rc;
+    k_copy_status<<<blocks(cnt, 256), 256, 0, st>>>(cnt, B, rank + s0, status + s0);
+    VI_LAUNCH_CHECK();
+  }
+  return VI_OK;
+}
+
+extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* bm,
+                              const double* G, const double* y, const int32_t* npts,
+                              int32_t R, int32_t P, int32_t N,
+                              const double* regmats, int32_t nreg, int32_t method,
+                              double* C, double* dC, double* chi2, double* lam, int32_t* rank, int32_t* status,
+                              int64_t* nsolve, void* workspace, int64_t workspace_bytes, void* stream) {
+  VI_REQUIRE(At && Wm && bm && G && y && npts && C && chi2 && rank && status && workspace, "NULL argument");
+  VI_REQUIRE(R >= 0 && P >= 1 && N >= 1 && N <= 1024 && nreg >= 0, "bad shape");
+  VI_REQUIRE(method == VI_METHOD_NONE || method == VI_METHOD_CHI2, "unknown method %d", method);
+  VI_REQUIRE(method == VI_METHOD_NONE || (nreg >= 1 && regmats && lam), "chi2 method needs regularisation matrices");
+  if (dC != nullptr) { vi_set_error("covariance output not available in this build"); return VI_EUNSUPPORTED; }
+  if (nsolve) *nsolve = 0;
+  if (R == 0) return VI_OK;
+  if (method == VI_METHOD_NONE) nreg = 0;
+  cudaStream_t st = vi_stream(stream);
+  const double rcond = VI_EPS;
+  const int64_t U = (int64_t)R * (nreg > 0 ? nreg : 1);
+
+  int64_t cap = cap_for_workspace(workspace_bytes, U, N, nreg);
+  if (cap < 32) { vi_set_error("workspace too small (%lld bytes)", (long long)workspace_bytes); return VI_EWORKSPACE; }
+  int64_t most = vi_align_up(method == VI_METHOD_CHI2 ? U * VI_NALPHA : (int64_t)R, 32);
+  if (cap > most) cap = most;
+  Bump b{reinterpret_cast<char*>(workspace), 0, workspace_bytes};
+  UnitBuf Ub;
+  unit_carve(b, Ub, U);
+  double* pow10tab = b.take<double>(VI_NALPHA);
+  SysBuf B;
+  sysbuf_carve(b, B, cap, N, nreg);
+  int64_t solved = 0;
+
+  if (method == VI_METHOD_CHI2) {
+    double h_tab[VI_NALPHA];
+    for (int k = 0; k < VI_NALPHA; ++k) h_tab[k] = pow(10.0, -(double)k);   // np.power(10., alpha), interpolate.py:250
+    VI_CUDA(cudaMemcpyAsync(pow10tab, h_tab, sizeof(h_tab), cudaMemcpyHostToDevice, st));
+    VI_CUDA(cudaMemsetAsync(Ub.tabbad, 0, U * sizeof(int32_t), st));
+    // ---- phase 1: chi2(10^-k) table for every unit -------------------------------------
+    const int64_t T = U * VI_NALPHA;
+    for (int64_t t0 = 0; t0 < T; t0 += cap) {
+      int64_t cnt = (T - t0 < cap) ? T - t0 : cap;
+      k_setup_table<<<blocks(cap, 256), 256, 0, st>>>(t0, cnt, nreg, npts, pow10tab, B);
+      VI_LAUNCH_CHECK();
+      if (int rc = run_systems(cnt, G, y, regmats, B, rcond, B.Csys, B.rank, st)) return rc;
+      if (int rc = run_chi2(cnt, At, Wm, bm, P, B, B.Csys, B.chi2, st)) return rc;
+      k_scatter_table<<<blocks(cnt, 256), 256, 0, st>>>(t0, cnt, B, Ub);
+      VI_LAUNCH_CHECK();
+      solved += cnt;
+    }
+    // ---- phase 2: bracket + Brent in lock step ------------------------------------------
+    k_bracket<<<blocks(U, 128), 128, 0, st>>>(U, nreg, npts, Ub);
+    VI_LAUNCH_CHECK();
+    for (int it = 0; it < VI_BRENT_MAXITER + 2; ++it) {
+      VI_CUDA(cudaMemsetAsync(Ub.count, 0, sizeof(int32_t), st));
+      int h_count_total = 0;
+      for (int64_t u0 = 0; u0 < U; u0 += cap) {
+        int64_t cnt = (U - u0 < cap) ? U - u0 : cap;
+        k_brent_propose<<<blocks(cap, 128), 128, 0, st>>>(u0, cnt, nreg, B, Ub);
+        VI_LAUNCH_CHECK();
+        if (U > cap) {
+          // several chunks: finish this chunk before its slots are reused
+          if (int rc = run_systems(cnt, G, y, regmats, B, rcond, B.Csys, B.rank, st)) return rc;
+          if (int rc = run_chi2(cnt, At, Wm, bm, P, B, B.Csys, B.chi2, st)) return rc;
+          k_brent_feed<<<blocks(cnt, 128), 128, 0, st>>>(u0, cnt, B, Ub);
+          VI_LAUNCH_CHECK();
+        }
+      }
+      int h_count = 0;
+      VI_CUDA(cudaMemcpyAsync(&h_count, Ub.count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      VI_CUDA(cudaStreamSynchronize(st));
+      h_count_total = h_count;
+      if (h_count_total == 0) break;
+      solved += h_count_total;
+      if (U <= cap) {
+        if (int rc = run_systems(U, G, y, regmats, B, rcond, B.Csys, B.rank, st)) return rc;
+        if (int rc = run_chi2(U, At, Wm, bm, P, B, B.Csys, B.chi2, st)) return rc;
+        k_brent_feed<<<blocks(U, 128), 128, 0, st>>>(0, U, B, Ub);
+        VI_LAUNCH_CHECK();
+      }
+    }
+  }
+  // ---- phase 3: final solve with the found parameters (interpolate.py:566-569) -----------
+  for (int64_t r0 = 0; r0 < R; r0 += cap) {
+    int64_t cnt = (R - r0 < cap) ? R - r0 : cap;
+    k_setup_final<<<blocks(cap, 128), 128, 0, st>>>(r0, cnt, nreg, method, npts, B, Ub, lam, status);
+    VI_LAUNCH_CHECK();
+    if (int rc = run_systems(cnt, G, y, regmats, B, rcond, C + r0 * N, B.rank, st)) return rc;
+    if (int rc = run_chi2(cnt, At, Wm, bm, P, B, C + r0 * N, B.chi2, st)) return rc;
+    k_finalize<<<(unsigned)cnt, 64, 0, st>>>(r0, cnt, N, B, C, chi2, rank, status);
+    VI_LAUNCH_CHECK();
+    solved += cnt;
+  }
+  if (nsolve) *nsolve = solved;
+  return VI_OK;
+}
+
+extern "C" int vi_fit_host(const double* A, const double* value, const double* error, const double* weight,
+                           int32_t R, int32_t P, int32_t N, const double* regmats, int32_t nreg, int32_t method,
+                           int32_t ne_mode, double* C, double* dC, double* chi2, double* lam, int32_t* rank,
+                           int32_t* status) {
+  VI_REQUIRE(A && value && error && C && chi2 && rank && status, "NULL argument");
+  VI_REQUIRE(R >= 0 && P >= 1 && N >= 1, "bad shape");
+  if (dC != nullptr) { vi_set_error("covariance output not available in this build"); return VI_EUNSUPPORTED; }
+  if (R == 0) return VI_OK;
+  cudaStream_t s = nullptr;
+  int64_t ws_bytes = 0;
+  if (int rc = vi_fit_workspace_bytes(R, P, N, nreg, 0, &ws_bytes)) return rc;
+  const size_t RP = (size_t)R * P, PN = (size_t)P * N, NN = (size_t)N * N;
+  std::vector<void*> owned;
+  auto dalloc = [&](size_t bytes) -> void* {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 8) != cudaSuccess) return nullptr;
+    owned.push_back(p);
+    return p;
+  };
+  auto cleanup = [&]() { for (void* p : owned) cudaFree(p); };
+  double* dA = (double*)dalloc(PN * 8);
+  double* dAt = (double*)dalloc(PN * 8);
+  double* dval = (double*)dalloc(RP * 8);
+  double* derr = (double*)dalloc(RP * 8);
+  double* dwt = weight ? (double*)dalloc(RP * 8) : nullptr;
+  double* dWm = (double*)dalloc(RP * 8);
+  double* dbm = (double*)dalloc(RP * 8);
+  double* dG = (double*)dalloc((size_t)R * NN * 8);
+  double* dy = (double*)dalloc((size_t)R * N * 8);
+  double* dreg = (double*)dalloc((size_t)(nreg > 0 ? nreg : 1) * NN * 8);
+  double* dC_ = (double*)dalloc((size_t)R * N * 8);
+  double* dchi = (double*)dalloc((size_t)R * 8);
+  double* dlam = (double*)dalloc((size_t)R * (nreg > 0 ? nreg : 1) * 8);
+  int32_t* dnp = (int32_t*)dalloc((size_t)R * 4);
+  int32_t* drank = (int32_t*)dalloc((size_t)R * 4);
+  int32_t* dst = (int32_t*)dalloc((size_t)R * 4);
+  void* ws = dalloc((size_t)ws_bytes);
+  if (!dA || !dAt || !dval || !derr || !dWm || !dbm || !dG || !dy || !dreg || !dC_ || !dchi || !dlam || !dnp ||
+      !drank || !dst || !ws || (weight && !dwt)) {
+    cleanup();
+    vi_set_error("cudaMalloc failed (workspace %lld bytes)", (long long)ws_bytes);
+    return VI_ECUDA;
+  }
+  int rc = VI_OK;
+#define VI_TRY(x) do { if (rc == VI_OK) { cudaError_t _e = (x); if (_e != cudaSuccess) { vi_set_error("%s -> %s", #x, cudaGetErrorString(_e)); rc = VI_ECUDA; } } } while (0)
+  VI_TRY(cudaMemcpyAsync(dA, A, PN * 8, cudaMemcpyHostToDevice, s));
+  VI_TRY(cudaMemcpyAsync(dval, value, RP * 8, cudaMemcpyHostToDevice, s));
+  VI_TRY(cudaMemcpyAsync(derr, error, RP * 8, cudaMemcpyHostToDevice, s));
+  if (weight) VI_TRY(cudaMemcpyAsync(dwt, weight, RP * 8, cudaMemcpyHostToDevice, s));
+  if (nreg > 0) VI_TRY(cudaMemcpyAsync(dreg, regmats, (size_t)nreg * NN * 8, cudaMemcpyHostToDevice, s));
+  if (rc == VI_OK) {
+    k_transpose<<<blocks((int64_t)PN, 256), 256, 0, s>>>(dA, P, N, dAt);
+    rc = vi_normal_eq_batched(dA, dval, derr, dwt, R, P, N, ne_mode, dG, dy, nullptr, dnp, dWm, dbm, s);
+  }
+  if (rc == VI_OK)
+    rc = vi_fit_batched(dAt, dWm, dbm, dG, dy, dnp, R, P, N, dreg, nreg, method, dC_, nullptr, dchi, dlam, drank, dst,
+                        nullptr, ws, ws_bytes, s);
+  VI_TRY(cudaMemcpyAsync(C, dC_, (size_t)R * N * 8, cudaMemcpyDeviceToHost, s));
+  VI_TRY(cudaMemcpyAsync(chi2, dchi, (size_t)R * 8, cudaMemcpyDeviceToHost, s));
+  if (lam && nreg > 0) VI_TRY(cudaMemcpyAsync(lam, dlam, (size_t)R * nreg * 8, cudaMemcpyDeviceToHost, s));
+  VI_TRY(cudaMemcpyAsync(rank, drank, (size_t)R * 4, cudaMemcpyDeviceToHost, s));
+  VI_TRY(cudaMemcpyAsync(status, dst, (size_t)R * 4, cudaMemcpyDeviceToHost, s));
+  VI_TRY(cudaStreamSynchronize(s));
+#undef VI_TRY
+  cleanup();
+  return rc;
+}

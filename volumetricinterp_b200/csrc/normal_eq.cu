@@ -1,0 +1,335 @@
+// K2 — error-weighted normal equations for many time records at once.
+//
+// Replaces, for R records per launch, the reference's
+//   mask = isfinite(ne0)                         interpolate.py:516-520
+//   W = er0**-2 ; b = ne0                        interpolate.py:523-524
+//   AWA = einsum('ji,j,jk->ik', A, W, A)         interpolate.py:456
+//   y   = einsum('ji,j,j->i',  A, W, b)          interpolate.py:458
+// The design matrix A (P x N) is evaluated once for all P gates; invalid gates get w = 0,
+// b = 0, which is bit-identical to the reference's row deletion (adding +0.0 terms).
+//
+// Two kernels:
+//   k_ne_strict  VI_NE_STRICT: acc = (A[j,i]*w[j])*A[j,k] + acc, sequential in j, two
+//                roundings per term, never fused — reproduces np.einsum bit for bit.
+//   k_ne_dmma    VI_NE_FAST: per record a symmetric rank-P update G = (A.w)^T A on the FP64
+//                tensor-core path (mma.sync m16n8k4 f64), lower-triangular 16x8 tiles only, the
+//                right-hand side y = A^T (w.b) rides along as one extra tile column.  A is
+//                staged through shared memory by cp.async double buffering; the weights are
+//                applied to the A-fragment in registers.
+#include "common.cuh"
+
+namespace {
+
+// correctly rounded 1/(e*e) (double-double product, one Newton correction)
+__device__ __forceinline__ double inv_square(double e) {
+  double hi = e * e;
+  double lo = fma(e, e, -hi);
+  double q = 1.0 / hi;
+  double r = fma(-q, hi, 1.0);
+  r = fma(-q, lo, r);
+  return fma(r, q, q);
+}
+
+// masked weight / datum of gate idx (flattened r*P + j)
+__device__ __forceinline__ void load_wb(const double* __restrict__ value, const double* __restrict__ error,
+                                        const double* __restrict__ weight, int64_t idx, double& w, double& b) {
+  double v = value[idx];
+  bool ok = isfinite(v);
+  double ww = weight ? weight[idx] : inv_square(error[idx]);
+  w = ok ? ww : 0.0;
+  b = ok ? v : 0.0;
+}
+
+__global__ void __launch_bounds__(256)
+k_prep(const double* __restrict__ value, const double* __restrict__ error, const double* __restrict__ weight,
+       int P, double* __restrict__ sWbb, int32_t* __restrict__ npts, double* __restrict__ Wm, double* __restrict__ bm) {
+  __shared__ double ssum[256];
+  __shared__ int scnt[256];
+  const int r = blockIdx.x;
+  double s = 0.0;
+  int cnt = 0;
+  for (int j = threadIdx.x; j < P; j += blockDim.x) {
+    int64_t idx = (int64_t)r * P + j;
+    double w, b;
+    load_wb(value, error, weight, idx, w, b);
+    if (isfinite(value[idx])) ++cnt;
+    s += w * b * b;
+    if (Wm) Wm[idx] = w;
+    if (bm) bm[idx] = b;
+  }
+  ssum[threadIdx.x] = s;
+  scnt[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { ssum[threadIdx.x] += ssum[threadIdx.x + o]; scnt[threadIdx.x] += scnt[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { if (sWbb) sWbb[r] = ssum[0]; if (npts) npts[r] = scnt[0]; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// strict: 128 x 128 output super-block per CTA, 8 x 8 per thread, gates staged 32 at a time
+// ---------------------------------------------------------------------------------------------
+constexpr int kSB = 128, kST = 8, kSJ = 32;
+
+__global__ void __launch_bounds__(256)
+k_ne_strict(const double* __restrict__ A, const double* __restrict__ value, const double* __restrict__ error,
+            const double* __restrict__ weight, int P, int N, int nsb, double* __restrict__ G, double* __restrict__ y) {
+  extern __shared__ double sm[];
+  double* Ai = sm;                    // kSJ x kSB
+  double* Ak = sm + kSJ * kSB;        // kSJ x kSB
+  double* sw = sm + 2 * kSJ * kSB;    // kSJ
+  double* sb = sw + kSJ;              // kSJ
+  const int r = blockIdx.x / (nsb * nsb);
+  const int sbi = (blockIdx.x / nsb) % nsb, sbk = blockIdx.x % nsb;
+  const int ti = threadIdx.x / 16, tk = threadIdx.x % 16;
+  const int i0 = sbi * kSB, k0 = sbk * kSB;
+  double acc[kST][kST];
+  double yacc[kST];
+#pragma unroll
+  for (int a = 0; a < kST; ++a) {
+    yacc[a] = 0.0;
+#pragma unroll
+    for (int b = 0; b < kST; ++b) acc[a][b] = 0.0;
+  }
+  const bool do_y = (sbk == 0) && (tk == 0);
+  for (int j0 = 0; j0 < P; j0 += kSJ) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < kSJ * kSB; e += 256) {
+      int jj = e / kSB, c = e % kSB;
+      int j = j0 + jj;
+      double vi = 0.0, vk = 0.0;
+      if (j < P) {
+        if (i0 + c < N) vi = A[(int64_t)j * N + i0 + c];
+        if (k0 + c < N) vk = A[(int64_t)j * N + k0 + c];
+      }
+      Ai[e] = vi;
+      Ak[e] = vk;
+    }
+    if (threadIdx.x < kSJ) {
+      int j = j0 + threadIdx.x;
+      double w = 0.0, b = 0.0;
+      if (j < P) load_wb(value, error, weight, (int64_t)r * P + j, w, b);
+      sw[threadIdx.x] = w;
+      sb[threadIdx.x] = b;
+    }
+    __syncthreads();
+    const int jn = min(kSJ, P - j0);
+    for (int jj = 0; jj < jn; ++jj) {
+      const double w = sw[jj];
+      double t[kST], ak[kST];
+#pragma unroll
+      for (int a = 0; a < kST; ++a) t[a] = __dmul_rn(Ai[jj * kSB + ti + 16 * a], w);
+#pragma unroll
+      for (int b = 0; b < kST; ++b) ak[b] = Ak[jj * kSB + tk + 16 * b];
+#pragma unroll
+      for (int a = 0; a < kST; ++a)
+#pragma unroll
+        for (int b = 0; b < kST; ++b) acc[a][b] = __dadd_rn(__dmul_rn(t[a], ak[b]), acc[a][b]);
+      if (do_y) {
+        const double bj = sb[jj];
+#pragma unroll
+        for (int a = 0; a < kST; ++a) yacc[a] = __dadd_rn(__dmul_rn(t[a], bj), yacc[a]);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < kST; ++a) {
+    int i = i0 + ti + 16 * a;
+    if (i >= N) continue;
+#pragma unroll
+    for (int b = 0; b < kST; ++b) {
+      int k = k0 + tk + 16 * b;
+      if (k < N) G[((int64_t)r * N + i) * N + k] = acc[a][b];
+    }
+    if (do_y) y[(int64_t)r * N + i] = yacc[a];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fast: FP64 tensor-core (DMMA) symmetric rank-P update, one record per CTA
+// ---------------------------------------------------------------------------------------------
+constexpr int kDW = 12;          // warps per CTA
+constexpr int kDT = 12;          // max 16x8 tiles per warp
+constexpr int kDJ = 32;          // gates per stage
+constexpr int kDStages = 2;
+
+__device__ __forceinline__ void dmma_16x8x4(double (&d)[4], double a0, double a1, double b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+      : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3])
+      : "d"(a0), "d"(a1), "d"(b0));
+}
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// leading dimension (doubles) of a staged row: >= cols, 2*ld mod 32 in {8, 24} (conflict-free fragments)
+__host__ __device__ inline int dmma_ld(int cols) {
+  int ld = cols;
+  while (((2 * ld) % 32) != 8 && ((2 * ld) % 32) != 24) ++ld;
+  return ld;
+}
+
+__global__ void __launch_bounds__(kDW * 32)
+k_ne_dmma(const double* __restrict__ A, const double* __restrict__ value, const double* __restrict__ error,
+          const double* __restrict__ weight, int P, int N, int mt, int nt, int ld, int ntiles, int tpw,
+          double* __restrict__ G, double* __restrict__ y) {
+  extern __shared__ double sm[];
+  double* As = sm;                                     // kDStages x kDJ x ld
+  double* sw = sm + (size_t)kDStages * kDJ * ld;       // kDStages x kDJ
+  unsigned char* tmi = reinterpret_cast<unsigned char*>(sw + kDStages * kDJ);   // ntiles
+  unsigned char* tni = tmi + 256;
+  const int r = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  // tile table: lower-triangular 16x8 tiles (8*ni <= 16*mi + 15), then the rhs column tiles (ni = nt-1)
+  if (tid == 0) {
+    int c = 0;
+    for (int mi = 0; mi < mt; ++mi) {
+      for (int ni = 0; ni < nt - 1; ++ni)
+        if (8 * ni <= 16 * mi + 15 && 8 * ni < N) { tmi[c] = (unsigned char)mi; tni[c] = (unsigned char)ni; ++c; }
+      tmi[c] = (unsigned char)mi; tni[c] = (unsigned char)(nt - 1); ++c;
+    }
+  }
+  // zero both stages once (padding columns stay zero; cp.async only overwrites columns < N)
+  for (int e = tid; e < kDStages * kDJ * ld; e += blockDim.x) As[e] = 0.0;
+  __syncthreads();
+
+  const int t0 = warp * tpw;
+  const int t1 = min(ntiles, t0 + tpw);
+  double acc[kDT][4];
+#pragma unroll
+  for (int q = 0; q < kDT; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0; }
+
+  // (mi, ni) of the tiles this warp owns, packed in registers (-1 = none)
+  int tinfo[kDT];
+#pragma unroll
+  for (int q = 0; q < kDT; ++q) {
+    const int tt = t0 + q;
+    tinfo[q] = (tt < t1) ? ((int)tmi[tt] | ((int)tni[tt] << 8)) : -1;
+  }
+
+  const int bcol = 8 * (nt - 1);      // the rhs lives in column bcol of the staged rows
+  const int nchunk = (P + kDJ - 1) / kDJ;
+  auto stage_load = [&](int chunk, int st) {
+    double* dst = As + (size_t)st * kDJ * ld;
+    const int j0 = chunk * kDJ;
+    for (int e = tid; e < kDJ * N; e += blockDim.x) {
+      int jj = e / N, c = e - jj * N;
+      int j = j0 + jj;
+      if (j < P) cp_async8(dst + jj * ld + c, A + (int64_t)j * N + c);
+      else dst[jj * ld + c] = 0.0;
+    }
+    if (tid < kDJ) {
+      int j = j0 + tid;
+      double w = 0.0, b = 0.0;
+      if (j < P) load_wb(value, error, weight, (int64_t)r * P + j, w, b);
+      sw[st * kDJ + tid] = w;
+      dst[tid * ld + bcol] = b;
+    }
+    cp_async_commit();
+  };
+
+  stage_load(0, 0);
+  for (int ch = 0; ch < nchunk; ++ch) {
+    const int st = ch & 1;
+    if (ch + 1 < nchunk) { stage_load(ch + 1, st ^ 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();
+    const double* S = As + (size_t)st * kDJ * ld;
+    const double* W = sw + st * kDJ;
+#pragma unroll 2
+    for (int ks = 0; ks < kDJ / 4; ++ks) {
+      const int jj = 4 * ks + t;
+      const double w = W[jj];
+      const double* row = S + jj * ld;
+      int cur_mi = -1;
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int q = 0; q < kDT; ++q) {
+        if (tinfo[q] >= 0) {
+          const int mi = tinfo[q] & 255, ni = tinfo[q] >> 8;
+          if (mi != cur_mi) {
+            cur_mi = mi;
+            a0 = row[16 * mi + g] * w;
+            a1 = row[16 * mi + g + 8] * w;
+          }
+          const double b0 = row[8 * ni + g];
+          dmma_16x8x4(acc[q], a0, a1, b0);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // epilogue: c0 (g, 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1)
+#pragma unroll
+  for (int q = 0; q < kDT; ++q) {
+    if (tinfo[q] < 0) continue;
+    const int mi = tinfo[q] & 255, ni = tinfo[q] >> 8;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int i = 16 * mi + g + ((v & 2) ? 8 : 0);
+      const int k = 8 * ni + 2 * t + (v & 1);
+      if (i >= N) continue;
+      const double val = acc[q][v];
+      if (ni == nt - 1) {
+        if (k == bcol) y[(int64_t)r * N + i] = val;
+      } else if (k <= i) {
+        G[((int64_t)r * N + i) * N + k] = val;
+        if (k != i) G[((int64_t)r * N + k) * N + i] = val;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int vi_normal_eq_batched(const double* A, const double* value, const double* error, const double* weight,
+                                    int32_t R, int32_t P, int32_t N, int32_t mode, double* G, double* y,
+                                    double* sWbb, int32_t* npts, double* Wm, double* bm, void* stream) {
+  VI_REQUIRE(A && value && (error || weight) && G && y, "NULL argument");
+  VI_REQUIRE(R >= 0 && P >= 1 && N >= 1, "bad shape R=%d P=%d N=%d", R, P, N);
+  if (R == 0) return VI_OK;
+  cudaStream_t s = vi_stream(stream);
+  if (sWbb || npts || Wm || bm) {
+    k_prep<<<R, 256, 0, s>>>(value, error, weight, P, sWbb, npts, Wm, bm);
+    VI_LAUNCH_CHECK();
+  }
+  if (mode == VI_NE_STRICT) {
+    int nsb = (N + kSB - 1) / kSB;
+    size_t smem = (size_t)(2 * kSJ * kSB + 2 * kSJ) * sizeof(double);
+    VI_CUDA(cudaFuncSetAttribute(k_ne_strict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_ne_strict<<<(unsigned)(R * nsb * nsb), 256, smem, s>>>(A, value, error, weight, P, N, nsb, G, y);
+    VI_LAUNCH_CHECK();
+    return VI_OK;
+  }
+  if (mode != VI_NE_FAST) { vi_set_error("unknown normal-equation mode %d", mode); return VI_EINVAL; }
+  const int mt = (N + 15) / 16;
+  const int nt = (N + 7) / 8 + 1;             // + rhs column tile
+  int ntiles = 0;
+  for (int mi = 0; mi < mt; ++mi) {
+    for (int ni = 0; ni < nt - 1; ++ni)
+      if (8 * ni <= 16 * mi + 15 && 8 * ni < N) ++ntiles;
+    ++ntiles;
+  }
+  if (ntiles > kDW * kDT || ntiles > 255) {
+    vi_set_error("VI_NE_FAST supports nbasis <= %d (got %d): use VI_NE_STRICT", VI_NMAX_SMEM, N);
+    return VI_EUNSUPPORTED;
+  }
+  const int cols = (16 * mt > 8 * nt) ? 16 * mt : 8 * nt;
+  const int ld = dmma_ld(cols);
+  const int tpw = (ntiles + kDW - 1) / kDW;
+  size_t smem = ((size_t)kDStages * kDJ * ld + kDStages * kDJ) * sizeof(double) + 512;
+  VI_CUDA(cudaFuncSetAttribute(k_ne_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_ne_dmma<<<(unsigned)R, kDW * 32, smem, s>>>(A, value, error, weight, P, N, mt, nt, ld, ntiles, tpw, G, y);
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}

@@ -1,0 +1,200 @@
+// Symmetric tridiagonal eigen-solve by implicit-shift QL with a ROTATION TAPE.
+//
+// Role on the hot path (kernel K3b): the reference solves
+// (A^T W A + lambda*R) C = A^T W d with scipy.linalg.lstsq == LAPACK gelsd with
+// rcond = eps (interpolate.py:462), i.e. the minimum-norm solution over the
+// singular values s_i > eps*s_max.  For the (symmetrised) matrix that is
+//   C = sum_{|l_i| > eps*max|l|}  v_i (v_i . y) / l_i .
+// The CTA kernel reduces X to tridiagonal T = Q^T X Q; this routine (one THREAD
+// per system, thousands of systems in flight) diagonalises T = Z L Z^T without
+// ever forming Z: every Givens rotation is applied on the fly to g = Z^T y'
+// and appended to a tape; Z*u is obtained afterwards by replaying the tape
+// backwards.  Cost O(n^2) per system instead of O(n^3).
+//
+// Like LAPACK dsteqr, each unreduced block is processed from its smaller-|d| end
+// (on the graded matrices this path produces, deflating from the large end
+// loses the small eigenvalues and changes the numerical rank — see DESIGN.md).
+//
+// VI_HD: compiled for the device in fit.cu and for the CPU in the test-only
+// harness (tests/cpu_harness.cpp) where it is checked against LAPACK.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifndef VI_HD
+#if defined(__CUDACC__)
+#define VI_HD __host__ __device__ __forceinline__
+#else
+#define VI_HD inline
+#endif
+#endif
+
+#define VI_EPS_HALF 1.1102230246251565e-16   // 2^-53 (LAPACK dlamch('E'))
+#define VI_EPS 2.220446049250313e-16         // numpy finfo(float64).eps, scipy lstsq rcond
+#define VI_SAFMIN 2.2250738585072014e-308
+
+// Strided view: element i of the vector owned by one thread lives at p[i*stride].
+// stride = 32 gives the warp-interleaved layout used on the GPU (coalesced when the
+// lanes of a warp index the same i); stride = 1 on the CPU.
+struct vi_svec {
+  double* p;
+  int64_t stride;
+  VI_HD double& operator[](int64_t i) const { return p[i * stride]; }
+};
+struct vi_sidx {
+  int32_t* p;
+  int64_t stride;
+  VI_HD int32_t& operator[](int64_t i) const { return p[i * stride]; }
+};
+
+struct vi_tape {
+  vi_svec c, s;     // rotation cosine / sine
+  vi_sidx ix;       // (physical index of logical i) * 2 + (1 if partner is index-1 else 0)
+  int32_t cap;      // capacity in rotations
+};
+
+VI_HD double vi_sign(double a, double b) { return b >= 0.0 ? fabs(a) : -fabs(a); }
+
+// status: 0 ok, 1 iteration limit, 2 tape overflow
+VI_HD int vi_tql(int n, vi_svec d, vi_svec e, vi_svec g, vi_tape tape, int32_t* nrot_out) {
+  int32_t nrot = 0;
+  int status = 0;
+  int budget = 30 * n;                     // LAPACK's nmaxit
+  int l1 = 0;
+  while (l1 < n) {
+    // ---- delimit the next unreduced block [l1, m] ----
+    int m = l1;
+    while (m < n - 1) {
+      double tst = fabs(e[m]);
+      if (tst == 0.0) break;
+      if (tst <= (sqrt(fabs(d[m])) * sqrt(fabs(d[m + 1]))) * VI_EPS_HALF) { e[m] = 0.0; break; }
+      ++m;
+    }
+    const int lo = l1, hi = m;
+    l1 = m + 1;
+    const int nb = hi - lo + 1;
+    if (nb == 1) continue;
+    // ---- exact power-of-two scaling of the block ----
+    double anorm = 0.0;
+    for (int i = lo; i <= hi; ++i) {
+      anorm = fmax(anorm, fabs(d[i]));
+      if (i < hi) anorm = fmax(anorm, fabs(e[i]));
+    }
+    if (anorm == 0.0) continue;
+    int ex;
+    frexp(anorm, &ex);
+    const double scl = ldexp(1.0, -ex), uns = ldexp(1.0, ex);
+    for (int i = lo; i <= hi; ++i) {
+      d[i] = d[i] * scl;
+      if (i < hi) e[i] = e[i] * scl;
+    }
+    // ---- logical view: QL deflates at logical index 0, which must be the small end ----
+    const bool rev = fabs(d[hi]) < fabs(d[lo]);
+#define PD(i) (rev ? (hi - (i)) : (lo + (i)))
+#define PE(i) (rev ? (hi - (i)-1) : (lo + (i)))
+    for (int l = 0; l < nb; ++l) {
+      for (;;) {
+        int mm = l;
+        while (mm < nb - 1) {
+          double ev = e[PE(mm)];
+          double tst = ev * ev;
+          if (tst <= (VI_EPS_HALF * VI_EPS_HALF * fabs(d[PD(mm)])) * fabs(d[PD(mm + 1)]) + VI_SAFMIN) break;
+          ++mm;
+        }
+        if (mm < nb - 1) e[PE(mm)] = 0.0;
+        if (mm == l) break;
+        if (budget-- <= 0) { status = 1; goto done_block; }
+        // Wilkinson shift from the leading 2x2 of the active block
+        double el = e[PE(l)];
+        double gg = (d[PD(l + 1)] - d[PD(l)]) / (2.0 * el);
+        double r = hypot(gg, 1.0);
+        gg = d[PD(mm)] - d[PD(l)] + el / (gg + vi_sign(r, gg));
+        double s = 1.0, c = 1.0, p = 0.0;
+        int i = mm - 1;
+        bool early = false;
+        for (; i >= l; --i) {
+          double ei = e[PE(i)];
+          double f = s * ei, b = c * ei;
+          r = hypot(f, gg);
+          if (i + 1 < nb - 1) e[PE(i + 1)] = r;
+          if (r == 0.0) {
+            d[PD(i + 1)] -= p;
+            if (mm < nb - 1) e[PE(mm)] = 0.0;
+            early = true;
+            break;
+          }
+          s = f / r;
+          c = gg / r;
+          gg = d[PD(i + 1)] - p;
+          r = (d[PD(i)] - gg) * s + 2.0 * c * b;
+          p = s * r;
+          d[PD(i + 1)] = gg + p;
+          gg = c * r - b;
+          // apply to g (row vector times rotation in the logical plane (i, i+1))
+          const int pi = PD(i), pj = PD(i + 1);
+          double gi = g[pi], gj = g[pj];
+          g[pj] = s * gi + c * gj;
+          g[pi] = c * gi - s * gj;
+          if (nrot < tape.cap) {
+            tape.c[nrot] = c;
+            tape.s[nrot] = s;
+            tape.ix[nrot] = pi * 2 + (rev ? 1 : 0);
+          } else {
+            status = 2;
+          }
+          ++nrot;
+        }
+        if (early) continue;
+        d[PD(l)] -= p;
+        e[PE(l)] = gg;
+        if (mm < nb - 1) e[PE(mm)] = 0.0;
+      }
+    }
+  done_block:
+#undef PD
+#undef PE
+    for (int i = lo; i <= hi; ++i) d[i] = d[i] * uns;
+    if (status == 1) break;
+  }
+  *nrot_out = nrot;
+  return status;
+}
+
+// w <- Z w  (replay the tape backwards).
+VI_HD void vi_tape_apply_z(vi_svec w, vi_tape tape, int32_t nrot) {
+  for (int32_t t = nrot - 1; t >= 0; --t) {
+    int32_t code = tape.ix[t];
+    int pi = code >> 1;
+    int pj = (code & 1) ? pi - 1 : pi + 1;
+    double c = tape.c[t], s = tape.s[t];
+    double a = w[pi], b = w[pj];
+    w[pi] = c * a + s * b;
+    w[pj] = c * b - s * a;
+  }
+}
+
+// g <- Z^T g  (replay the tape forwards).
+VI_HD void vi_tape_apply_zt(vi_svec g, vi_tape tape, int32_t nrot) {
+  for (int32_t t = 0; t < nrot; ++t) {
+    int32_t code = tape.ix[t];
+    int pi = code >> 1;
+    int pj = (code & 1) ? pi - 1 : pi + 1;
+    double c = tape.c[t], s = tape.s[t];
+    double gi = g[pi], gj = g[pj];
+    g[pj] = s * gi + c * gj;
+    g[pi] = c * gi - s * gj;
+  }
+}
+
+// u_i = g_i / l_i over |l_i| > rcond * max|l|, else 0 (gelsd / pinv cut-off).  Returns rank.
+VI_HD int vi_spectral_divide(int n, vi_svec lam, vi_svec g, double rcond) {
+  double lmax = 0.0;
+  for (int i = 0; i < n; ++i) lmax = fmax(lmax, fabs(lam[i]));
+  const double cut = rcond * lmax;
+  int rank = 0;
+  for (int i = 0; i < n; ++i) {
+    if (fabs(lam[i]) > cut) { g[i] = g[i] / lam[i]; ++rank; }
+    else g[i] = 0.0;
+  }
+  return rank;
+}

@@ -90,9 +90,10 @@ def true_coeffs(nbasis, maxl=None, seed=1, n_terms=5, scale=1e11):
 
 
 def make_records(A, nrecords, seed=2, c_true=None, bad_frac=0.10, drift=0.05,
-                 maxl=None):
+                 maxl=None, noise_scale=1.0):
     """Records generated from the model itself: d = A c + sigma N(0,1) with
-    sigma = clip(0.05|d| + 2e10, 1.1e10, 9e12) (inside the default ERRLIM).
+    sigma = clip(0.05|d| + 2e10, 1.1e10, 9e12) (inside the default ERRLIM); the
+    noise actually added is noise_scale*sigma.
 
     A: (P, N) design matrix at the P valid (non-NaN-altitude) points.
     Returns value, error (nrecords, P) with ~bad_frac of the gates set to NaN
@@ -109,7 +110,7 @@ def make_records(A, nrecords, seed=2, c_true=None, bad_frac=0.10, drift=0.05,
         c = c_true * (1.0 + drift * rng.standard_normal(N))
         d0 = A @ c
         sigma = np.clip(0.05 * np.abs(d0) + 2e10, 1.1e10, 9e12)
-        d = d0 + sigma * rng.standard_normal(P)
+        d = d0 + noise_scale * sigma * rng.standard_normal(P)
         bad = rng.uniform(size=P) < bad_frac
         d[bad] = np.nan
         sigma[bad] = np.nan
