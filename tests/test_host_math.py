@@ -1,0 +1,202 @@
+"""Device-agnostic scalar code of volumetricinterp_b200/csrc (vi_math.h, vi_tridiag.h, vi_tql.h,
+vi_brent.h) compiled for the CPU by the TEST-ONLY harness and checked against the golden vectors,
+scipy and LAPACK.  The product never loads this harness; it has no CPU path."""
+import ctypes as C
+import io
+
+import numpy as np
+import pytest
+import scipy.linalg
+import scipy.optimize
+
+from conftest import dptr, load_golden, product_model
+import ref_port as rp
+
+EPS = np.finfo(float).eps
+
+
+def _rel(a, b):
+    scale = np.maximum(np.abs(b), 1e-12 * np.abs(b).max())
+    return np.max(np.abs(a - b) / scale)
+
+
+@pytest.mark.parametrize("name", ["lo8", "lo12", "mid27", "c1_144"])
+def test_sphharmlag_rows_match_reference_basis(harness, name):
+    g = load_golden(name)
+    m = product_model(g)
+    P = m.params()
+    assert harness.h_sizeof_shl_params() == C.sizeof(P)
+    n = g["lat"].size
+    A = np.zeros((n, m.nbasis))
+    harness.h_shl_rows(C.byref(P), dptr(g["lat"]), dptr(g["lon"]), dptr(g["alt"]), C.c_int64(n), dptr(A))
+    # column-relative tolerance: entries near a zero of P_v^m are compared against the column scale
+    for c in range(m.nbasis):
+        ref = g["A"][:, c]
+        tol = 2e-12 * max(np.abs(ref).max(), 1e-300)
+        assert np.max(np.abs(A[:, c] - ref)) <= tol, (c, np.max(np.abs(A[:, c] - ref)), np.abs(ref).max())
+
+
+def test_radbasfun_rows_match_reference_basis(harness):
+    g = load_golden("rbf27")
+    m = product_model(g)
+    n = g["lat"].size
+    A = np.zeros((n, m.nbasis))
+    harness.h_rbf_rows(dptr(g["lat"]), dptr(g["lon"]), dptr(g["alt"]), C.c_int64(n), dptr(m.centers),
+                       m.nbasis, C.c_double(m.eps), dptr(A))
+    assert np.allclose(A, g["A"], rtol=1e-12, atol=1e-300)
+
+
+def _system(harness, G, y, regs, lam, nt):
+    n = G.shape[0]
+    Cq = np.zeros(n)
+    rank, bad = C.c_int(0), C.c_int(0)
+    dd, ee = np.zeros(n), np.zeros(n)
+    regs = np.ascontiguousarray(regs)
+    lam = np.ascontiguousarray(lam, dtype=float)
+    st = harness.h_system_solve(n, dptr(G), dptr(y), dptr(regs), dptr(lam), len(lam), nt, C.c_double(EPS),
+                                dptr(Cq), C.byref(rank), dptr(dd), dptr(ee), C.byref(bad))
+    return st, bad.value, rank.value, Cq, dd, ee
+
+
+@pytest.mark.parametrize("name,nt", [("lo8", 8), ("lo8", 32), ("lo12", 48), ("lo12_two", 12)])
+def test_system_pipeline_matches_lstsq_low_order(harness, name, nt):
+    """tridiagonalise (CTA phases run thread by thread) + tape QL + truncated solve + back-transform
+    == scipy.linalg.lstsq (interpolate.py:462) on full-rank systems."""
+    g = load_golden(name)
+    for r in range(g["value"].shape[0]):
+        ok = np.isfinite(g["value"][r])
+        A, W, b = g["A"][ok], g["error"][r][ok] ** -2, g["value"][r][ok]
+        G, y = rp.normal_equations(A, W, b)
+        for alpha in (0.0, -12.0, -24.0, -30.0):
+            lam = np.zeros(len(g["regs"]))
+            lam[0] = 10.0 ** alpha
+            X = G + sum(l * R for l, R in zip(lam, g["regs"]))
+            ref = scipy.linalg.lstsq(X, y)[0]
+            st, bad, rank, Cq, dd, ee = _system(harness, np.ascontiguousarray(G), np.ascontiguousarray(y),
+                                                np.stack(g["regs"]), lam, nt)
+            assert st == 0 and bad == 0 and rank == G.shape[0]
+            # tridiagonal form has the same spectrum
+            T = np.diag(dd) + np.diag(ee[:-1], 1) + np.diag(ee[:-1], -1)
+            ev = np.linalg.eigvalsh(0.5 * (X + X.T))
+            scl = np.abs(ev).max() / np.abs(np.linalg.eigvalsh(T)).max()
+            assert np.allclose(np.linalg.eigvalsh(T) * scl, ev, rtol=0, atol=1e-13 * np.abs(ev).max())
+            cond = np.abs(ev).max() / np.abs(ev).min()
+            assert np.max(np.abs(Cq - ref)) <= 50 * EPS * cond * np.abs(ref).max()
+
+
+def test_system_pipeline_rank_deficient(harness):
+    """N = 144: numerical rank and fitted densities agree with lstsq where the solve is well posed."""
+    g = load_golden("c1_144")
+    ok = np.isfinite(g["value"][0])
+    A, W, b = g["A"][ok], g["error"][0][ok] ** -2, g["value"][0][ok]
+    G, y = rp.normal_equations(A, W, b)
+    for alpha in (0.0, -10.0):
+        X = G + 10.0 ** alpha * g["regs"][0]
+        ref = scipy.linalg.lstsq(X, y)[0]
+        s = np.linalg.svd(X, compute_uv=False)
+        st, bad, rank, Cq, _, _ = _system(harness, np.ascontiguousarray(G), np.ascontiguousarray(y),
+                                          np.stack(g["regs"]), [10.0 ** alpha], 576)
+        assert st == 0 and bad == 0
+        assert abs(rank - int((s > EPS * s[0]).sum())) <= 1
+        dens, dref = A @ Cq, A @ ref
+        assert np.max(np.abs(dens - dref)) <= 1e-5 * np.abs(dref).max()
+
+
+def test_nonfinite_system_is_flagged(harness):
+    G = np.eye(4)
+    G[1, 2] = np.inf
+    st, bad, *_ = _system(harness, G, np.ones(4), np.zeros((1, 4, 4)), [0.0], 4)
+    assert bad == 1
+
+
+def test_tql_against_lapack(harness):
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 3, 17, 64):
+        d = rng.standard_normal(n) * 10.0 ** rng.uniform(-8, 0, n)
+        e = rng.standard_normal(max(n - 1, 0)) * 10.0 ** rng.uniform(-8, 0, max(n - 1, 0))
+        g0 = rng.standard_normal(n)
+        T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+        w = np.zeros(n); lam = np.zeros(n)
+        rank, nrot = C.c_int(0), C.c_int(0)
+        st = harness.h_tql_solve(n, dptr(d), dptr(np.append(e, 0.0)), dptr(g0), C.c_double(EPS), dptr(w), dptr(lam),
+                                 C.byref(rank), C.byref(nrot))
+        assert st == 0
+        ev, V = np.linalg.eigh(T)
+        assert np.allclose(np.sort(lam), ev, rtol=0, atol=4 * EPS * np.abs(ev).max() * n)
+        keep = np.abs(ev) > EPS * np.abs(ev).max()
+        ref = V[:, keep] @ ((V[:, keep].T @ g0) / ev[keep])
+        assert rank.value == keep.sum()
+        cond = np.abs(ev).max() / np.abs(ev[keep]).min()
+        assert np.max(np.abs(w - ref)) <= 100 * EPS * cond * np.abs(ref).max()
+
+
+def test_brentq_state_machine_replays_scipy(harness):
+    """Same abscissae, same root as scipy.optimize.brentq (interpolate.py:214)."""
+    FN = C.CFUNCTYPE(C.c_double, C.c_double)
+    for f, a, b in [(lambda x: np.tanh(3 * (x + 24.3)) * 40 + 1.5, -25.0, -24.0),
+                    (lambda x: (x + 7.123456789) * (1 + (x + 7) ** 2), -8.0, -7.0),
+                    (lambda x: np.exp(x + 50.5) - 1.0, -51.0, -50.0)]:
+        xs_ref = []
+        def fr(x):
+            xs_ref.append(x)
+            return f(x)
+        root_ref = scipy.optimize.brentq(fr, a, b, disp=True)
+        xs = np.zeros(256)
+        root, nfev = C.c_double(0), C.c_int(0)
+        done = harness.h_brentq(FN(lambda x: float(f(x))), C.c_double(a), C.c_double(b), C.byref(root), dptr(xs),
+                                C.byref(nfev))
+        assert done == 1
+        assert root.value == root_ref
+        assert list(xs[:nfev.value]) == xs_ref
+    # a triple root does not converge within maxiter=100: scipy raises, the state machine says done == 2
+    f = lambda x: (x + 7.123456789) ** 3
+    with pytest.raises(RuntimeError):
+        scipy.optimize.brentq(f, -8.0, -7.0, disp=True)
+    xs = np.zeros(256)
+    root, nfev = C.c_double(0), C.c_int(0)
+    assert harness.h_brentq(FN(lambda x: float(f(x))), C.c_double(-8.0), C.c_double(-7.0), C.byref(root), dptr(xs),
+                            C.byref(nfev)) == 2
+
+
+def _walk_python(table, npts):
+    """interpolate.py:173-211 on a table of chi2(10^-k)."""
+    bracket = False
+    for sf in (0.6, 0.7, 0.8, 0.9, 1.0):
+        nu = npts * sf
+        k, val0, val = 0, 1.0, table[0] - nu
+        if val < 0:
+            return 1, -1, nu
+        while val0 * val > 0:
+            bracket = True
+            val0 = val
+            k += 1
+            val = table[k] - nu
+            if k > 100:
+                bracket = False
+                break
+        if bracket:
+            return 0, k, nu
+    return 2, -1, 0.0
+
+
+def test_bracket_walk(harness):
+    rng = np.random.default_rng(7)
+    for trial in range(200):
+        npts = int(rng.integers(50, 800))
+        kind = trial % 4
+        k0 = rng.integers(1, 100)
+        if kind == 0:      # monotone decrease through nu somewhere
+            table = npts * (1.5 - 1.0 / (1 + np.exp(-(np.arange(102) - k0))))
+        elif kind == 1:    # never below: no root
+            table = npts * (1.2 + rng.uniform(0, 1, 102))
+        elif kind == 2:    # too smooth at alpha = 0
+            table = npts * rng.uniform(0.1, 0.5, 102)
+        else:              # noisy
+            table = npts * rng.uniform(0.5, 1.6, 102)
+            table[0] = npts * 1.7
+        st, k, nu = C.c_int(0), C.c_int(0), C.c_double(0)
+        harness.h_chi2_bracket(dptr(np.ascontiguousarray(table)), npts, C.byref(st), C.byref(k), C.byref(nu))
+        est, ek, enu = _walk_python(table, npts)
+        assert (st.value, k.value) == (est, ek)
+        if est != 2:
+            assert nu.value == enu

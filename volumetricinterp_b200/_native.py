@@ -43,20 +43,36 @@ _i32, _i64, _dbl, _ptr = C.c_int32, C.c_int64, C.c_double, C.c_void_p
 
 # name -> argtypes; every function returns int status (0 ok).  Keep in sync with
 # include/volinterp_b200.h (tests/test_cabi.py checks every header symbol).
+_shl = C.POINTER(ShlParams)
 SIGNATURES = {
-    "vi_basis_sphharmlag": [_ptr, _ptr, _ptr, _i64, C.POINTER(ShlParams), _ptr, _ptr, _ptr],
+    "vi_basis_sphharmlag": [_ptr, _ptr, _ptr, _i64, _shl, _ptr, _ptr, _ptr],
     "vi_basis_radbasfun": [_ptr, _ptr, _ptr, _i64, _ptr, _i32, _dbl, _ptr, _ptr, _ptr],
-    "vi_normal_eq_batched": [_ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr],
-    "vi_fit_workspace_bytes": [_i32, _i32, _i32, _i32, C.POINTER(_i64)],
-    "vi_fit_batched": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _ptr, _i32, _i32,
-                       _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr],
-    "vi_solve_batched": [_ptr, _ptr, _ptr, _i32, _i32, _i32, _dbl, _ptr, _ptr, _ptr, _ptr, _i64, _ptr],
-    "vi_estimate_sphharmlag": [_ptr, _ptr, _ptr, _i64, C.POINTER(ShlParams), _ptr, _i32, _ptr, _i32, _ptr, _ptr],
+    "vi_normal_eq_batched": [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "vi_fit_workspace_bytes": [_i32, _i32, _i32, _i32, _i64, C.POINTER(_i64)],
+    "vi_solve_batched": [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _dbl, _ptr, _ptr, _ptr, _ptr, _i64, _ptr],
+    "vi_fit_batched": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _ptr, _i32, _i32,
+                       _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, C.POINTER(_i64), _ptr, _i64, _ptr],
+    "vi_estimate_sphharmlag": [_ptr, _ptr, _ptr, _i64, _shl, _ptr, _i32, _ptr, _i32, _ptr, _ptr],
     "vi_estimate_radbasfun": [_ptr, _ptr, _ptr, _i64, _ptr, _i32, _dbl, _ptr, _i32, _ptr, _i32, _ptr, _ptr],
-    "vi_fit_host": [_ptr, _ptr, _ptr, _i32, _i32, _i32, _ptr, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
-    "vi_estimate_sphharmlag_host": [_ptr, _ptr, _ptr, _i64, C.POINTER(ShlParams), _ptr, _i32, _ptr, _i32, _ptr],
-    "vi_fp64_peak_probe": [_i32, _i32, _ptr, _ptr],
+    "vi_fit_host": [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _ptr, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "vi_estimate_sphharmlag_host": [_ptr, _ptr, _ptr, _i64, _shl, _ptr, _i32, _ptr, _i32, _ptr],
+    "vi_fp64_peak_probe": [_i32, _i32, C.POINTER(_dbl), _ptr],
+    "vi_profile_enable": [_i32],
+    "vi_profile_reset": [],
+    "vi_profile_read": [_ptr, _ptr, _i32],
 }
+PROFILE_KINDS = ("basis", "normal_eq", "tridiag", "tql", "chi2", "covariance", "estimate", "misc")
+
+
+def profile_read():
+    """-> ({kind: device ms}, {kind: launches}) since the last vi_profile_reset."""
+    n = len(PROFILE_KINDS)
+    ms = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    check(lib().vi_profile_read(ms, cnt, n))
+    return dict(zip(PROFILE_KINDS, list(ms))), dict(zip(PROFILE_KINDS, list(cnt)))
+NE_STRICT, NE_FAST = 0, 1
+METHOD_NONE, METHOD_CHI2 = 0, 1
 
 
 def lib():

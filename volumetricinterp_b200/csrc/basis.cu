@@ -178,7 +178,7 @@ extern "C" int vi_basis_sphharmlag(const double* lat, const double* lon, const d
   VI_REQUIRE(npts >= 0, "npts < 0");
   if (npts == 0) return VI_OK;
   unsigned grid = (unsigned)((npts + kThreads - 1) / kThreads);
-  k_basis_shl<<<grid, kThreads, 0, vi_stream(stream)>>>(lat, lon, alt, npts, *params, A, At);
+  VI_KERNEL(VI_K_BASIS, vi_stream(stream), k_basis_shl<<<grid, kThreads, 0, vi_stream(stream)>>>(lat, lon, alt, npts, *params, A, At));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
@@ -188,7 +188,7 @@ extern "C" int vi_basis_radbasfun(const double* lat, const double* lon, const do
   VI_REQUIRE(npts >= 0 && N >= 1 && centers != nullptr, "bad arguments");
   if (npts == 0) return VI_OK;
   unsigned grid = (unsigned)((npts + kThreads - 1) / kThreads);
-  k_basis_rbf<<<grid, kThreads, 0, vi_stream(stream)>>>(lat, lon, alt, npts, centers, N, eps, A, At);
+  VI_KERNEL(VI_K_BASIS, vi_stream(stream), k_basis_rbf<<<grid, kThreads, 0, vi_stream(stream)>>>(lat, lon, alt, npts, centers, N, eps, A, At));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
@@ -205,12 +205,12 @@ extern "C" int vi_estimate_sphharmlag(const double* lat, const double* lon, cons
   cudaStream_t s = vi_stream(stream);
   size_t smem = (size_t)N * kThreads * sizeof(double);
   if (Rsel == 1) {
-    k_est_shl_reg<1><<<grid, kThreads, 0, s>>>(lat, lon, alt, npts, *params, C, Rsel, hull_eq, F, out);
+    VI_KERNEL(VI_K_ESTIMATE, s, k_est_shl_reg<1><<<grid, kThreads, 0, s>>>(lat, lon, alt, npts, *params, C, Rsel, hull_eq, F, out));
   } else if (Rsel <= 8 || smem > 220 * 1024) {
-    k_est_shl_reg<8><<<grid, kThreads, 0, s>>>(lat, lon, alt, npts, *params, C, Rsel, hull_eq, F, out);
+    VI_KERNEL(VI_K_ESTIMATE, s, k_est_shl_reg<8><<<grid, kThreads, 0, s>>>(lat, lon, alt, npts, *params, C, Rsel, hull_eq, F, out));
   } else {
     VI_CUDA(cudaFuncSetAttribute(k_est_shl_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_est_shl_tile<<<grid, kThreads, smem, s>>>(lat, lon, alt, npts, *params, C, Rsel, hull_eq, F, out);
+    VI_KERNEL(VI_K_ESTIMATE, s, k_est_shl_tile<<<grid, kThreads, smem, s>>>(lat, lon, alt, npts, *params, C, Rsel, hull_eq, F, out));
   }
   VI_LAUNCH_CHECK();
   return VI_OK;
@@ -225,9 +225,9 @@ extern "C" int vi_estimate_radbasfun(const double* lat, const double* lon, const
   unsigned grid = (unsigned)((npts + kThreads - 1) / kThreads);
   cudaStream_t s = vi_stream(stream);
   if (Rsel == 1)
-    k_est_rbf<1><<<grid, kThreads, 0, s>>>(lat, lon, alt, npts, centers, N, eps, C, Rsel, hull_eq, F, out);
+    VI_KERNEL(VI_K_ESTIMATE, s, k_est_rbf<1><<<grid, kThreads, 0, s>>>(lat, lon, alt, npts, centers, N, eps, C, Rsel, hull_eq, F, out));
   else
-    k_est_rbf<8><<<grid, kThreads, 0, s>>>(lat, lon, alt, npts, centers, N, eps, C, Rsel, hull_eq, F, out);
+    VI_KERNEL(VI_K_ESTIMATE, s, k_est_rbf<8><<<grid, kThreads, 0, s>>>(lat, lon, alt, npts, centers, N, eps, C, Rsel, hull_eq, F, out));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }

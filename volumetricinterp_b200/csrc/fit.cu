@@ -447,9 +447,9 @@ int run_systems(int64_t cnt, const double* G, const double* y, const double* reg
                 double* Cout, int32_t* rank_out, cudaStream_t s) {
   if (cnt <= 0) return VI_OK;
   VI_CUDA(cudaFuncSetAttribute(k_tridiag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
-  k_tridiag<<<(unsigned)cnt, B.nt, B.smem, s>>>(G, y, regs, B);
+  VI_KERNEL(VI_K_TRIDIAG, s, k_tridiag<<<(unsigned)cnt, B.nt, B.smem, s>>>(G, y, regs, B));
   VI_LAUNCH_CHECK();
-  k_tql<<<blocks(cnt, 64), 64, 0, s>>>(cnt, B, rcond, Cout, rank_out);
+  VI_KERNEL(VI_K_TQL, s, k_tql<<<blocks(cnt, 64), 64, 0, s>>>(cnt, B, rcond, Cout, rank_out));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
@@ -459,7 +459,7 @@ int run_chi2(int64_t cnt, const double* At, const double* Wm, const double* bm, 
   if (cnt <= 0) return VI_OK;
   size_t smem = ((size_t)B.n * kChiSB + (kChiThreads / 32) * kChiSB) * sizeof(double);
   VI_CUDA(cudaFuncSetAttribute(k_chi2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_chi2<<<blocks(cnt, kChiSB), kChiThreads, smem, s>>>(At, Wm, bm, P, B.n, cnt, B.rec, B.st, Csys, chi2);
+  VI_KERNEL(VI_K_CHI2, s, k_chi2<<<blocks(cnt, kChiSB), kChiThreads, smem, s>>>(At, Wm, bm, P, B.n, cnt, B.rec, B.st, Csys, chi2));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }
@@ -512,10 +512,10 @@ extern "C" int vi_solve_batched(const double* G, const double* y, const int32_t*
   sysbuf_carve(b, B, cap, N, nreg);
   for (int64_t s0 = 0; s0 < S; s0 += cap) {
     int64_t cnt = (S - s0 < cap) ? S - s0 : cap;
-    k_setup_solve<<<blocks(cap, 256), 256, 0, st>>>(s0, cnt, nreg, rec, lam, B);
+    VI_KERNEL(VI_K_MISC, st, k_setup_solve<<<blocks(cap, 256), 256, 0, st>>>(s0, cnt, nreg, rec, lam, B));
     VI_LAUNCH_CHECK();
     if (int rc = run_systems(cnt, G, y, regmats, B, rcond, C + s0 * N, B.rank, st)) return rc;
-    k_copy_status<<<blocks(cnt, 256), 256, 0, st>>>(cnt, B, rank + s0, status + s0);
+    VI_KERNEL(VI_K_MISC, st, k_copy_status<<<blocks(cnt, 256), 256, 0, st>>>(cnt, B, rank + s0, status + s0));
     VI_LAUNCH_CHECK();
   }
   return VI_OK;
@@ -560,29 +560,29 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
     const int64_t T = U * VI_NALPHA;
     for (int64_t t0 = 0; t0 < T; t0 += cap) {
       int64_t cnt = (T - t0 < cap) ? T - t0 : cap;
-      k_setup_table<<<blocks(cap, 256), 256, 0, st>>>(t0, cnt, nreg, npts, pow10tab, B);
+      VI_KERNEL(VI_K_MISC, st, k_setup_table<<<blocks(cap, 256), 256, 0, st>>>(t0, cnt, nreg, npts, pow10tab, B));
       VI_LAUNCH_CHECK();
       if (int rc = run_systems(cnt, G, y, regmats, B, rcond, B.Csys, B.rank, st)) return rc;
       if (int rc = run_chi2(cnt, At, Wm, bm, P, B, B.Csys, B.chi2, st)) return rc;
-      k_scatter_table<<<blocks(cnt, 256), 256, 0, st>>>(t0, cnt, B, Ub);
+      VI_KERNEL(VI_K_MISC, st, k_scatter_table<<<blocks(cnt, 256), 256, 0, st>>>(t0, cnt, B, Ub));
       VI_LAUNCH_CHECK();
       solved += cnt;
     }
     // ---- phase 2: bracket + Brent in lock step ------------------------------------------
-    k_bracket<<<blocks(U, 128), 128, 0, st>>>(U, nreg, npts, Ub);
+    VI_KERNEL(VI_K_MISC, st, k_bracket<<<blocks(U, 128), 128, 0, st>>>(U, nreg, npts, Ub));
     VI_LAUNCH_CHECK();
     for (int it = 0; it < VI_BRENT_MAXITER + 2; ++it) {
       VI_CUDA(cudaMemsetAsync(Ub.count, 0, sizeof(int32_t), st));
       int h_count_total = 0;
       for (int64_t u0 = 0; u0 < U; u0 += cap) {
         int64_t cnt = (U - u0 < cap) ? U - u0 : cap;
-        k_brent_propose<<<blocks(cap, 128), 128, 0, st>>>(u0, cnt, nreg, B, Ub);
+        VI_KERNEL(VI_K_MISC, st, k_brent_propose<<<blocks(cap, 128), 128, 0, st>>>(u0, cnt, nreg, B, Ub));
         VI_LAUNCH_CHECK();
         if (U > cap) {
           // several chunks: finish this chunk before its slots are reused
           if (int rc = run_systems(cnt, G, y, regmats, B, rcond, B.Csys, B.rank, st)) return rc;
           if (int rc = run_chi2(cnt, At, Wm, bm, P, B, B.Csys, B.chi2, st)) return rc;
-          k_brent_feed<<<blocks(cnt, 128), 128, 0, st>>>(u0, cnt, B, Ub);
+          VI_KERNEL(VI_K_MISC, st, k_brent_feed<<<blocks(cnt, 128), 128, 0, st>>>(u0, cnt, B, Ub));
           VI_LAUNCH_CHECK();
         }
       }
@@ -595,7 +595,7 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
       if (U <= cap) {
         if (int rc = run_systems(U, G, y, regmats, B, rcond, B.Csys, B.rank, st)) return rc;
         if (int rc = run_chi2(U, At, Wm, bm, P, B, B.Csys, B.chi2, st)) return rc;
-        k_brent_feed<<<blocks(U, 128), 128, 0, st>>>(0, U, B, Ub);
+        VI_KERNEL(VI_K_MISC, st, k_brent_feed<<<blocks(U, 128), 128, 0, st>>>(0, U, B, Ub));
         VI_LAUNCH_CHECK();
       }
     }
@@ -603,11 +603,11 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
   // ---- phase 3: final solve with the found parameters (interpolate.py:566-569) -----------
   for (int64_t r0 = 0; r0 < R; r0 += cap) {
     int64_t cnt = (R - r0 < cap) ? R - r0 : cap;
-    k_setup_final<<<blocks(cap, 128), 128, 0, st>>>(r0, cnt, nreg, method, npts, B, Ub, lam, status);
+    VI_KERNEL(VI_K_MISC, st, k_setup_final<<<blocks(cap, 128), 128, 0, st>>>(r0, cnt, nreg, method, npts, B, Ub, lam, status));
     VI_LAUNCH_CHECK();
     if (int rc = run_systems(cnt, G, y, regmats, B, rcond, C + r0 * N, B.rank, st)) return rc;
     if (int rc = run_chi2(cnt, At, Wm, bm, P, B, C + r0 * N, B.chi2, st)) return rc;
-    k_finalize<<<(unsigned)cnt, 64, 0, st>>>(r0, cnt, N, B, C, chi2, rank, status);
+    VI_KERNEL(VI_K_MISC, st, k_finalize<<<(unsigned)cnt, 64, 0, st>>>(r0, cnt, N, B, C, chi2, rank, status));
     VI_LAUNCH_CHECK();
     solved += cnt;
   }
@@ -666,7 +666,7 @@ extern "C" int vi_fit_host(const double* A, const double* value, const double* e
   if (weight) VI_TRY(cudaMemcpyAsync(dwt, weight, RP * 8, cudaMemcpyHostToDevice, s));
   if (nreg > 0) VI_TRY(cudaMemcpyAsync(dreg, regmats, (size_t)nreg * NN * 8, cudaMemcpyHostToDevice, s));
   if (rc == VI_OK) {
-    k_transpose<<<blocks((int64_t)PN, 256), 256, 0, s>>>(dA, P, N, dAt);
+    VI_KERNEL(VI_K_MISC, s, k_transpose<<<blocks((int64_t)PN, 256), 256, 0, s>>>(dA, P, N, dAt));
     rc = vi_normal_eq_batched(dA, dval, derr, dwt, R, P, N, ne_mode, dG, dy, nullptr, dnp, dWm, dbm, s);
   }
   if (rc == VI_OK)

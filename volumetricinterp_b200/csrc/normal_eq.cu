@@ -300,14 +300,14 @@ extern "C" int vi_normal_eq_batched(const double* A, const double* value, const 
   if (R == 0) return VI_OK;
   cudaStream_t s = vi_stream(stream);
   if (sWbb || npts || Wm || bm) {
-    k_prep<<<R, 256, 0, s>>>(value, error, weight, P, sWbb, npts, Wm, bm);
+    VI_KERNEL(VI_K_NORMAL_EQ, s, k_prep<<<R, 256, 0, s>>>(value, error, weight, P, sWbb, npts, Wm, bm));
     VI_LAUNCH_CHECK();
   }
   if (mode == VI_NE_STRICT) {
     int nsb = (N + kSB - 1) / kSB;
     size_t smem = (size_t)(2 * kSJ * kSB + 2 * kSJ) * sizeof(double);
     VI_CUDA(cudaFuncSetAttribute(k_ne_strict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_ne_strict<<<(unsigned)(R * nsb * nsb), 256, smem, s>>>(A, value, error, weight, P, N, nsb, G, y);
+    VI_KERNEL(VI_K_NORMAL_EQ, s, k_ne_strict<<<(unsigned)(R * nsb * nsb), 256, smem, s>>>(A, value, error, weight, P, N, nsb, G, y));
     VI_LAUNCH_CHECK();
     return VI_OK;
   }
@@ -329,7 +329,7 @@ extern "C" int vi_normal_eq_batched(const double* A, const double* value, const 
   const int tpw = (ntiles + kDW - 1) / kDW;
   size_t smem = ((size_t)kDStages * kDJ * ld + kDStages * kDJ) * sizeof(double) + 512;
   VI_CUDA(cudaFuncSetAttribute(k_ne_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_ne_dmma<<<(unsigned)R, kDW * 32, smem, s>>>(A, value, error, weight, P, N, mt, nt, ld, ntiles, tpw, G, y);
+  VI_KERNEL(VI_K_NORMAL_EQ, s, k_ne_dmma<<<(unsigned)R, kDW * 32, smem, s>>>(A, value, error, weight, P, N, mt, nt, ld, ntiles, tpw, G, y));
   VI_LAUNCH_CHECK();
   return VI_OK;
 }

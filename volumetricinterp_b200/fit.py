@@ -1,0 +1,137 @@
+"""Device driver of the fit hot path: records in, coefficients out.
+
+Python stays a thin host layer (device memory through torch, kernels through the
+C ABI in _native.py).  One call fits all R records of a file:
+
+    K1  design matrix A (P x N) and its transpose, once per file      (vi_basis_*)
+    K2  masked weights + normal equations for a batch of records      (vi_normal_eq_batched)
+    K3  chi^2 = nu search, final solve, chi^2                         (vi_fit_batched)
+
+which replaces the reference's record loop, interpolate.py:511-574.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _native
+
+METHODS = {None: _native.METHOD_CHI2, 'chi2': _native.METHOD_CHI2}
+
+
+@dataclass
+class FitResult:
+    Coeffs: object        # (R, N)
+    Covariance: object    # (R, N, N) or None
+    chi_sq: object        # (R,)
+    reg_params: object    # (R, nreg)
+    rank: object          # (R,) int32
+    status: object        # (R,) int32, _native.ST_*
+    nsolve: int = 0       # eigen-systems solved
+
+
+def _cuda_stream(device):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def normal_equations_device(A, value, error, weight=None, mode=_native.NE_FAST, want_masked=True):
+    """A (P,N), value/error (R,P) CUDA float64 tensors -> G (R,N,N), y (R,N), sWbb (R), npts (R), Wm, bm."""
+    import torch
+    R, P = value.shape
+    N = A.shape[1]
+    dev = A.device
+    G = torch.empty((R, N, N), dtype=torch.float64, device=dev)
+    y = torch.empty((R, N), dtype=torch.float64, device=dev)
+    sw = torch.empty((R,), dtype=torch.float64, device=dev)
+    npts = torch.empty((R,), dtype=torch.int32, device=dev)
+    Wm = torch.empty((R, P), dtype=torch.float64, device=dev) if want_masked else None
+    bm = torch.empty((R, P), dtype=torch.float64, device=dev) if want_masked else None
+    _native.check(_native.lib().vi_normal_eq_batched(
+        A.data_ptr(), value.data_ptr(), error.data_ptr() if error is not None else None,
+        weight.data_ptr() if weight is not None else None, R, P, N, mode,
+        G.data_ptr(), y.data_ptr(), sw.data_ptr(), npts.data_ptr(),
+        Wm.data_ptr() if want_masked else None, bm.data_ptr() if want_masked else None, _cuda_stream(dev)))
+    return G, y, sw, npts, Wm, bm
+
+
+_ws_cache = {}
+
+
+def _workspace(dev, R, P, N, nreg, systems):
+    """Scratch for vi_fit_batched, cached per (device, shape) so repeated fits do not re-allocate."""
+    import torch
+    need = C.c_int64(0)
+    _native.check(_native.lib().vi_fit_workspace_bytes(R, P, N, nreg, systems, C.byref(need)))
+    key = str(dev)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < need.value:
+        _ws_cache.pop(key, None)
+        ws = torch.empty((need.value,), dtype=torch.uint8, device=dev)
+        _ws_cache[key] = ws
+    return ws
+
+
+def fit_batch_device(At, Wm, bm, G, y, npts, regs, method, systems=0, want_cov=False):
+    """vi_fit_batched on device tensors.  regs: (nreg,N,N) tensor or None."""
+    import torch
+    R, N = y.shape
+    P = At.shape[1]
+    dev = y.device
+    nreg = 0 if regs is None else regs.shape[0]
+    meth = _native.METHOD_NONE if nreg == 0 else method
+    Cf = torch.empty((R, N), dtype=torch.float64, device=dev)
+    dC = torch.empty((R, N, N), dtype=torch.float64, device=dev) if want_cov else None
+    chi2 = torch.empty((R,), dtype=torch.float64, device=dev)
+    lam = torch.zeros((R, max(nreg, 1)), dtype=torch.float64, device=dev)
+    rank = torch.zeros((R,), dtype=torch.int32, device=dev)
+    status = torch.zeros((R,), dtype=torch.int32, device=dev)
+    ws = _workspace(dev, R, P, N, nreg, systems)
+    nsolve = C.c_int64(0)
+    _native.check(_native.lib().vi_fit_batched(
+        At.data_ptr(), Wm.data_ptr(), bm.data_ptr(), G.data_ptr(), y.data_ptr(), npts.data_ptr(),
+        R, P, N, regs.data_ptr() if nreg else None, nreg, meth,
+        Cf.data_ptr(), dC.data_ptr() if want_cov else None, chi2.data_ptr(), lam.data_ptr(),
+        rank.data_ptr(), status.data_ptr(), C.byref(nsolve), ws.data_ptr(), ws.numel(), _cuda_stream(dev)))
+    return Cf, dC, chi2, lam[:, :nreg], rank, status, nsolve.value
+
+
+def fit_records(model, lat, lon, alt, value, error, reg_matrices=None, method='chi2',
+                ne_mode=_native.NE_FAST, weight=None, device=None, rec_batch=8192, systems=0,
+                want_cov=False, to_host=True):
+    """Fit every record (reference interpolate.py:511-579).
+
+    lat/lon/alt: (P,) NaN-altitude-filtered gate coordinates; value/error: (R,P) with NaN
+    marking invalid gates; reg_matrices: list of (N,N) arrays in REGULARIZATION_LIST order.
+    weight: optional (R,P) precomputed error**-2 (bit-exact parity with numpy's pow)."""
+    import torch
+    if method not in METHODS:
+        raise ValueError(f"REGULARIZATION_METHOD {method!r} is not available on the device path (chi2 only)")
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    f64 = lambda a: a.to(dev, torch.float64) if isinstance(a, torch.Tensor) else \
+        torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev, non_blocking=True)
+    la, lo, al = f64(np.ravel(lat)), f64(np.ravel(lon)), f64(np.ravel(alt))
+    P, N = la.numel(), model.nbasis
+    A = torch.empty((P, N), dtype=torch.float64, device=dev)
+    At = torch.empty((N, P), dtype=torch.float64, device=dev)
+    model.basis_device(la, lo, al, out=A, out_t=At)
+    regs = None
+    if reg_matrices is not None and len(reg_matrices) > 0:
+        regs = f64(np.stack([np.asarray(m, dtype=np.float64) for m in reg_matrices]))
+    R = value.shape[0]
+    outs = []
+    nsolve = 0
+    for r0 in range(0, R, rec_batch):
+        r1 = min(R, r0 + rec_batch)
+        v, e = f64(value[r0:r1]), f64(error[r0:r1])
+        w = f64(weight[r0:r1]) if weight is not None else None
+        G, y, _, npts, Wm, bm = normal_equations_device(A, v, e, w, ne_mode)
+        Cf, dC, chi2, lam, rank, status, ns = fit_batch_device(At, Wm, bm, G, y, npts, regs, METHODS[method],
+                                                                systems, want_cov)
+        nsolve += ns
+        outs.append((Cf, dC, chi2, lam, rank, status))
+    cat = lambda i: torch.cat([o[i] for o in outs]) if outs and outs[0][i] is not None else None
+    res = [cat(i) for i in range(6)]
+    if to_host:
+        res = [t.cpu().numpy() if t is not None else None for t in res]
+    return FitResult(*res, nsolve=nsolve)

@@ -83,12 +83,22 @@ class Model(object):
         row-major on the device; optionally also fills out_t (N, npts)."""
         import torch
         npts = lat.numel()
-        if out is None:
+        if out is None and out_t is None:
             out = torch.empty((npts, self.nbasis), dtype=torch.float64, device=lat.device)
         s = stream if stream is not None else torch.cuda.current_stream(lat.device).cuda_stream
         _native.check(_native.lib().vi_basis_sphharmlag(
             lat.data_ptr(), lon.data_ptr(), alt.data_ptr(), npts, C.byref(self.params()),
-            out.data_ptr(), out_t.data_ptr() if out_t is not None else None, s))
+            out.data_ptr() if out is not None else None, out_t.data_ptr() if out_t is not None else None, s))
+        return out
+
+    def estimate_device(self, lat, lon, alt, Cf, hull_eq, out, stream=None):
+        """out[r, p] = basis(p) . Cf[r], NaN outside the hull (estimate.py:113-121)."""
+        import torch
+        s = stream if stream is not None else torch.cuda.current_stream(lat.device).cuda_stream
+        F = 0 if hull_eq is None else hull_eq.shape[0]
+        _native.check(_native.lib().vi_estimate_sphharmlag(
+            lat.data_ptr(), lon.data_ptr(), alt.data_ptr(), lat.numel(), C.byref(self.params()),
+            Cf.data_ptr(), Cf.shape[0], hull_eq.data_ptr() if F else None, F, out.data_ptr(), s))
         return out
 
     def basis(self, gdlat, gdlon, gdalt):
