@@ -97,6 +97,7 @@ struct UnitBuf {      // one search unit = (record, regulariser)
   int32_t* status;    // U
   int32_t* active;    // U
   int32_t* tabbad;    // U
+  int32_t* kstar;     // U
   int32_t* count;     // 1
 };
 
@@ -107,6 +108,7 @@ void unit_carve(Bump& b, UnitBuf& Ub, int64_t U) {
   Ub.status = b.take<int32_t>(U);
   Ub.active = b.take<int32_t>(U);
   Ub.tabbad = b.take<int32_t>(U);
+  Ub.kstar = b.take<int32_t>(U);
   Ub.count = b.take<int32_t>(8);
 }
 
@@ -161,22 +163,12 @@ k_tridiag(const double* __restrict__ G, const double* __restrict__ y, const doub
   if (tid == 0) { B.scl[s] = S.sc[0]; B.st[s] = bad ? VI_ST_NONFINITE : VI_ST_OK; }
 }
 
-__global__ void __launch_bounds__(64)
-k_tql(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, int32_t* __restrict__ rank_out) {
-  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nsys) return;
-  const int st = B.st[s];
-  if (st == kSkip) return;
+// Common tail of the two QL kernels: d, e, g are this thread's strided vectors (shared or global).
+__device__ __forceinline__ void tql_system(int64_t s, const SysBuf& B, double rcond, vi_svec d, vi_svec e, vi_svec g,
+                                           double* __restrict__ Cs, int32_t* __restrict__ rank_out) {
   const int n = B.n;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
-  double* Cs = Cout + s * (int64_t)n;
-  if (st != VI_ST_OK) {
-    for (int i = 0; i < n; ++i) Cs[i] = nan;
-    rank_out[s] = 0;
-    return;
-  }
   const int64_t base = ileave(s, n);
-  vi_svec d{B.d + base, 32}, e{B.e + base, 32}, g{B.g + base, 32};
   const int64_t tb = ileave(s, B.tapecap);
   vi_tape tape{{B.tc + tb, 32}, {B.ts + tb, 32}, {B.tix + tb, 32}, B.tapecap};
   int32_t nrot = 0;
@@ -191,9 +183,58 @@ k_tql(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, int32_t* 
   vi_tape_apply_z(g, tape, nrot);
   const double scl = B.scl[s];
   for (int i = 0; i < n; ++i) g[i] = g[i] * scl;
-  vi_tri_backtransform(n, B.V + s * (int64_t)n * n, B.tau + base, 32, g.p, 32);
+  vi_tri_backtransform(n, B.V + s * (int64_t)n * n, B.tau + base, 32, g.p, g.stride);
   for (int i = 0; i < n; ++i) Cs[i] = g[i];
   rank_out[s] = rank;
+}
+
+// One THREAD per system.  The three working vectors (d, e, g: 3n doubles per thread) sit on the
+// critical dependency chain of every rotation, so they live in shared memory, laid out [i][thread]
+// (a lane always hits its own bank pair whatever i it is at: no conflicts beyond the 64-bit minimum).
+__global__ void k_tql_smem(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout,
+                           int32_t* __restrict__ rank_out) {
+  extern __shared__ __align__(16) double sm[];
+  const int T = blockDim.x, tid = threadIdx.x, n = B.n;
+  const int64_t s = (int64_t)blockIdx.x * T + tid;
+  if (s >= nsys) return;
+  const int st = B.st[s];
+  if (st == kSkip) return;
+  double* Cs = Cout + s * (int64_t)n;
+  if (st != VI_ST_OK) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int i = 0; i < n; ++i) Cs[i] = nan;
+    rank_out[s] = 0;
+    return;
+  }
+  vi_svec d{sm + tid, T}, e{sm + (size_t)n * T + tid, T}, g{sm + (size_t)2 * n * T + tid, T};
+  const int64_t base = ileave(s, n);
+  for (int i = 0; i < n; ++i) {
+    d[i] = B.d[base + (int64_t)i * 32];
+    e[i] = B.e[base + (int64_t)i * 32];
+    g[i] = B.g[base + (int64_t)i * 32];
+  }
+  tql_system(s, B, rcond, d, e, g, Cs, rank_out);
+}
+
+// Fallback for orders whose vectors do not fit shared memory: same algorithm on the global
+// (warp-interleaved) workspace.
+__global__ void __launch_bounds__(64)
+k_tql(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, int32_t* __restrict__ rank_out) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nsys) return;
+  const int st = B.st[s];
+  if (st == kSkip) return;
+  const int n = B.n;
+  double* Cs = Cout + s * (int64_t)n;
+  if (st != VI_ST_OK) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int i = 0; i < n; ++i) Cs[i] = nan;
+    rank_out[s] = 0;
+    return;
+  }
+  const int64_t base = ileave(s, n);
+  vi_svec d{B.d + base, 32}, e{B.e + base, 32}, g{B.g + base, 32};
+  tql_system(s, B, rcond, d, e, g, Cs, rank_out);
 }
 
 // chi2[s] = sum_j Wm[r][j] * (sum_n At[n][j] C_s[n] - bm[r][j])^2   (chi2objfunct, interpolate.py:258-259)
@@ -281,7 +322,7 @@ k_chi2(const double* __restrict__ At, const double* __restrict__ Wm, const doubl
 // ---- system set-up for the three phases ---------------------------------------------------
 // table phase: global system index t = u*VI_NALPHA + k, chunk covers [t0, t0 + cnt)
 __global__ void k_setup_table(int64_t t0, int64_t cnt, int nreg, const int32_t* __restrict__ npts,
-                              const double* __restrict__ pow10tab, SysBuf B) {
+                              const double* __restrict__ pow10tab, const int32_t* __restrict__ kstar, int32_t* count, SysBuf B) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= B.cap) return;
   if (s >= cnt) { B.rec[s] = kSkip; return; }
@@ -289,8 +330,53 @@ __global__ void k_setup_table(int64_t t0, int64_t cnt, int nreg, const int32_t* 
   int64_t u = t / VI_NALPHA;
   int k = (int)(t - u * VI_NALPHA);
   int r = (int)(u / nreg), q = (int)(u - (int64_t)r * nreg);
-  B.rec[s] = (npts[r] > 0) ? r : kSkip;
+  const bool use = (npts[r] > 0 && k <= kstar[u]);             // k > kstar: bit-identical to system kstar
+  B.rec[s] = use ? r : kSkip;
+  if (use) atomicAdd(count + 1, 1);
   for (int i = 0; i < nreg; ++i) B.lam[s * nreg + i] = (i == q) ? pow10tab[k] : 0.0;
+}
+
+// kstar[u] = smallest k for which fl(sym(G) + 10^-k R) == sym(G) in every entry (VI_NALPHA if none).
+// Rounding is monotone, so every k >= kstar gives the bit-identical system; the reference solves all
+// of them again and gets the same chi^2 (interpolate.py:193-203 walks alpha down to -101).
+__global__ void __launch_bounds__(256)
+k_kstar(int nreg, int n, const double* __restrict__ G, const double* __restrict__ regs,
+        const double* __restrict__ pow10tab, int32_t* __restrict__ kstar) {
+  __shared__ int sflag;
+  const int64_t u = blockIdx.x;
+  const int r = (int)(u / nreg), q = (int)(u - (int64_t)r * nreg);
+  const double* Gr = G + (int64_t)r * n * n;
+  const double* Rq = regs + (int64_t)q * n * n;
+  int lo = 0, hi = VI_NALPHA;       // invariant: systems with k >= hi are identical to G (hi = NALPHA: none known)
+  // bisection on the monotone predicate same(k)
+  while (lo < hi) {
+    const int k = (lo + hi) / 2;
+    const double l = pow10tab[k];
+    if (threadIdx.x == 0) sflag = 1;
+    __syncthreads();
+    int same = 1;
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+      int i = idx / n, c = idx - i * n;
+      double x = 0.5 * (Gr[(int64_t)i * n + c] + Gr[(int64_t)c * n + i]);
+      double x2 = fma(l, Rq[idx], x);      // same expression as vi_tri_load
+      if (x2 != x) same = 0;
+    }
+    if (!same) sflag = 0;
+    __syncthreads();
+    const int all = sflag;
+    __syncthreads();
+    if (all) hi = k; else lo = k + 1;
+  }
+  if (threadIdx.x == 0) kstar[u] = hi;
+}
+
+__global__ void k_fill_table(int64_t U, const int32_t* __restrict__ kstar, UnitBuf Ub) {
+  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  const int ks = kstar[u];
+  if (ks >= VI_NALPHA) return;
+  const double v = Ub.table[u * VI_NALPHA + ks];
+  for (int k = ks + 1; k < VI_NALPHA; ++k) Ub.table[u * VI_NALPHA + k] = v;
 }
 
 __global__ void k_scatter_table(int64_t t0, int64_t cnt, SysBuf B, UnitBuf Ub) {
@@ -449,8 +535,16 @@ int run_systems(int64_t cnt, const double* G, const double* y, const double* reg
   VI_CUDA(cudaFuncSetAttribute(k_tridiag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
   VI_KERNEL(VI_K_TRIDIAG, s, k_tridiag<<<(unsigned)cnt, B.nt, B.smem, s>>>(G, y, regs, B));
   VI_LAUNCH_CHECK();
-  VI_KERNEL(VI_K_TQL, s, k_tql<<<blocks(cnt, 64), 64, 0, s>>>(cnt, B, rcond, Cout, rank_out));
-  VI_LAUNCH_CHECK();
+  // threads per block for the shared-memory QL: as many as 3n doubles per thread allow (<= 64)
+  int T = (int)((227 * 1024) / ((size_t)3 * B.n * sizeof(double))) / 32 * 32;
+  if (T > 64) T = 64;
+  if (T >= 32) {
+    size_t smem = (size_t)3 * B.n * T * sizeof(double);
+    VI_CUDA(cudaFuncSetAttribute(k_tql_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VI_KERNEL(VI_K_TQL, s, k_tql_smem<<<blocks(cnt, T), T, smem, s>>>(cnt, B, rcond, Cout, rank_out));
+  } else {
+    VI_KERNEL(VI_K_TQL, s, k_tql<<<blocks(cnt, 64), 64, 0, s>>>(cnt, B, rcond, Cout, rank_out));
+  }
   return VI_OK;
 }
 
@@ -556,17 +650,25 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
     for (int k = 0; k < VI_NALPHA; ++k) h_tab[k] = pow(10.0, -(double)k);   // np.power(10., alpha), interpolate.py:250
     VI_CUDA(cudaMemcpyAsync(pow10tab, h_tab, sizeof(h_tab), cudaMemcpyHostToDevice, st));
     VI_CUDA(cudaMemsetAsync(Ub.tabbad, 0, U * sizeof(int32_t), st));
+    VI_CUDA(cudaMemsetAsync(Ub.count, 0, 8 * sizeof(int32_t), st));
     // ---- phase 1: chi2(10^-k) table for every unit -------------------------------------
+    VI_KERNEL(VI_K_MISC, st, k_kstar<<<(unsigned)U, 256, 0, st>>>(nreg, N, G, regmats, pow10tab, Ub.kstar));
     const int64_t T = U * VI_NALPHA;
     for (int64_t t0 = 0; t0 < T; t0 += cap) {
       int64_t cnt = (T - t0 < cap) ? T - t0 : cap;
-      VI_KERNEL(VI_K_MISC, st, k_setup_table<<<blocks(cap, 256), 256, 0, st>>>(t0, cnt, nreg, npts, pow10tab, B));
+      VI_KERNEL(VI_K_MISC, st, k_setup_table<<<blocks(cap, 256), 256, 0, st>>>(t0, cnt, nreg, npts, pow10tab, Ub.kstar, Ub.count, B));
       VI_LAUNCH_CHECK();
       if (int rc = run_systems(cnt, G, y, regmats, B, rcond, B.Csys, B.rank, st)) return rc;
       if (int rc = run_chi2(cnt, At, Wm, bm, P, B, B.Csys, B.chi2, st)) return rc;
       VI_KERNEL(VI_K_MISC, st, k_scatter_table<<<blocks(cnt, 256), 256, 0, st>>>(t0, cnt, B, Ub));
       VI_LAUNCH_CHECK();
-      solved += cnt;
+    }
+    VI_KERNEL(VI_K_MISC, st, k_fill_table<<<blocks(U, 128), 128, 0, st>>>(U, Ub.kstar, Ub));
+    {
+      int h_tab = 0;
+      VI_CUDA(cudaMemcpyAsync(&h_tab, Ub.count + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      VI_CUDA(cudaStreamSynchronize(st));
+      solved += h_tab;
     }
     // ---- phase 2: bracket + Brent in lock step ------------------------------------------
     VI_KERNEL(VI_K_MISC, st, k_bracket<<<blocks(U, 128), 128, 0, st>>>(U, nreg, npts, Ub));

@@ -115,7 +115,9 @@ VI_HD int vi_tql(int n, vi_svec d, vi_svec e, vi_svec g, vi_tape tape, int32_t* 
         for (; i >= l; --i) {
           double ei = e[PE(i)];
           double f = s * ei, b = c * ei;
-          r = hypot(f, gg);
+          // the block is scaled to max|.| ~ 1, so f*f + gg*gg cannot overflow; squares that underflow are
+          // below 1e-308 relative to 1 and are treated as zero (the r == 0 branch, as in LAPACK)
+          r = sqrt(f * f + gg * gg);
           if (i + 1 < nb - 1) e[PE(i + 1)] = r;
           if (r == 0.0) {
             d[PD(i + 1)] -= p;
@@ -123,8 +125,9 @@ VI_HD int vi_tql(int n, vi_svec d, vi_svec e, vi_svec g, vi_tape tape, int32_t* 
             early = true;
             break;
           }
-          s = f / r;
-          c = gg / r;
+          const double ri = 1.0 / r;
+          s = f * ri;
+          c = gg * ri;
           gg = d[PD(i + 1)] - p;
           r = (d[PD(i)] - gg) * s + 2.0 * c * b;
           p = s * r;
@@ -160,9 +163,28 @@ VI_HD int vi_tql(int n, vi_svec d, vi_svec e, vi_svec g, vi_tape tape, int32_t* 
   return status;
 }
 
-// w <- Z w  (replay the tape backwards).
+// w <- Z w  (replay the tape backwards).  The tape lives in global memory: four entries are fetched
+// ahead of the (dependent) updates of w so their latency overlaps.
 VI_HD void vi_tape_apply_z(vi_svec w, vi_tape tape, int32_t nrot) {
-  for (int32_t t = nrot - 1; t >= 0; --t) {
+  int32_t t = nrot - 1;
+  for (; t >= 3; t -= 4) {
+    int32_t code[4]; double c[4], s[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 4; ++q) { code[q] = tape.ix[t - q]; c[q] = tape.c[t - q]; s[q] = tape.s[t - q]; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 4; ++q) {
+      int pi = code[q] >> 1;
+      int pj = (code[q] & 1) ? pi - 1 : pi + 1;
+      double a = w[pi], b = w[pj];
+      w[pi] = c[q] * a + s[q] * b;
+      w[pj] = c[q] * b - s[q] * a;
+    }
+  }
+  for (; t >= 0; --t) {
     int32_t code = tape.ix[t];
     int pi = code >> 1;
     int pj = (code & 1) ? pi - 1 : pi + 1;

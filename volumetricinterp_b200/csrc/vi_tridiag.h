@@ -27,9 +27,37 @@
 
 #if defined(__CUDA_ARCH__)
 #define VI_PHASE(...) { __VA_ARGS__; } __syncthreads();
+#define VI_WPHASE(...) if (tid < 32) { { __VA_ARGS__; } __syncwarp(); }      // warp 0 only, warp-level barrier
 #else
 #define VI_PHASE(...) for (int tid = 0; tid < nt; ++tid) { __VA_ARGS__; }
+#define VI_WPHASE(...) for (int tid = 0; tid < 32 && tid < nt; ++tid) { __VA_ARGS__; }
 #endif
+
+// sum_{k in [a,b)} f(k) in a fixed order: 32 strided partial sums, then an xor butterfly.  Every lane of
+// the (converged) warp gets the same bits; the host version reproduces exactly that order.
+template <class F>
+VI_HD double vi_warp_sum(int a, int b, int lane, F f) {
+#if defined(__CUDA_ARCH__)
+  double s = 0.0;
+  for (int k = a + lane; k < b; k += 32) s += f(k);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+#else
+  (void)lane;
+  double part[32], nxt[32];
+  for (int l = 0; l < 32; ++l) {
+    double s = 0.0;
+    for (int k = a + l; k < b; k += 32) s += f(k);
+    part[l] = s;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    for (int l = 0; l < 32; ++l) nxt[l] = part[l] + part[l ^ o];
+    for (int l = 0; l < 32; ++l) part[l] = nxt[l];
+  }
+  return part[0];
+#endif
+}
 
 // CTA-shared working set of one system.
 struct vi_tri_ws {
@@ -63,7 +91,7 @@ VI_HD void vi_tri_load(const vi_tri_ws& S, int n, const double* G, const double*
       double x = 0.5 * (G[(int64_t)i * n + c] + G[(int64_t)c * n + i]);
       for (int r = 0; r < nreg; ++r) {
         double l = lam[r];
-        if (l != 0.0) x = x + l * regs[((int64_t)r * n + i) * n + c];
+        if (l != 0.0) x = fma(l, regs[((int64_t)r * n + i) * n + c], x);
       }
       if (!(fabs(x) <= 1.79769313486231570e308)) bad = 1.0;
       mx = fmax(mx, fabs(x));
@@ -91,62 +119,73 @@ VI_HD void vi_tri_load(const vi_tri_ws& S, int n, const double* G, const double*
 
 // Reduction proper.  V (global or host): (n x n) row j holds reflector j in columns j+1..n-1
 // (v[j+1] = 1 stored explicitly).  After the call S.d, S.e, S.tau, S.yv (= Q^T y) are final.
+// Per step: [every warp: column norm by warp-sum -> reflector] | [all: partial mat-vec] |
+// [warp 0: p, two dot products, w, rhs update] | [all: rank-2 update]  -> 4 CTA barriers.
 VI_HD void vi_tri_reduce(const vi_tri_ws& S, int n, double* V, int tid, int nt) {
   (void)tid;
   const int ng = (nt / n) < 1 ? 1 : (nt / n);
+  const int ld = S.ld;
   for (int j = 0; j + 2 < n; ++j) {
     const int lo = j + 1;
     VI_PHASE(
-      if (tid >= lo + 1 && tid < n) { double x = S.X[tid * S.ld + j]; S.red1[tid] = x * x; }
-    )
-    VI_PHASE(
-      if (tid >= lo && tid < n) {
-        double xn2 = 0.0;
-        for (int i = lo + 1; i < n; ++i) xn2 += S.red1[i];
-        double alpha = S.X[lo * S.ld + j];
-        double tau = 0.0; double beta = alpha; double scale = 0.0;
-        if (xn2 != 0.0) {
-          beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
-          tau = (beta - alpha) / beta;
-          scale = 1.0 / (alpha - beta);
-        }
-        S.v[tid] = (tid == lo) ? 1.0 : S.X[tid * S.ld + j] * scale;
-        if (tid == lo) { S.e[j] = beta; S.tau[j] = tau; S.d[j] = S.X[j * S.ld + j]; }
+      const double* col = S.X + j;
+      double xn2 = vi_warp_sum(lo + 1, n, tid & 31, [&](int k) { double x = col[k * ld]; return x * x; });
+      double alpha = col[lo * ld];
+      double tau = 0.0; double beta = alpha; double scale = 0.0;
+      if (xn2 != 0.0) {
+        beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
+        tau = (beta - alpha) / beta;
+        scale = 1.0 / (alpha - beta);
       }
+      if (tid >= lo && tid < n) {
+        double vv = (tid == lo) ? 1.0 : col[tid * ld] * scale;
+        if (tau == 0.0) vv = (tid == lo) ? 1.0 : 0.0;
+        S.v[tid] = vv;
+        V[(int64_t)j * n + tid] = vv;
+      }
+      if (tid == lo) { S.e[j] = beta; S.tau[j] = tau; S.d[j] = S.X[j * ld + j]; }
     )
     const double tau = S.tau[j];
-    if (tau == 0.0) {   // H_j = I (uniform across the CTA: tau lives in shared memory)
-      VI_PHASE( if (tid >= lo && tid < n) V[(int64_t)j * n + tid] = (tid == lo) ? 1.0 : 0.0; )
-      continue;
-    }
+    if (tau == 0.0) continue;   // H_j = I (uniform across the CTA: tau lives in shared memory)
     VI_PHASE(
       {
         int g = tid / n; int c = tid - g * n;
         if (g < ng && c >= lo) {
-          double acc = 0.0;
-          for (int i = lo + g; i < n; i += ng) acc += S.X[i * S.ld + c] * S.v[i];
-          S.psum[g * n + c] = acc;
+          const double* xc = S.X + c;
+          double a0 = 0.0; double a1 = 0.0; double a2 = 0.0; double a3 = 0.0;
+          int i = lo + g;
+          for (; i + 3 * ng < n; i += 4 * ng) {
+            a0 += xc[i * ld] * S.v[i];
+            a1 += xc[(i + ng) * ld] * S.v[i + ng];
+            a2 += xc[(i + 2 * ng) * ld] * S.v[i + 2 * ng];
+            a3 += xc[(i + 3 * ng) * ld] * S.v[i + 3 * ng];
+          }
+          for (; i < n; i += ng) a0 += xc[i * ld] * S.v[i];
+          S.psum[g * n + c] = (a0 + a1) + (a2 + a3);
         }
-        if (tid >= lo && tid < n) V[(int64_t)j * n + tid] = S.v[tid];
       }
     )
-    VI_PHASE(
-      if (tid >= lo && tid < n) {
+    VI_WPHASE(
+      for (int c = lo + tid; c < n; c += 32) {
         double p = 0.0;
-        for (int g = 0; g < ng; ++g) p += S.psum[g * n + tid];
-        p = tau * p;
-        S.w[tid] = p;
-        S.red1[tid] = p * S.v[tid];
-        S.red2[tid] = S.v[tid] * S.yv[tid];
+        for (int g = 0; g < ng; ++g) p += S.psum[g * n + c];
+        S.w[c] = tau * p;
       }
     )
+    VI_WPHASE(
+      double dot = vi_warp_sum(lo, n, tid, [&](int k) { return S.w[k] * S.v[k]; });
+      double dot2 = vi_warp_sum(lo, n, tid, [&](int k) { return S.v[k] * S.yv[k]; });
+      if (tid == 0) { S.sc[2] = dot; S.sc[3] = dot2; }
+    )
     VI_PHASE(
-      if (tid >= lo && tid < n) {
-        double dot = 0.0; double dot2 = 0.0;
-        for (int i = lo; i < n; ++i) { dot += S.red1[i]; dot2 += S.red2[i]; }
-        double a2 = -0.5 * tau * dot;
-        S.w[tid] = S.w[tid] + a2 * S.v[tid];
-        S.yv[tid] = S.yv[tid] - (tau * dot2) * S.v[tid];
+      if (tid < 32) {
+        double a2 = -0.5 * tau * S.sc[2];
+        double t2 = tau * S.sc[3];
+        for (int c = lo + tid; c < n; c += 32) {
+          double vc = S.v[c];
+          S.w[c] = S.w[c] + a2 * vc;
+          S.yv[c] = S.yv[c] - t2 * vc;
+        }
       }
     )
     VI_PHASE(
@@ -154,11 +193,15 @@ VI_HD void vi_tri_reduce(const vi_tri_ws& S, int n, double* V, int tid, int nt) 
         int g = tid / n; int c = tid - g * n;
         if (g < ng && c >= lo) {
           double wc = S.w[c]; double vc = S.v[c];
+          double* xc = S.X + c;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 4
+#endif
           for (int i = lo + g; i < n; i += ng) {
-            double x = S.X[i * S.ld + c];
+            double x = xc[i * ld];
             x = x - S.v[i] * wc;
             x = x - S.w[i] * vc;
-            S.X[i * S.ld + c] = x;
+            xc[i * ld] = x;
           }
         }
       }
@@ -167,11 +210,11 @@ VI_HD void vi_tri_reduce(const vi_tri_ws& S, int n, double* V, int tid, int nt) 
   VI_PHASE(
     if (tid == 0) {
       if (n >= 2) {
-        S.d[n - 2] = S.X[(n - 2) * S.ld + (n - 2)];
-        S.e[n - 2] = S.X[(n - 1) * S.ld + (n - 2)];
+        S.d[n - 2] = S.X[(n - 2) * ld + (n - 2)];
+        S.e[n - 2] = S.X[(n - 1) * ld + (n - 2)];
         S.tau[n - 2] = 0.0;
       }
-      S.d[n - 1] = S.X[(n - 1) * S.ld + (n - 1)];
+      S.d[n - 1] = S.X[(n - 1) * ld + (n - 1)];
       S.e[n - 1] = 0.0; S.tau[n - 1] = 0.0;
     }
   )
@@ -185,9 +228,25 @@ VI_HD void vi_tri_backtransform(int n, const double* V, const double* tau, int64
     double t = tau[(int64_t)j * tau_stride];
     if (t == 0.0) continue;
     const double* vj = V + (int64_t)j * n;
-    double dot = 0.0;
-    for (int i = j + 1; i < n; ++i) dot += vj[i] * c[(int64_t)i * stride];
-    dot = dot * t;
-    for (int i = j + 1; i < n; ++i) c[(int64_t)i * stride] -= dot * vj[i];
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+    int i = j + 1;
+    for (; i + 3 < n; i += 4) {
+      double v0 = vj[i], v1 = vj[i + 1], v2 = vj[i + 2], v3 = vj[i + 3];
+      d0 += v0 * c[(int64_t)i * stride];
+      d1 += v1 * c[(int64_t)(i + 1) * stride];
+      d2 += v2 * c[(int64_t)(i + 2) * stride];
+      d3 += v3 * c[(int64_t)(i + 3) * stride];
+    }
+    for (; i < n; ++i) d0 += vj[i] * c[(int64_t)i * stride];
+    double dot = ((d0 + d1) + (d2 + d3)) * t;
+    i = j + 1;
+    for (; i + 3 < n; i += 4) {
+      double v0 = vj[i], v1 = vj[i + 1], v2 = vj[i + 2], v3 = vj[i + 3];
+      c[(int64_t)i * stride] -= dot * v0;
+      c[(int64_t)(i + 1) * stride] -= dot * v1;
+      c[(int64_t)(i + 2) * stride] -= dot * v2;
+      c[(int64_t)(i + 3) * stride] -= dot * v3;
+    }
+    for (; i < n; ++i) c[(int64_t)i * stride] -= dot * vj[i];
   }
 }
