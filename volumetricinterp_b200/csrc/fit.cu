@@ -48,11 +48,13 @@ struct Bump {
 
 struct SysBuf {
   int64_t cap;         // systems held at once (multiple of 32)
-  int n, nreg, tapecap, nt, use_gx, ld;
+  int n, nreg, tapecap, nt, use_gx, ld, nchunk;
   size_t smem;
-  double *V, *d, *e, *g, *tau, *scl, *tc, *ts, *lam, *Csys, *chi2, *Xg;
-  int32_t *tix, *st, *rec, *rank;
+  double *V, *d, *e, *g, *tau, *scl, *tcs, *lam, *Csys, *chi2, *chi2p, *Xg;
+  int32_t *tix, *st, *rec, *rank, *nrot;
 };
+
+constexpr int kChiGates = 1024;    // gates per CTA in k_chi2 (partial sums combined in fixed order)
 
 int tri_threads(int n) {
   int ng = 1024 / n;
@@ -63,11 +65,12 @@ int tri_threads(int n) {
   return nt;
 }
 
-void sysbuf_carve(Bump& b, SysBuf& S, int64_t cap, int n, int nreg) {
+void sysbuf_carve(Bump& b, SysBuf& S, int64_t cap, int n, int nreg, int P) {
   S.cap = cap; S.n = n; S.nreg = nreg;
   S.tapecap = n * n + 64;
   S.nt = tri_threads(n);
   S.ld = vi_tri_ld(n);
+  S.nchunk = (P + kChiGates - 1) / kChiGates;
   size_t smem_x = (size_t)n * S.ld * sizeof(double);
   size_t smem_aux = (size_t)vi_tri_aux_doubles(n, S.nt) * sizeof(double);
   S.use_gx = (smem_x + smem_aux > 227 * 1024) ? 1 : 0;
@@ -78,15 +81,16 @@ void sysbuf_carve(Bump& b, SysBuf& S, int64_t cap, int n, int nreg) {
   S.g = b.take<double>(cap * n);
   S.tau = b.take<double>(cap * n);
   S.scl = b.take<double>(cap);
-  S.tc = b.take<double>(cap * S.tapecap);
-  S.ts = b.take<double>(cap * S.tapecap);
+  S.tcs = b.take<double>(cap * S.tapecap * 2);     // (c, s) pairs, contiguous per system
   S.tix = b.take<int32_t>(cap * S.tapecap);
   S.lam = b.take<double>(cap * (nreg > 0 ? nreg : 1));
   S.Csys = b.take<double>(cap * n);
   S.chi2 = b.take<double>(cap);
+  S.chi2p = b.take<double>(cap * (S.nchunk > 0 ? S.nchunk : 1));
   S.st = b.take<int32_t>(cap);
   S.rec = b.take<int32_t>(cap);
   S.rank = b.take<int32_t>(cap);
+  S.nrot = b.take<int32_t>(cap);
   S.Xg = S.use_gx ? b.take<double>(cap * n * S.ld) : nullptr;
 }
 
@@ -112,15 +116,15 @@ void unit_carve(Bump& b, UnitBuf& Ub, int64_t U) {
   Ub.count = b.take<int32_t>(8);
 }
 
-int64_t per_system_bytes(int n, int nreg) {
+int64_t per_system_bytes(int n, int nreg, int P) {
   Bump b{nullptr, 0, 0};
   SysBuf S;
-  sysbuf_carve(b, S, 32, n, nreg);
+  sysbuf_carve(b, S, 32, n, nreg, P);
   return (b.off + 32 * 256) / 32;
 }
 
-int64_t default_system_cap(int64_t wanted, int n, int nreg) {
-  int64_t per = per_system_bytes(n, nreg);
+int64_t default_system_cap(int64_t wanted, int n, int nreg, int P) {
+  int64_t per = per_system_bytes(n, nreg, P);
   int64_t budget = (int64_t)16 << 30;   // 16 GiB of scratch by default
   int64_t cap = budget / per;
   if (cap > wanted) cap = wanted;
@@ -133,6 +137,7 @@ int64_t default_system_cap(int64_t wanted, int n, int nreg) {
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int64_t ileave(int64_t s, int n) { return (s >> 5) * 32 * (int64_t)n + (s & 31); }
 
+template <bool GX>
 __global__ void __launch_bounds__(1024)
 k_tridiag(const double* __restrict__ G, const double* __restrict__ y, const double* __restrict__ regs, SysBuf B) {
   extern __shared__ __align__(16) double sm[];
@@ -141,14 +146,12 @@ k_tridiag(const double* __restrict__ G, const double* __restrict__ y, const doub
   if (r < 0) { if (threadIdx.x == 0) B.st[s] = kSkip; return; }
   const int n = B.n, nt = blockDim.x, tid = threadIdx.x;
   vi_tri_ws S;
-  double* aux = sm;
+  double* aux;
   S.ld = B.ld;
-  if (B.use_gx) S.X = B.Xg + s * (int64_t)n * S.ld;
-  else { S.X = sm; aux = sm + (size_t)n * S.ld; }
-  const int ng = (nt / n) < 1 ? 1 : (nt / n);
+  if (GX) { S.X = B.Xg + s * (int64_t)n * S.ld; aux = sm; }
+  else { S.X = sm; aux = sm + (size_t)n * S.ld; }      // X stays a provable shared-memory pointer (LDS/STS)
   S.v = aux; S.w = aux + n; S.yv = aux + 2 * n; S.red2 = aux + 3 * n; S.d = aux + 4 * n; S.e = aux + 5 * n;
   S.tau = aux + 6 * n; S.sc = aux + 7 * n; S.red1 = aux + 7 * n + 8; S.psum = S.red1 + (nt > n ? nt : n);
-  (void)ng;
   vi_tri_load(S, n, G + (int64_t)r * n * n, y + (int64_t)r * n, regs, B.lam + s * (B.nreg > 0 ? B.nreg : 1), B.nreg, tid, nt);
   const bool bad = S.sc[1] != 0.0;
   if (!bad) vi_tri_reduce(S, n, B.V + s * (int64_t)n * n, tid, nt);
@@ -163,14 +166,99 @@ k_tridiag(const double* __restrict__ G, const double* __restrict__ y, const doub
   if (tid == 0) { B.scl[s] = S.sc[0]; B.st[s] = bad ? VI_ST_NONFINITE : VI_ST_OK; }
 }
 
-// Common tail of the two QL kernels: d, e, g are this thread's strided vectors (shared or global).
-__device__ __forceinline__ void tql_system(int64_t s, const SysBuf& B, double rcond, vi_svec d, vi_svec e, vi_svec g,
-                                           double* __restrict__ Cs, int32_t* __restrict__ rank_out) {
+__device__ __forceinline__ vi_tape tape_of(const SysBuf& B, int64_t s) {
+  double* cs = B.tcs + s * (int64_t)B.tapecap * 2;
+  return vi_tape{{cs, 2}, {cs + 1, 2}, {B.tix + s * (int64_t)B.tapecap, 1}, B.tapecap};
+}
+
+// QL proper, one THREAD per system.  d, e, g (3n doubles) sit on the dependency chain of every
+// rotation, so they live in shared memory laid out [i][thread] (a lane always hits its own bank pair
+// whatever i it is at).  Leaves u = L^+ Z^T Q^T y in B.g, the rotation tape in B.tcs/B.tix.
+__global__ void k_tql_smem(int64_t nsys, SysBuf B, double rcond) {
+  extern __shared__ __align__(16) double sm[];
+  const int T = blockDim.x, tid = threadIdx.x, n = B.n;
+  const int64_t s = (int64_t)blockIdx.x * T + tid;
+  if (s >= nsys) return;
+  if (B.st[s] != VI_ST_OK) return;
+  vi_svec d{sm + tid, T}, e{sm + (size_t)n * T + tid, T}, g{sm + (size_t)2 * n * T + tid, T};
+  const int64_t base = ileave(s, n);
+  for (int i = 0; i < n; ++i) {
+    d[i] = B.d[base + (int64_t)i * 32];
+    e[i] = B.e[base + (int64_t)i * 32];
+    g[i] = B.g[base + (int64_t)i * 32];
+  }
+  int32_t nrot = 0;
+  const int q = vi_tql(n, d, e, g, tape_of(B, s), &nrot);
+  if (q != 0) { B.st[s] = VI_ST_NOCONV; return; }
+  B.rank[s] = vi_spectral_divide(n, d, g, rcond);
+  B.nrot[s] = nrot;
+  for (int i = 0; i < n; ++i) B.g[base + (int64_t)i * 32] = g[i];
+}
+
+// c = Q Z u, one WARP per system: the tape replay is a dependent chain (all lanes run it redundantly
+// on the warp's shared vector, tape entries arrive as broadcast loads fetched four ahead); the
+// reflectors are then applied cooperatively (coalesced V rows, shuffle-tree dot products).
+constexpr int kApplyWarps = 8;
+__global__ void __launch_bounds__(kApplyWarps * 32)
+k_apply(int64_t nsys, SysBuf B, double* __restrict__ Cout, int32_t* __restrict__ rank_out) {
+  extern __shared__ __align__(16) double sm[];
+  const int n = B.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t s = (int64_t)blockIdx.x * kApplyWarps + warp;
+  if (s >= nsys) return;
+  const int st = B.st[s];
+  if (st == kSkip) return;
+  double* Cs = Cout + s * (int64_t)n;
+  if (st != VI_ST_OK) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int i = lane; i < n; i += 32) Cs[i] = nan;
+    if (lane == 0) rank_out[s] = 0;
+    return;
+  }
+  double* w = sm + (size_t)warp * n;
+  const int64_t base = ileave(s, n);
+  for (int i = lane; i < n; i += 32) w[i] = B.g[base + (int64_t)i * 32];
+  __syncwarp();
+  vi_tape_apply_z(vi_svec{w, 1}, tape_of(B, s), B.nrot[s]);
+  __syncwarp();
+  const double scl = B.scl[s];
+  for (int i = lane; i < n; i += 32) w[i] *= scl;
+  __syncwarp();
+  const double* V = B.V + s * (int64_t)n * n;
+  for (int j = n - 3; j >= 0; --j) {
+    const double t = B.tau[base + (int64_t)j * 32];
+    if (t == 0.0) continue;
+    const double* vj = V + (int64_t)j * n;
+    double dot = 0.0;
+    for (int i = j + 1 + lane; i < n; i += 32) dot += vj[i] * w[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    dot *= t;
+    for (int i = j + 1 + lane; i < n; i += 32) w[i] -= dot * vj[i];
+    __syncwarp();
+  }
+  for (int i = lane; i < n; i += 32) Cs[i] = w[i];
+  if (lane == 0) rank_out[s] = B.rank[s];
+}
+
+// Fallback for orders whose vectors do not fit shared memory: everything in one thread per system
+// on the global (warp-interleaved) workspace.
+__global__ void __launch_bounds__(64)
+k_tql(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, int32_t* __restrict__ rank_out) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nsys) return;
+  const int st = B.st[s];
+  if (st == kSkip) return;
   const int n = B.n;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  double* Cs = Cout + s * (int64_t)n;
+  if (st != VI_ST_OK) {
+    for (int i = 0; i < n; ++i) Cs[i] = nan;
+    rank_out[s] = 0;
+    return;
+  }
   const int64_t base = ileave(s, n);
-  const int64_t tb = ileave(s, B.tapecap);
-  vi_tape tape{{B.tc + tb, 32}, {B.ts + tb, 32}, {B.tix + tb, 32}, B.tapecap};
+  vi_svec d{B.d + base, 32}, e{B.e + base, 32}, g{B.g + base, 32};
+  vi_tape tape = tape_of(B, s);
   int32_t nrot = 0;
   const int q = vi_tql(n, d, e, g, tape, &nrot);
   if (q != 0) {
@@ -188,65 +276,20 @@ __device__ __forceinline__ void tql_system(int64_t s, const SysBuf& B, double rc
   rank_out[s] = rank;
 }
 
-// One THREAD per system.  The three working vectors (d, e, g: 3n doubles per thread) sit on the
-// critical dependency chain of every rotation, so they live in shared memory, laid out [i][thread]
-// (a lane always hits its own bank pair whatever i it is at: no conflicts beyond the 64-bit minimum).
-__global__ void k_tql_smem(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout,
-                           int32_t* __restrict__ rank_out) {
-  extern __shared__ __align__(16) double sm[];
-  const int T = blockDim.x, tid = threadIdx.x, n = B.n;
-  const int64_t s = (int64_t)blockIdx.x * T + tid;
-  if (s >= nsys) return;
-  const int st = B.st[s];
-  if (st == kSkip) return;
-  double* Cs = Cout + s * (int64_t)n;
-  if (st != VI_ST_OK) {
-    const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    for (int i = 0; i < n; ++i) Cs[i] = nan;
-    rank_out[s] = 0;
-    return;
-  }
-  vi_svec d{sm + tid, T}, e{sm + (size_t)n * T + tid, T}, g{sm + (size_t)2 * n * T + tid, T};
-  const int64_t base = ileave(s, n);
-  for (int i = 0; i < n; ++i) {
-    d[i] = B.d[base + (int64_t)i * 32];
-    e[i] = B.e[base + (int64_t)i * 32];
-    g[i] = B.g[base + (int64_t)i * 32];
-  }
-  tql_system(s, B, rcond, d, e, g, Cs, rank_out);
-}
-
-// Fallback for orders whose vectors do not fit shared memory: same algorithm on the global
-// (warp-interleaved) workspace.
-__global__ void __launch_bounds__(64)
-k_tql(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, int32_t* __restrict__ rank_out) {
-  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nsys) return;
-  const int st = B.st[s];
-  if (st == kSkip) return;
-  const int n = B.n;
-  double* Cs = Cout + s * (int64_t)n;
-  if (st != VI_ST_OK) {
-    const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    for (int i = 0; i < n; ++i) Cs[i] = nan;
-    rank_out[s] = 0;
-    return;
-  }
-  const int64_t base = ileave(s, n);
-  vi_svec d{B.d + base, 32}, e{B.e + base, 32}, g{B.g + base, 32};
-  tql_system(s, B, rcond, d, e, g, Cs, rank_out);
-}
-
 // chi2[s] = sum_j Wm[r][j] * (sum_n At[n][j] C_s[n] - bm[r][j])^2   (chi2objfunct, interpolate.py:258-259)
+// grid (systems/16, gate chunks): a CTA contracts kChiGates gates against 16 coefficient vectors (the
+// design matrix is streamed once per 16 systems) and writes one partial sum per system; k_chi2_sum
+// adds the partials in chunk order (deterministic).
 __global__ void __launch_bounds__(kChiThreads)
 k_chi2(const double* __restrict__ At, const double* __restrict__ Wm, const double* __restrict__ bm, int P, int n,
        int64_t nsys, const int32_t* __restrict__ rec, const int32_t* __restrict__ st, const double* __restrict__ Csys,
-       double* __restrict__ chi2) {
+       double* __restrict__ part, int nchunk) {
   extern __shared__ __align__(16) double sm[];
   double* Cs = sm;                         // n x kChiSB  (n-major so one LDS.128 serves two systems)
   double* red = sm + (size_t)n * kChiSB;   // kChiThreads/32 x kChiSB
   __shared__ int srec[kChiSB];
   const int64_t s0 = (int64_t)blockIdx.x * kChiSB;
+  const int chunk = blockIdx.y;
   const int tid = threadIdx.x;
   if (tid < kChiSB) {
     int64_t s = s0 + tid;
@@ -268,13 +311,15 @@ k_chi2(const double* __restrict__ At, const double* __restrict__ Wm, const doubl
   double csum[kChiSB];
 #pragma unroll
   for (int q = 0; q < kChiSB; ++q) csum[q] = 0.0;
-  for (int j = tid; j < P; j += kChiThreads) {
+  const int jend = min(P, (chunk + 1) * kChiGates);
+  for (int j = chunk * kChiGates + tid; j < jend; j += kChiThreads) {
     double acc[kChiSB];
 #pragma unroll
     for (int q = 0; q < kChiSB; ++q) acc[q] = 0.0;
-#pragma unroll 4
+    const double* ap = At + j;
+#pragma unroll 8
     for (int i = 0; i < n; ++i) {
-      const double a = At[(int64_t)i * P + j];
+      const double a = __ldg(ap + (int64_t)i * P);
       const double2* c2 = reinterpret_cast<const double2*>(Cs + i * kChiSB);
 #pragma unroll
       for (int q = 0; q < kChiSB / 2; ++q) {
@@ -300,7 +345,6 @@ k_chi2(const double* __restrict__ At, const double* __restrict__ Wm, const doubl
       }
     }
   }
-  // deterministic reduction: warp shuffle tree, then the 8 warp sums in order
   const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
   for (int q = 0; q < kChiSB; ++q) {
@@ -314,9 +358,18 @@ k_chi2(const double* __restrict__ At, const double* __restrict__ Wm, const doubl
     if (s < nsys && srec[tid] >= 0) {
       double v = 0.0;
       for (int w = 0; w < kChiThreads / 32; ++w) v += red[w * kChiSB + tid];
-      chi2[s] = v;
+      part[s * nchunk + chunk] = v;
     }
   }
+}
+
+__global__ void k_chi2_sum(int64_t nsys, const int32_t* __restrict__ st, const double* __restrict__ part, int nchunk,
+                           double* __restrict__ chi2) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nsys || st[s] != VI_ST_OK) return;
+  double v = 0.0;
+  for (int c = 0; c < nchunk; ++c) v += part[s * nchunk + c];
+  chi2[s] = v;
 }
 
 // ---- system set-up for the three phases ---------------------------------------------------
@@ -532,16 +585,22 @@ inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / p
 int run_systems(int64_t cnt, const double* G, const double* y, const double* regs, const SysBuf& B, double rcond,
                 double* Cout, int32_t* rank_out, cudaStream_t s) {
   if (cnt <= 0) return VI_OK;
-  VI_CUDA(cudaFuncSetAttribute(k_tridiag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
-  VI_KERNEL(VI_K_TRIDIAG, s, k_tridiag<<<(unsigned)cnt, B.nt, B.smem, s>>>(G, y, regs, B));
-  VI_LAUNCH_CHECK();
+  if (B.use_gx) {
+    VI_CUDA(cudaFuncSetAttribute(k_tridiag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
+    VI_KERNEL(VI_K_TRIDIAG, s, k_tridiag<true><<<(unsigned)cnt, B.nt, B.smem, s>>>(G, y, regs, B));
+  } else {
+    VI_CUDA(cudaFuncSetAttribute(k_tridiag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
+    VI_KERNEL(VI_K_TRIDIAG, s, k_tridiag<false><<<(unsigned)cnt, B.nt, B.smem, s>>>(G, y, regs, B));
+  }
   // threads per block for the shared-memory QL: as many as 3n doubles per thread allow (<= 64)
   int T = (int)((227 * 1024) / ((size_t)3 * B.n * sizeof(double))) / 32 * 32;
   if (T > 64) T = 64;
   if (T >= 32) {
     size_t smem = (size_t)3 * B.n * T * sizeof(double);
     VI_CUDA(cudaFuncSetAttribute(k_tql_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VI_KERNEL(VI_K_TQL, s, k_tql_smem<<<blocks(cnt, T), T, smem, s>>>(cnt, B, rcond, Cout, rank_out));
+    VI_KERNEL(VI_K_TQL, s, k_tql_smem<<<blocks(cnt, T), T, smem, s>>>(cnt, B, rcond));
+    size_t smem2 = (size_t)kApplyWarps * B.n * sizeof(double);
+    VI_KERNEL(VI_K_TQL, s, k_apply<<<blocks(cnt, kApplyWarps), kApplyWarps * 32, smem2, s>>>(cnt, B, Cout, rank_out));
   } else {
     VI_KERNEL(VI_K_TQL, s, k_tql<<<blocks(cnt, 64), 64, 0, s>>>(cnt, B, rcond, Cout, rank_out));
   }
@@ -553,8 +612,9 @@ int run_chi2(int64_t cnt, const double* At, const double* Wm, const double* bm, 
   if (cnt <= 0) return VI_OK;
   size_t smem = ((size_t)B.n * kChiSB + (kChiThreads / 32) * kChiSB) * sizeof(double);
   VI_CUDA(cudaFuncSetAttribute(k_chi2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  VI_KERNEL(VI_K_CHI2, s, k_chi2<<<blocks(cnt, kChiSB), kChiThreads, smem, s>>>(At, Wm, bm, P, B.n, cnt, B.rec, B.st, Csys, chi2));
-  VI_LAUNCH_CHECK();
+  dim3 grid(blocks(cnt, kChiSB), (unsigned)B.nchunk);
+  VI_KERNEL(VI_K_CHI2, s, k_chi2<<<grid, kChiThreads, smem, s>>>(At, Wm, bm, P, B.n, cnt, B.rec, B.st, Csys, B.chi2p, B.nchunk));
+  VI_KERNEL(VI_K_CHI2, s, k_chi2_sum<<<blocks(cnt, 256), 256, 0, s>>>(cnt, B.st, B.chi2p, B.nchunk, chi2));
   return VI_OK;
 }
 
@@ -562,28 +622,27 @@ int run_chi2(int64_t cnt, const double* At, const double* Wm, const double* bm, 
 
 extern "C" int vi_fit_workspace_bytes(int32_t R, int32_t P, int32_t N, int32_t nreg, int64_t systems, int64_t* bytes) {
   VI_REQUIRE(bytes != nullptr && R >= 0 && N >= 1 && nreg >= 0, "bad arguments");
-  (void)P;
   if (N > 1024) { vi_set_error("nbasis %d > 1024 not supported", N); return VI_EUNSUPPORTED; }
   int64_t U = (int64_t)R * (nreg > 0 ? nreg : 1);
   int64_t wanted = U * VI_NALPHA;
   if (wanted < R) wanted = R;
-  int64_t cap = systems > 0 ? vi_align_up(systems, 32) : default_system_cap(wanted, N, nreg);
+  int64_t cap = systems > 0 ? vi_align_up(systems, 32) : default_system_cap(wanted, N, nreg, P);
   Bump b{nullptr, 0, 0};
   UnitBuf Ub;
   unit_carve(b, Ub, U);
   b.take<double>(VI_NALPHA);
-  *bytes = b.off + per_system_bytes(N, nreg) * (cap + 32) + 16384;
+  *bytes = b.off + per_system_bytes(N, nreg, P) * (cap + 32) + 16384;
   return VI_OK;
 }
 
 // cap actually available inside a given workspace
-static int64_t cap_for_workspace(int64_t ws_bytes, int64_t U, int n, int nreg) {
+static int64_t cap_for_workspace(int64_t ws_bytes, int64_t U, int n, int nreg, int P) {
   Bump b{nullptr, 0, 0};
   UnitBuf Ub;
   unit_carve(b, Ub, U);
   b.take<double>(VI_NALPHA);
   int64_t left = ws_bytes - b.off - 8192;
-  int64_t per = per_system_bytes(n, nreg);
+  int64_t per = per_system_bytes(n, nreg, P);
   int64_t cap = left / per;
   cap = cap / 32 * 32;
   return cap;
@@ -598,12 +657,12 @@ extern "C" int vi_solve_batched(const double* G, const double* y, const int32_t*
   VI_REQUIRE(nreg == 0 || (regmats && lam), "regmats/lam missing");
   if (S == 0) return VI_OK;
   cudaStream_t st = vi_stream(stream);
-  int64_t cap = cap_for_workspace(workspace_bytes, 0, N, nreg);
+  int64_t cap = cap_for_workspace(workspace_bytes, 0, N, nreg, 1);
   if (cap < 32) { vi_set_error("workspace too small (%lld bytes)", (long long)workspace_bytes); return VI_EWORKSPACE; }
   if (cap > vi_align_up(S, 32)) cap = vi_align_up(S, 32);
   Bump b{reinterpret_cast<char*>(workspace), 0, workspace_bytes};
   SysBuf B;
-  sysbuf_carve(b, B, cap, N, nreg);
+  sysbuf_carve(b, B, cap, N, nreg, 1);
   for (int64_t s0 = 0; s0 < S; s0 += cap) {
     int64_t cnt = (S - s0 < cap) ? S - s0 : cap;
     VI_KERNEL(VI_K_MISC, st, k_setup_solve<<<blocks(cap, 256), 256, 0, st>>>(s0, cnt, nreg, rec, lam, B));
@@ -633,7 +692,7 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
   const double rcond = VI_EPS;
   const int64_t U = (int64_t)R * (nreg > 0 ? nreg : 1);
 
-  int64_t cap = cap_for_workspace(workspace_bytes, U, N, nreg);
+  int64_t cap = cap_for_workspace(workspace_bytes, U, N, nreg, P);
   if (cap < 32) { vi_set_error("workspace too small (%lld bytes)", (long long)workspace_bytes); return VI_EWORKSPACE; }
   int64_t most = vi_align_up(method == VI_METHOD_CHI2 ? U * VI_NALPHA : (int64_t)R, 32);
   if (cap > most) cap = most;
@@ -642,7 +701,7 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
   unit_carve(b, Ub, U);
   double* pow10tab = b.take<double>(VI_NALPHA);
   SysBuf B;
-  sysbuf_carve(b, B, cap, N, nreg);
+  sysbuf_carve(b, B, cap, N, nreg, P);
   int64_t solved = 0;
 
   if (method == VI_METHOD_CHI2) {

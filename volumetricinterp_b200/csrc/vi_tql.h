@@ -117,15 +117,23 @@ VI_HD int vi_tql(int n, vi_svec d, vi_svec e, vi_svec g, vi_tape tape, int32_t* 
           double f = s * ei, b = c * ei;
           // the block is scaled to max|.| ~ 1, so f*f + gg*gg cannot overflow; squares that underflow are
           // below 1e-308 relative to 1 and are treated as zero (the r == 0 branch, as in LAPACK)
-          r = sqrt(f * f + gg * gg);
-          if (i + 1 < nb - 1) e[PE(i + 1)] = r;
-          if (r == 0.0) {
+          const double r2 = f * f + gg * gg;
+          if (r2 == 0.0) {
+            if (i + 1 < nb - 1) e[PE(i + 1)] = 0.0;
             d[PD(i + 1)] -= p;
             if (mm < nb - 1) e[PE(mm)] = 0.0;
             early = true;
             break;
           }
-          const double ri = 1.0 / r;
+          // one reciprocal square root instead of hypot + two divisions (the dependent chain of every
+          // rotation runs through here): r = r2 / sqrt(r2), s = f / r, c = g / r
+#if defined(__CUDA_ARCH__)
+          const double ri = rsqrt(r2);
+#else
+          const double ri = 1.0 / sqrt(r2);
+#endif
+          r = r2 * ri;
+          if (i + 1 < nb - 1) e[PE(i + 1)] = r;
           s = f * ri;
           c = gg * ri;
           gg = d[PD(i + 1)] - p;

@@ -26,6 +26,12 @@
 #endif
 
 #if defined(__CUDA_ARCH__)
+#define VI_UNROLL4 _Pragma("unroll 4")
+#else
+#define VI_UNROLL4
+#endif
+
+#if defined(__CUDA_ARCH__)
 #define VI_PHASE(...) { __VA_ARGS__; } __syncthreads();
 #define VI_WPHASE(...) if (tid < 32) { { __VA_ARGS__; } __syncwarp(); }      // warp 0 only, warp-level barrier
 #else
@@ -151,16 +157,20 @@ VI_HD void vi_tri_reduce(const vi_tri_ws& S, int n, double* V, int tid, int nt) 
       {
         int g = tid / n; int c = tid - g * n;
         if (g < ng && c >= lo) {
-          const double* xc = S.X + c;
+          const int step = ng * ld;
+          const double* xp = S.X + (lo + g) * ld + c;
+          const double* vp = S.v + lo + g;
+          const int cnt = (n - lo - g + ng - 1) / ng;
           double a0 = 0.0; double a1 = 0.0; double a2 = 0.0; double a3 = 0.0;
-          int i = lo + g;
-          for (; i + 3 * ng < n; i += 4 * ng) {
-            a0 += xc[i * ld] * S.v[i];
-            a1 += xc[(i + ng) * ld] * S.v[i + ng];
-            a2 += xc[(i + 2 * ng) * ld] * S.v[i + 2 * ng];
-            a3 += xc[(i + 3 * ng) * ld] * S.v[i + 3 * ng];
+          int k = 0;
+          for (; k + 3 < cnt; k += 4) {
+            a0 += xp[0] * vp[0];
+            a1 += xp[step] * vp[ng];
+            a2 += xp[2 * step] * vp[2 * ng];
+            a3 += xp[3 * step] * vp[3 * ng];
+            xp += 4 * step; vp += 4 * ng;
           }
-          for (; i < n; i += ng) a0 += xc[i * ld] * S.v[i];
+          for (; k < cnt; ++k) { a0 += xp[0] * vp[0]; xp += step; vp += ng; }
           S.psum[g * n + c] = (a0 + a1) + (a2 + a3);
         }
       }
@@ -192,16 +202,19 @@ VI_HD void vi_tri_reduce(const vi_tri_ws& S, int n, double* V, int tid, int nt) 
       {
         int g = tid / n; int c = tid - g * n;
         if (g < ng && c >= lo) {
-          double wc = S.w[c]; double vc = S.v[c];
-          double* xc = S.X + c;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 4
-#endif
-          for (int i = lo + g; i < n; i += ng) {
-            double x = xc[i * ld];
-            x = x - S.v[i] * wc;
-            x = x - S.w[i] * vc;
-            xc[i * ld] = x;
+          const double wc = S.w[c]; const double vc = S.v[c];
+          const int step = ng * ld;
+          double* xp = S.X + (lo + g) * ld + c;
+          const double* vp = S.v + lo + g;
+          const double* wp = S.w + lo + g;
+          const int cnt = (n - lo - g + ng - 1) / ng;
+          VI_UNROLL4
+          for (int k = 0; k < cnt; ++k) {
+            double x = xp[0];
+            x = x - vp[0] * wc;
+            x = x - wp[0] * vc;
+            xp[0] = x;
+            xp += step; vp += ng; wp += ng;
           }
         }
       }
