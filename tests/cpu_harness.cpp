@@ -59,6 +59,27 @@ int h_tql_solve(int n, const double* d0, const double* e0, const double* g0, dou
   return st;
 }
 
+// Same solve through the GPU hot-path variant: eigenvalues + tape (vi_tql_values), Z^T g by forward
+// replay, divide, Z u by backward replay.
+int h_tql_values_solve(int n, const double* d0, const double* e0, const double* g0, double rcond,
+                       double* w, double* lam, int* rank, int* nrot) {
+  std::vector<double> d(d0, d0 + n), e(n, 0.0), g(g0, g0 + n);
+  for (int i = 0; i + 1 < n; ++i) e[i] = e0[i];
+  int cap = n * n + 64;
+  std::vector<double> tcs(2 * (size_t)cap);
+  std::vector<int32_t> ti(cap);
+  vi_tape tape{{tcs.data(), 2}, {tcs.data() + 1, 2}, {ti.data(), 1}, cap};
+  int32_t nr = 0;
+  int st = vi_tql_values(n, {d.data(), 1}, {e.data(), 1}, tape, &nr);
+  std::memcpy(lam, d.data(), n * sizeof(double));
+  vi_tape_apply_zt({g.data(), 1}, tape, nr);
+  *rank = vi_spectral_divide(n, {d.data(), 1}, {g.data(), 1}, rcond);
+  vi_tape_apply_z({g.data(), 1}, tape, nr);
+  std::memcpy(w, g.data(), n * sizeof(double));
+  *nrot = nr;
+  return st;
+}
+
 typedef double (*h_fn)(double);
 // brentq driven through the state machine; xs receives every abscissa evaluated.
 int h_brentq(h_fn f, double xa, double xb, double* root, double* xs, int* nfev) {
@@ -101,12 +122,13 @@ int h_system_solve(int n, const double* G, const double* y, const double* regs, 
   for (int i = 0; i < n; ++i) { dd[i] = S.d[i]; ee[i] = S.e[i]; }
   std::vector<double> d(S.d, S.d + n), e(S.e, S.e + n), g(S.yv, S.yv + n), tau(S.tau, S.tau + n);
   int cap = n * n + 64;
-  std::vector<double> tc(cap), ts(cap);
+  std::vector<double> tcs(2 * (size_t)cap);
   std::vector<int32_t> ti(cap);
-  vi_tape tape{{tc.data(), 1}, {ts.data(), 1}, {ti.data(), 1}, cap};
+  vi_tape tape{{tcs.data(), 2}, {tcs.data() + 1, 2}, {ti.data(), 1}, cap};
   int32_t nr = 0;
-  int st = vi_tql(n, {d.data(), 1}, {e.data(), 1}, {g.data(), 1}, tape, &nr);
+  int st = vi_tql_values(n, {d.data(), 1}, {e.data(), 1}, tape, &nr);
   if (st != 0) return st;
+  vi_tape_apply_zt({g.data(), 1}, tape, nr);
   *rank = vi_spectral_divide(n, {d.data(), 1}, {g.data(), 1}, rcond);
   vi_tape_apply_z({g.data(), 1}, tape, nr);
   for (int i = 0; i < n; ++i) g[i] *= S.sc[0];

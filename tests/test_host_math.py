@@ -128,6 +128,13 @@ def test_tql_against_lapack(harness):
         assert rank.value == keep.sum()
         cond = np.abs(ev).max() / np.abs(ev[keep]).min()
         assert np.max(np.abs(w - ref)) <= 100 * EPS * cond * np.abs(ref).max()
+        # the variant the GPU runs: eigenvalues + tape, right-hand side through tape replays
+        w2 = np.zeros(n); lam2 = np.zeros(n)
+        st = harness.h_tql_values_solve(n, dptr(d), dptr(np.append(e, 0.0)), dptr(g0), C.c_double(EPS), dptr(w2),
+                                        dptr(lam2), C.byref(rank), C.byref(nrot))
+        assert st == 0 and rank.value == keep.sum()
+        assert np.allclose(np.sort(lam2), ev, rtol=0, atol=4 * EPS * np.abs(ev).max() * n)
+        assert np.max(np.abs(w2 - ref)) <= 100 * EPS * cond * np.abs(ref).max()
 
 
 def test_brentq_state_machine_replays_scipy(harness):

@@ -171,36 +171,36 @@ __device__ __forceinline__ vi_tape tape_of(const SysBuf& B, int64_t s) {
   return vi_tape{{cs, 2}, {cs + 1, 2}, {B.tix + s * (int64_t)B.tapecap, 1}, B.tapecap};
 }
 
-// QL proper, one THREAD per system.  d, e, g (3n doubles) sit on the dependency chain of every
-// rotation, so they live in shared memory laid out [i][thread] (a lane always hits its own bank pair
-// whatever i it is at).  Leaves u = L^+ Z^T Q^T y in B.g, the rotation tape in B.tcs/B.tix.
-__global__ void k_tql_smem(int64_t nsys, SysBuf B, double rcond) {
+// QL proper, one THREAD per system: eigenvalues + rotation tape (vi_tql_values).  d and e (2n doubles)
+// sit on the dependency chain of every rotation, so they live in shared memory laid out [i][thread]
+// (a lane always hits its own bank pair whatever i it is at).  Leaves the eigenvalues in B.d, the
+// tape in B.tcs / B.tix; the right-hand side is handled by k_apply.
+__global__ void k_tql_smem(int64_t nsys, SysBuf B) {
   extern __shared__ __align__(16) double sm[];
   const int T = blockDim.x, tid = threadIdx.x, n = B.n;
   const int64_t s = (int64_t)blockIdx.x * T + tid;
   if (s >= nsys) return;
   if (B.st[s] != VI_ST_OK) return;
-  vi_svec d{sm + tid, T}, e{sm + (size_t)n * T + tid, T}, g{sm + (size_t)2 * n * T + tid, T};
+  vi_svec d{sm + tid, T}, e{sm + (size_t)n * T + tid, T};
   const int64_t base = ileave(s, n);
   for (int i = 0; i < n; ++i) {
     d[i] = B.d[base + (int64_t)i * 32];
     e[i] = B.e[base + (int64_t)i * 32];
-    g[i] = B.g[base + (int64_t)i * 32];
   }
   int32_t nrot = 0;
-  const int q = vi_tql(n, d, e, g, tape_of(B, s), &nrot);
+  const int q = vi_tql_values(n, d, e, tape_of(B, s), &nrot);
   if (q != 0) { B.st[s] = VI_ST_NOCONV; return; }
-  B.rank[s] = vi_spectral_divide(n, d, g, rcond);
   B.nrot[s] = nrot;
-  for (int i = 0; i < n; ++i) B.g[base + (int64_t)i * 32] = g[i];
+  for (int i = 0; i < n; ++i) B.d[base + (int64_t)i * 32] = d[i];
 }
 
-// c = Q Z u, one WARP per system: the tape replay is a dependent chain (all lanes run it redundantly
-// on the warp's shared vector, tape entries arrive as broadcast loads fetched four ahead); the
-// reflectors are then applied cooperatively (coalesced V rows, shuffle-tree dot products).
+// c = Q Z L^+ Z^T (Q^T y), one WARP per system.  The two tape replays are dependent chains (all lanes
+// run them redundantly on the warp's shared vector; tape entries arrive as broadcast loads fetched four
+// ahead); the spectral cut-off (|l_i| > rcond max|l|: gelsd's rule) and the reflectors are applied
+// cooperatively (coalesced V rows, shuffle-tree dot products).
 constexpr int kApplyWarps = 8;
 __global__ void __launch_bounds__(kApplyWarps * 32)
-k_apply(int64_t nsys, SysBuf B, double* __restrict__ Cout, int32_t* __restrict__ rank_out) {
+k_apply(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, int32_t* __restrict__ rank_out) {
   extern __shared__ __align__(16) double sm[];
   const int n = B.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t s = (int64_t)blockIdx.x * kApplyWarps + warp;
@@ -218,9 +218,27 @@ k_apply(int64_t nsys, SysBuf B, double* __restrict__ Cout, int32_t* __restrict__
   const int64_t base = ileave(s, n);
   for (int i = lane; i < n; i += 32) w[i] = B.g[base + (int64_t)i * 32];
   __syncwarp();
-  vi_tape_apply_z(vi_svec{w, 1}, tape_of(B, s), B.nrot[s]);
+  const vi_tape tape = tape_of(B, s);
+  const int32_t nrot = B.nrot[s];
+  vi_tape_apply_zt(vi_svec{w, 1}, tape, nrot);
   __syncwarp();
-  const double scl = B.scl[s];
+  // truncated division by the eigenvalues
+  double lmax = 0.0;
+  for (int i = lane; i < n; i += 32) lmax = fmax(lmax, fabs(B.d[base + (int64_t)i * 32]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  const double cut = rcond * lmax, scl = B.scl[s];
+  int rank = 0;
+  for (int i = lane; i < n; i += 32) {
+    const double l = B.d[base + (int64_t)i * 32];
+    if (fabs(l) > cut) { w[i] = w[i] / l; ++rank; }
+    else w[i] = 0.0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+  __syncwarp();
+  vi_tape_apply_z(vi_svec{w, 1}, tape, nrot);
+  __syncwarp();
   for (int i = lane; i < n; i += 32) w[i] *= scl;
   __syncwarp();
   const double* V = B.V + s * (int64_t)n * n;
@@ -237,7 +255,7 @@ k_apply(int64_t nsys, SysBuf B, double* __restrict__ Cout, int32_t* __restrict__
     __syncwarp();
   }
   for (int i = lane; i < n; i += 32) Cs[i] = w[i];
-  if (lane == 0) rank_out[s] = B.rank[s];
+  if (lane == 0) rank_out[s] = rank;
 }
 
 // Fallback for orders whose vectors do not fit shared memory: everything in one thread per system
@@ -592,15 +610,15 @@ int run_systems(int64_t cnt, const double* G, const double* y, const double* reg
     VI_CUDA(cudaFuncSetAttribute(k_tridiag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
     VI_KERNEL(VI_K_TRIDIAG, s, k_tridiag<false><<<(unsigned)cnt, B.nt, B.smem, s>>>(G, y, regs, B));
   }
-  // threads per block for the shared-memory QL: as many as 3n doubles per thread allow (<= 64)
-  int T = (int)((227 * 1024) / ((size_t)3 * B.n * sizeof(double))) / 32 * 32;
-  if (T > 64) T = 64;
+  // threads per block for the shared-memory QL: as many as 2n doubles per thread allow (<= 96)
+  int T = (int)((227 * 1024) / ((size_t)2 * B.n * sizeof(double))) / 32 * 32;
+  if (T > 96) T = 96;
   if (T >= 32) {
-    size_t smem = (size_t)3 * B.n * T * sizeof(double);
+    size_t smem = (size_t)2 * B.n * T * sizeof(double);
     VI_CUDA(cudaFuncSetAttribute(k_tql_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VI_KERNEL(VI_K_TQL, s, k_tql_smem<<<blocks(cnt, T), T, smem, s>>>(cnt, B, rcond));
+    VI_KERNEL(VI_K_TQL, s, k_tql_smem<<<blocks(cnt, T), T, smem, s>>>(cnt, B));
     size_t smem2 = (size_t)kApplyWarps * B.n * sizeof(double);
-    VI_KERNEL(VI_K_TQL, s, k_apply<<<blocks(cnt, kApplyWarps), kApplyWarps * 32, smem2, s>>>(cnt, B, Cout, rank_out));
+    VI_KERNEL(VI_K_APPLY, s, k_apply<<<blocks(cnt, kApplyWarps), kApplyWarps * 32, smem2, s>>>(cnt, B, rcond, Cout, rank_out));
   } else {
     VI_KERNEL(VI_K_TQL, s, k_tql<<<blocks(cnt, 64), 64, 0, s>>>(cnt, B, rcond, Cout, rank_out));
   }

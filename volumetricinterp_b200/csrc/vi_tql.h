@@ -171,6 +171,151 @@ VI_HD int vi_tql(int n, vi_svec d, vi_svec e, vi_svec g, vi_tape tape, int32_t* 
   return status;
 }
 
+// Eigenvalues + rotation tape only (no right-hand side): the variant the GPU hot path runs, one
+// thread per system with d and e in shared memory.  Same algorithm and deflation rules as vi_tql
+// above; the differences are mechanical, to shorten the dependent chain and the instruction count of
+// the inner loop:
+//   * a block whose small end is at the top is physically reversed first (and reversed back at the
+//     end), so the loops index d/e directly instead of through the PD/PE view;
+//   * running pointers instead of index arithmetic; (c, s) stored as one pair;
+//   * Z^T g is NOT accumulated here - the tape is replayed forwards by the apply kernel.
+// tape.c / tape.s must be the two halves of interleaved (c, s) pairs (c.p + 1 == s.p, stride 2).
+VI_HD int vi_tql_values(int n, vi_svec d, vi_svec e, vi_tape tape, int32_t* nrot_out) {
+  int32_t nrot = 0;
+  int status = 0;
+  int budget = 30 * n;
+  const int64_t sd = d.stride, se = e.stride;
+  double* const cs = tape.c.p;        // pairs: cs[2t] = c, cs[2t+1] = s
+  int32_t* const ix = tape.ix.p;
+  const int32_t cap = tape.cap;
+  int l1 = 0;
+  while (l1 < n) {
+    int m = l1;
+    while (m < n - 1) {
+      double tst = fabs(e[m]);
+      if (tst == 0.0) break;
+      if (tst <= (sqrt(fabs(d[m])) * sqrt(fabs(d[m + 1]))) * VI_EPS_HALF) { e[m] = 0.0; break; }
+      ++m;
+    }
+    const int lo = l1, hi = m;
+    l1 = m + 1;
+    const int nb = hi - lo + 1;
+    if (nb == 1) continue;
+    double anorm = 0.0;
+    for (int i = lo; i <= hi; ++i) {
+      anorm = fmax(anorm, fabs(d[i]));
+      if (i < hi) anorm = fmax(anorm, fabs(e[i]));
+    }
+    if (anorm == 0.0) continue;
+    int ex;
+    frexp(anorm, &ex);
+    const double scl = ldexp(1.0, -ex), uns = ldexp(1.0, ex);
+    const bool rev = fabs(d[hi]) < fabs(d[lo]);
+    // scale, and lay the block out so that logical index 0 (where QL deflates) is the small end
+    if (!rev) {
+      for (int i = lo; i <= hi; ++i) { d[i] = d[i] * scl; if (i < hi) e[i] = e[i] * scl; }
+    } else {
+      for (int a = lo, b = hi; a <= b; ++a, --b) {
+        double da = d[a] * scl, db = d[b] * scl;
+        d[a] = db; if (a != b) d[b] = da;
+      }
+      for (int a = lo, b = hi - 1; a <= b; ++a, --b) {
+        double ea = e[a] * scl, eb = e[b] * scl;
+        e[a] = eb; if (a != b) e[b] = ea;
+      }
+    }
+    double* const D = d.p + (int64_t)lo * sd;     // D[i*sd], E[i*se]: logical i = 0..nb-1
+    double* const E = e.p + (int64_t)lo * se;
+    // physical index of logical i: lo + i (not reversed) or hi - i (reversed); partner = logical i+1
+    const int pbase = rev ? hi : lo;
+    const int pstep = rev ? -1 : 1;
+    for (int l = 0; l < nb; ++l) {
+      for (;;) {
+        int mm = l;
+        {
+          const double* dp = D + (int64_t)l * sd;
+          const double* ep = E + (int64_t)l * se;
+          double dcur = fabs(*dp);
+          while (mm < nb - 1) {
+            const double ev = *ep;
+            const double dnx = fabs(dp[sd]);
+            if (ev * ev <= (VI_EPS_HALF * VI_EPS_HALF * dcur) * dnx + VI_SAFMIN) break;
+            dcur = dnx; dp += sd; ep += se; ++mm;
+          }
+        }
+        if (mm < nb - 1) E[(int64_t)mm * se] = 0.0;
+        if (mm == l) break;
+        if (budget-- <= 0) { status = 1; goto done_block; }
+        const double el = E[(int64_t)l * se];
+        const double dl = D[(int64_t)l * sd];
+        double gg = (D[(int64_t)(l + 1) * sd] - dl) / (2.0 * el);
+        double r = sqrt(gg * gg + 1.0);
+        gg = D[(int64_t)mm * sd] - dl + el / (gg + vi_sign(r, gg));
+        double s = 1.0, c = 1.0, p = 0.0;
+        int i = mm - 1;
+        double* dp = D + (int64_t)i * sd;          // d[i]; dp[sd] = d[i+1]
+        double* ep = E + (int64_t)i * se;          // e[i]; ep[se] = e[i+1]
+        double dnext = dp[sd];                     // d[i+1], carried in a register between steps
+        bool early = false;
+        for (; i >= l; --i) {
+          const double ei = *ep;
+          const double f = s * ei, b = c * ei;
+          const double r2 = f * f + gg * gg;
+          if (r2 == 0.0) {
+            if (i + 1 < nb - 1) ep[se] = 0.0;
+            dp[sd] = dnext - p;
+            if (mm < nb - 1) E[(int64_t)mm * se] = 0.0;
+            early = true;
+            break;
+          }
+#if defined(__CUDA_ARCH__)
+          const double ri = rsqrt(r2);
+#else
+          const double ri = 1.0 / sqrt(r2);
+#endif
+          r = r2 * ri;
+          if (i + 1 < nb - 1) ep[se] = r;
+          s = f * ri;
+          c = gg * ri;
+          gg = dnext - p;
+          const double di = *dp;
+          r = (di - gg) * s + 2.0 * c * b;
+          p = s * r;
+          dp[sd] = gg + p;
+          gg = c * r - b;
+          dnext = di;
+          if (nrot < cap) {
+            cs[2 * (int64_t)nrot] = c;
+            cs[2 * (int64_t)nrot + 1] = s;
+            ix[nrot] = (pbase + pstep * i) * 2 + (rev ? 1 : 0);
+          } else {
+            status = 2;
+          }
+          ++nrot;
+          dp -= sd; ep -= se;
+        }
+        if (early) continue;
+        D[(int64_t)l * sd] = dnext - p;
+        E[(int64_t)l * se] = gg;
+        if (mm < nb - 1) E[(int64_t)mm * se] = 0.0;
+      }
+    }
+  done_block:
+    // unscale and restore the physical order
+    if (!rev) {
+      for (int i = lo; i <= hi; ++i) d[i] = d[i] * uns;
+    } else {
+      for (int a = lo, b = hi; a <= b; ++a, --b) {
+        double da = d[a] * uns, db = d[b] * uns;
+        d[a] = db; if (a != b) d[b] = da;
+      }
+    }
+    if (status == 1) break;
+  }
+  *nrot_out = nrot;
+  return status;
+}
+
 // w <- Z w  (replay the tape backwards).  The tape lives in global memory: four entries are fetched
 // ahead of the (dependent) updates of w so their latency overlaps.
 VI_HD void vi_tape_apply_z(vi_svec w, vi_tape tape, int32_t nrot) {
@@ -203,9 +348,27 @@ VI_HD void vi_tape_apply_z(vi_svec w, vi_tape tape, int32_t nrot) {
   }
 }
 
-// g <- Z^T g  (replay the tape forwards).
+// g <- Z^T g  (replay the tape forwards), four entries fetched ahead.
 VI_HD void vi_tape_apply_zt(vi_svec g, vi_tape tape, int32_t nrot) {
-  for (int32_t t = 0; t < nrot; ++t) {
+  int32_t t = 0;
+  for (; t + 3 < nrot; t += 4) {
+    int32_t code[4]; double c[4], s[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 4; ++q) { code[q] = tape.ix[t + q]; c[q] = tape.c[t + q]; s[q] = tape.s[t + q]; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 4; ++q) {
+      int pi = code[q] >> 1;
+      int pj = (code[q] & 1) ? pi - 1 : pi + 1;
+      double gi = g[pi], gj = g[pj];
+      g[pj] = s[q] * gi + c[q] * gj;
+      g[pi] = c[q] * gi - s[q] * gj;
+    }
+  }
+  for (; t < nrot; ++t) {
     int32_t code = tape.ix[t];
     int pi = code >> 1;
     int pj = (code & 1) ? pi - 1 : pi + 1;

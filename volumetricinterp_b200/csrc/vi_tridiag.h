@@ -126,7 +126,8 @@ VI_HD void vi_tri_load(const vi_tri_ws& S, int n, const double* G, const double*
 // Reduction proper.  V (global or host): (n x n) row j holds reflector j in columns j+1..n-1
 // (v[j+1] = 1 stored explicitly).  After the call S.d, S.e, S.tau, S.yv (= Q^T y) are final.
 // Per step: [every warp: column norm by warp-sum -> reflector] | [all: partial mat-vec] |
-// [warp 0: p, two dot products, w, rhs update] | [all: rank-2 update]  -> 4 CTA barriers.
+// [column owners: p, products] | [their warps: two dot products by warp-sum, w, rhs update] |
+// [all: rank-2 update]  -> 5 CTA barriers, no single-warp section.
 VI_HD void vi_tri_reduce(const vi_tri_ws& S, int n, double* V, int tid, int nt) {
   (void)tid;
   const int ng = (nt / n) < 1 ? 1 : (nt / n);
@@ -175,26 +176,25 @@ VI_HD void vi_tri_reduce(const vi_tri_ws& S, int n, double* V, int tid, int nt) 
         }
       }
     )
-    VI_WPHASE(
-      for (int c = lo + tid; c < n; c += 32) {
+    VI_PHASE(
+      if (tid >= lo && tid < n) {
         double p = 0.0;
-        for (int g = 0; g < ng; ++g) p += S.psum[g * n + c];
-        S.w[c] = tau * p;
+        for (int g = 0; g < ng; ++g) p += S.psum[g * n + tid];
+        p = tau * p;
+        const double vc = S.v[tid];
+        S.w[tid] = p;
+        S.red1[tid] = p * vc;
+        S.red2[tid] = vc * S.yv[tid];
       }
     )
-    VI_WPHASE(
-      double dot = vi_warp_sum(lo, n, tid, [&](int k) { return S.w[k] * S.v[k]; });
-      double dot2 = vi_warp_sum(lo, n, tid, [&](int k) { return S.v[k] * S.yv[k]; });
-      if (tid == 0) { S.sc[2] = dot; S.sc[3] = dot2; }
-    )
     VI_PHASE(
-      if (tid < 32) {
-        double a2 = -0.5 * tau * S.sc[2];
-        double t2 = tau * S.sc[3];
-        for (int c = lo + tid; c < n; c += 32) {
-          double vc = S.v[c];
-          S.w[c] = S.w[c] + a2 * vc;
-          S.yv[c] = S.yv[c] - t2 * vc;
+      if (tid < ((n + 31) & ~31)) {      // the warps that own an element: each forms both dot products itself
+        const double dot = vi_warp_sum(lo, n, tid & 31, [&](int k) { return S.red1[k]; });
+        const double dot2 = vi_warp_sum(lo, n, tid & 31, [&](int k) { return S.red2[k]; });
+        if (tid >= lo && tid < n) {
+          const double vc = S.v[tid];
+          S.w[tid] = S.w[tid] + (-0.5 * tau * dot) * vc;
+          S.yv[tid] = S.yv[tid] - (tau * dot2) * vc;
         }
       }
     )
