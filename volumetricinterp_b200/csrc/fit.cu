@@ -51,7 +51,7 @@ struct SysBuf {
   int n, nreg, tapecap, nt, use_gx, ld, nchunk;
   size_t smem;
   double *V, *d, *e, *g, *tau, *scl, *tcs, *lam, *Csys, *chi2, *chi2p, *Xg;
-  int32_t *tix, *st, *rec, *rank, *nrot;
+  int32_t *tix, *st, *rec, *rank, *nrot, *unit, *kidx;
 };
 
 constexpr int kChiGates = 1024;    // gates per CTA in k_chi2 (partial sums combined in fixed order)
@@ -91,6 +91,8 @@ void sysbuf_carve(Bump& b, SysBuf& S, int64_t cap, int n, int nreg, int P) {
   S.rec = b.take<int32_t>(cap);
   S.rank = b.take<int32_t>(cap);
   S.nrot = b.take<int32_t>(cap);
+  S.unit = b.take<int32_t>(cap);
+  S.kidx = b.take<int32_t>(cap);
   S.Xg = S.use_gx ? b.take<double>(cap * n * S.ld) : nullptr;
 }
 
@@ -102,6 +104,7 @@ struct UnitBuf {      // one search unit = (record, regulariser)
   int32_t* active;    // U
   int32_t* tabbad;    // U
   int32_t* kstar;     // U
+  int64_t* off;       // U + 1: exclusive prefix sum of the number of distinct table systems per unit
   int32_t* count;     // 1
 };
 
@@ -113,6 +116,7 @@ void unit_carve(Bump& b, UnitBuf& Ub, int64_t U) {
   Ub.active = b.take<int32_t>(U);
   Ub.tabbad = b.take<int32_t>(U);
   Ub.kstar = b.take<int32_t>(U);
+  Ub.off = b.take<int64_t>(U + 1);
   Ub.count = b.take<int32_t>(8);
 }
 
@@ -392,18 +396,55 @@ __global__ void k_chi2_sum(int64_t nsys, const int32_t* __restrict__ st, const d
 
 // ---- system set-up for the three phases ---------------------------------------------------
 // table phase: global system index t = u*VI_NALPHA + k, chunk covers [t0, t0 + cnt)
-__global__ void k_setup_table(int64_t t0, int64_t cnt, int nreg, const int32_t* __restrict__ npts,
-                              const double* __restrict__ pow10tab, const int32_t* __restrict__ kstar, int32_t* count, SysBuf B) {
+// Exclusive prefix sum of the distinct table systems per unit (min(kstar, NALPHA-1) + 1, or 0 for a unit
+// without valid gates): one block, each thread scans a contiguous slice.
+__global__ void __launch_bounds__(1024)
+k_table_offsets(int64_t U, int nreg, const int32_t* __restrict__ npts, const int32_t* __restrict__ kstar,
+                int64_t* __restrict__ off) {
+  __shared__ int64_t part[1024];
+  const int t = threadIdx.x;
+  const int64_t per = (U + 1023) / 1024;
+  const int64_t a = t * per, b = (a + per < U) ? a + per : U;
+  int64_t sum = 0;
+  for (int64_t u = a; u < b; ++u) {
+    int ks = kstar[u];
+    sum += (npts[u / nreg] > 0) ? ((ks < VI_NALPHA - 1 ? ks : VI_NALPHA - 1) + 1) : 0;
+  }
+  part[t] = sum;
+  __syncthreads();
+  if (t == 0) {
+    int64_t run = 0;
+    for (int i = 0; i < 1024; ++i) { int64_t v = part[i]; part[i] = run; run += v; }
+    off[U] = run;
+  }
+  __syncthreads();
+  int64_t run = part[t];
+  for (int64_t u = a; u < b; ++u) {
+    off[u] = run;
+    int ks = kstar[u];
+    run += (npts[u / nreg] > 0) ? ((ks < VI_NALPHA - 1 ? ks : VI_NALPHA - 1) + 1) : 0;
+  }
+}
+
+// table phase, compact numbering: system t in [0, off[U]) belongs to unit u = last unit with off[u] <= t,
+// k = t - off[u]; the chunk covers [t0, t0 + cnt)
+__global__ void k_setup_table(int64_t t0, int64_t cnt, int64_t U, int nreg, const double* __restrict__ pow10tab,
+                              const int64_t* __restrict__ off, SysBuf B) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= B.cap) return;
   if (s >= cnt) { B.rec[s] = kSkip; return; }
-  int64_t t = t0 + s;
-  int64_t u = t / VI_NALPHA;
-  int k = (int)(t - u * VI_NALPHA);
-  int r = (int)(u / nreg), q = (int)(u - (int64_t)r * nreg);
-  const bool use = (npts[r] > 0 && k <= kstar[u]);             // k > kstar: bit-identical to system kstar
-  B.rec[s] = use ? r : kSkip;
-  if (use) atomicAdd(count + 1, 1);
+  const int64_t t = t0 + s;
+  int64_t lo = 0, hi = U;              // off[lo] <= t < off[hi]
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (off[mid] <= t) lo = mid; else hi = mid;
+  }
+  const int64_t u = lo;
+  const int k = (int)(t - off[u]);
+  const int r = (int)(u / nreg), q = (int)(u - (int64_t)r * nreg);
+  B.rec[s] = r;
+  B.unit[s] = (int32_t)u;
+  B.kidx[s] = k;
   for (int i = 0; i < nreg; ++i) B.lam[s * nreg + i] = (i == q) ? pow10tab[k] : 0.0;
 }
 
@@ -450,13 +491,13 @@ __global__ void k_fill_table(int64_t U, const int32_t* __restrict__ kstar, UnitB
   for (int k = ks + 1; k < VI_NALPHA; ++k) Ub.table[u * VI_NALPHA + k] = v;
 }
 
-__global__ void k_scatter_table(int64_t t0, int64_t cnt, SysBuf B, UnitBuf Ub) {
+__global__ void k_scatter_table(int64_t cnt, SysBuf B, UnitBuf Ub) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= cnt) return;
-  int64_t t = t0 + s;
-  int64_t u = t / VI_NALPHA;
   int st = B.st[s];
   if (st == kSkip) return;
+  const int64_t u = B.unit[s];
+  const int64_t t = u * VI_NALPHA + B.kidx[s];
   if (st != VI_ST_OK) { atomicMax(&Ub.tabbad[u], st); Ub.table[t] = __longlong_as_double(0x7ff8000000000000LL); return; }
   Ub.table[t] = B.chi2[s];
 }
@@ -481,13 +522,12 @@ __global__ void k_bracket(int64_t U, int nreg, const int32_t* __restrict__ npts,
   Ub.active[u] = 1;
 }
 
-// Brent: advance units [u0, u0+cnt) to their next abscissa; system slot s = u - u0
+// Brent: advance units [u0, u0+cnt) to their next abscissa; units still searching get a compact system
+// slot (atomic counter: slot order is arbitrary, results do not depend on it)
 __global__ void k_brent_propose(int64_t u0, int64_t cnt, int nreg, SysBuf B, UnitBuf Ub) {
-  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= B.cap) return;
-  if (s >= cnt) { B.rec[s] = kSkip; return; }
-  int64_t u = u0 + s;
-  B.rec[s] = kSkip;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  int64_t u = u0 + i;
   if (!Ub.active[u]) return;
   vi_brent b = Ub.br[u];
   bool fin = vi_brent_propose(b);
@@ -498,17 +538,17 @@ __global__ void k_brent_propose(int64_t u0, int64_t cnt, int nreg, SysBuf B, Uni
     return;
   }
   int r = (int)(u / nreg), q = (int)(u - (int64_t)r * nreg);
+  const int64_t s = atomicAdd(Ub.count, 1);
   B.rec[s] = r;
+  B.unit[s] = (int32_t)u;
   const double lamv = exp10(b.xcur);   // np.power(10., alpha), interpolate.py:250
-  for (int i = 0; i < nreg; ++i) B.lam[s * nreg + i] = (i == q) ? lamv : 0.0;
-  atomicAdd(Ub.count, 1);
+  for (int k = 0; k < nreg; ++k) B.lam[s * nreg + k] = (k == q) ? lamv : 0.0;
 }
 
-__global__ void k_brent_feed(int64_t u0, int64_t cnt, SysBuf B, UnitBuf Ub) {
+__global__ void k_brent_feed(int64_t cnt, SysBuf B, UnitBuf Ub) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= cnt) return;
-  int64_t u = u0 + s;
-  if (!Ub.active[u] || B.rec[s] < 0) return;
+  int64_t u = B.unit[s];
   int st = B.st[s];
   if (st != VI_ST_OK) { Ub.active[u] = 0; Ub.status[u] = (st == VI_ST_NONFINITE) ? VI_ST_NONFINITE : VI_ST_NOCONV; return; }
   double f = B.chi2[s] - Ub.nu[u];
@@ -730,53 +770,39 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
     VI_CUDA(cudaMemsetAsync(Ub.count, 0, 8 * sizeof(int32_t), st));
     // ---- phase 1: chi2(10^-k) table for every unit -------------------------------------
     VI_KERNEL(VI_K_MISC, st, k_kstar<<<(unsigned)U, 256, 0, st>>>(nreg, N, G, regmats, pow10tab, Ub.kstar));
-    const int64_t T = U * VI_NALPHA;
+    VI_KERNEL(VI_K_MISC, st, k_table_offsets<<<1, 1024, 0, st>>>(U, nreg, npts, Ub.kstar, Ub.off));
+    int64_t T = 0;
+    VI_CUDA(cudaMemcpyAsync(&T, Ub.off + U, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    VI_CUDA(cudaStreamSynchronize(st));
     for (int64_t t0 = 0; t0 < T; t0 += cap) {
       int64_t cnt = (T - t0 < cap) ? T - t0 : cap;
-      VI_KERNEL(VI_K_MISC, st, k_setup_table<<<blocks(cap, 256), 256, 0, st>>>(t0, cnt, nreg, npts, pow10tab, Ub.kstar, Ub.count, B));
-      VI_LAUNCH_CHECK();
+      VI_KERNEL(VI_K_MISC, st, k_setup_table<<<blocks(cap, 256), 256, 0, st>>>(t0, cnt, U, nreg, pow10tab, Ub.off, B));
       if (int rc = run_systems(cnt, G, y, regmats, B, rcond, B.Csys, B.rank, st)) return rc;
       if (int rc = run_chi2(cnt, At, Wm, bm, P, B, B.Csys, B.chi2, st)) return rc;
-      VI_KERNEL(VI_K_MISC, st, k_scatter_table<<<blocks(cnt, 256), 256, 0, st>>>(t0, cnt, B, Ub));
-      VI_LAUNCH_CHECK();
+      VI_KERNEL(VI_K_MISC, st, k_scatter_table<<<blocks(cnt, 256), 256, 0, st>>>(cnt, B, Ub));
     }
+    solved += T;
     VI_KERNEL(VI_K_MISC, st, k_fill_table<<<blocks(U, 128), 128, 0, st>>>(U, Ub.kstar, Ub));
-    {
-      int h_tab = 0;
-      VI_CUDA(cudaMemcpyAsync(&h_tab, Ub.count + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-      VI_CUDA(cudaStreamSynchronize(st));
-      solved += h_tab;
-    }
     // ---- phase 2: bracket + Brent in lock step ------------------------------------------
     VI_KERNEL(VI_K_MISC, st, k_bracket<<<blocks(U, 128), 128, 0, st>>>(U, nreg, npts, Ub));
     VI_LAUNCH_CHECK();
     for (int it = 0; it < VI_BRENT_MAXITER + 2; ++it) {
-      VI_CUDA(cudaMemsetAsync(Ub.count, 0, sizeof(int32_t), st));
-      int h_count_total = 0;
+      int64_t round_total = 0;
       for (int64_t u0 = 0; u0 < U; u0 += cap) {
         int64_t cnt = (U - u0 < cap) ? U - u0 : cap;
-        VI_KERNEL(VI_K_MISC, st, k_brent_propose<<<blocks(cap, 128), 128, 0, st>>>(u0, cnt, nreg, B, Ub));
-        VI_LAUNCH_CHECK();
-        if (U > cap) {
-          // several chunks: finish this chunk before its slots are reused
-          if (int rc = run_systems(cnt, G, y, regmats, B, rcond, B.Csys, B.rank, st)) return rc;
-          if (int rc = run_chi2(cnt, At, Wm, bm, P, B, B.Csys, B.chi2, st)) return rc;
-          VI_KERNEL(VI_K_MISC, st, k_brent_feed<<<blocks(cnt, 128), 128, 0, st>>>(u0, cnt, B, Ub));
-          VI_LAUNCH_CHECK();
-        }
+        VI_CUDA(cudaMemsetAsync(Ub.count, 0, sizeof(int32_t), st));
+        VI_KERNEL(VI_K_MISC, st, k_brent_propose<<<blocks(cnt, 128), 128, 0, st>>>(u0, cnt, nreg, B, Ub));
+        int h_count = 0;
+        VI_CUDA(cudaMemcpyAsync(&h_count, Ub.count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        VI_CUDA(cudaStreamSynchronize(st));
+        if (h_count == 0) continue;
+        round_total += h_count;
+        if (int rc = run_systems(h_count, G, y, regmats, B, rcond, B.Csys, B.rank, st)) return rc;
+        if (int rc = run_chi2(h_count, At, Wm, bm, P, B, B.Csys, B.chi2, st)) return rc;
+        VI_KERNEL(VI_K_MISC, st, k_brent_feed<<<blocks(h_count, 128), 128, 0, st>>>(h_count, B, Ub));
       }
-      int h_count = 0;
-      VI_CUDA(cudaMemcpyAsync(&h_count, Ub.count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-      VI_CUDA(cudaStreamSynchronize(st));
-      h_count_total = h_count;
-      if (h_count_total == 0) break;
-      solved += h_count_total;
-      if (U <= cap) {
-        if (int rc = run_systems(U, G, y, regmats, B, rcond, B.Csys, B.rank, st)) return rc;
-        if (int rc = run_chi2(U, At, Wm, bm, P, B, B.Csys, B.chi2, st)) return rc;
-        VI_KERNEL(VI_K_MISC, st, k_brent_feed<<<blocks(U, 128), 128, 0, st>>>(0, U, B, Ub));
-        VI_LAUNCH_CHECK();
-      }
+      if (round_total == 0) break;
+      solved += round_total;
     }
   }
   // ---- phase 3: final solve with the found parameters (interpolate.py:566-569) -----------
