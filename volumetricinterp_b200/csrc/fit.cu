@@ -96,6 +96,8 @@ void sysbuf_carve(Bump& b, SysBuf& S, int64_t cap, int n, int nreg, int P) {
   S.Xg = S.use_gx ? b.take<double>(cap * n * S.ld) : nullptr;
 }
 
+constexpr int kCovChunk = 512;     // records whose eigenvector / H / T scratch is held at once
+
 struct UnitBuf {      // one search unit = (record, regulariser)
   double* table;      // U x VI_NALPHA
   vi_brent* br;       // U
@@ -118,6 +120,11 @@ void unit_carve(Bump& b, UnitBuf& Ub, int64_t U) {
   Ub.kstar = b.take<int32_t>(U);
   Ub.off = b.take<int64_t>(U + 1);
   Ub.count = b.take<int32_t>(8);
+}
+
+int64_t cov_scratch_bytes(int64_t R, int n) {
+  int64_t cc = R < kCovChunk ? R : kCovChunk;
+  return (3 * cc * (int64_t)n * n + cc * n) * (int64_t)sizeof(double) + 4096;
 }
 
 int64_t per_system_bytes(int n, int nreg, int P) {
@@ -260,6 +267,104 @@ k_apply(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, int32_t
   }
   for (int i = lane; i < n; i += 32) Cs[i] = w[i];
   if (lane == 0) rank_out[s] = rank;
+}
+
+// ---- covariance: dC = H (A^T W A) H, H = pinv(X)  (interpolate.py:464-467) ---------------------
+// scipy.linalg.pinv keeps singular values above max(M,N)*eps*s_max; for the symmetrised X that is
+// |eigenvalue| > N*eps*max|eigenvalue|.  The eigenvectors E = Q Z are formed once per record:
+// thread i owns column i of Z in shared memory and replays the rotation tape on it (all threads run
+// the same rotation sequence: uniform control flow, tape entries are broadcast loads), then applies the
+// reflectors.  H = E diag(scl/lambda) E^T, T = H G and dC = T H are three batched N x N products.
+__global__ void k_eigvec(int64_t s0, SysBuf B, double pinv_rtol, double* __restrict__ E, double* __restrict__ dinv) {
+  extern __shared__ __align__(16) double sm[];
+  const int n = B.n, i = threadIdx.x, ld = B.ld;
+  const int64_t s = s0 + blockIdx.x;
+  if (B.st[s] != VI_ST_OK || B.rec[s] < 0) return;
+  const int64_t base = ileave(s, n);
+  if (i < n) {
+    for (int r = 0; r < n; ++r) sm[r * ld + i] = (r == i) ? 1.0 : 0.0;
+    vi_tape_apply_z(vi_svec{sm + i, ld}, tape_of(B, s), B.nrot[s]);
+    vi_tri_backtransform(n, B.V + s * (int64_t)n * n, B.tau + base, 32, sm + i, ld);
+    double* Es = E + (int64_t)blockIdx.x * n * n;
+    for (int r = 0; r < n; ++r) Es[(int64_t)r * n + i] = sm[r * ld + i];
+    double lmax = 0.0;
+    for (int m = 0; m < n; ++m) lmax = fmax(lmax, fabs(B.d[base + (int64_t)m * 32]));
+    const double l = B.d[base + (int64_t)i * 32];
+    dinv[(int64_t)blockIdx.x * n + i] = (fabs(l) > pinv_rtol * lmax) ? B.scl[s] / l : 0.0;
+  }
+}
+
+// C[b] = A[b] diag(sc[b]) op(B[b]), all n x n row-major; BT: op(B) = B^T.  64 x 64 tile per CTA, 4 x 4 per thread.
+template <bool BT>
+__global__ void __launch_bounds__(256)
+k_bgemm(const double* __restrict__ A, int64_t strideA, const double* __restrict__ Bm, int64_t strideB,
+        const int32_t* __restrict__ recB, const double* __restrict__ sc, double* __restrict__ C, int64_t strideC, int n) {
+  __shared__ double As[16][65];
+  __shared__ double Bs[16][65];
+  const int b = blockIdx.z;
+  const double* Ab = A + b * strideA;
+  const double* Bb = Bm + (recB ? (int64_t)recB[b] : (int64_t)b) * strideB;
+  if (recB && recB[b] < 0) return;
+  const int i0 = blockIdx.y * 64, k0 = blockIdx.x * 64;
+  const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.0;
+  for (int m0 = 0; m0 < n; m0 += 16) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < 1024; e += 256) {
+      int ii = e / 16, mm = e % 16;
+      double v = 0.0;
+      if (i0 + ii < n && m0 + mm < n) {
+        v = Ab[(int64_t)(i0 + ii) * n + m0 + mm];
+        if (sc) v *= sc[(int64_t)b * n + m0 + mm];
+      }
+      As[mm][ii] = v;
+      double w = 0.0;
+      if (BT) {
+        if (k0 + ii < n && m0 + mm < n) w = Bb[(int64_t)(k0 + ii) * n + m0 + mm];
+        Bs[mm][ii] = w;
+      } else {
+        int mm2 = e / 64, kk = e % 64;
+        if (m0 + mm2 < n && k0 + kk < n) w = Bb[(int64_t)(m0 + mm2) * n + k0 + kk];
+        Bs[mm2][kk] = w;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int mm = 0; mm < 16; ++mm) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) af[a] = As[mm][ty + 16 * a];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) bf[c] = Bs[mm][tx + 16 * c];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = fma(af[a], bf[c], acc[a][c]);
+    }
+  }
+  double* Cb = C + b * strideC;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    int i = i0 + ty + 16 * a;
+    if (i >= n) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      int k = k0 + tx + 16 * c;
+      if (k < n) Cb[(int64_t)i * n + k] = acc[a][c];
+    }
+  }
+}
+
+__global__ void k_cov_nan(int64_t s0, int64_t r0, int n, SysBuf B, double* __restrict__ dC) {
+  const int64_t s = s0 + blockIdx.x;
+  if (B.st[s] == VI_ST_OK && B.rec[s] >= 0) return;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  double* out = dC + (r0 + s) * (int64_t)n * n;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) out[e] = nan;
 }
 
 // Fallback for orders whose vectors do not fit shared memory: everything in one thread per system
@@ -689,17 +794,17 @@ extern "C" int vi_fit_workspace_bytes(int32_t R, int32_t P, int32_t N, int32_t n
   UnitBuf Ub;
   unit_carve(b, Ub, U);
   b.take<double>(VI_NALPHA);
-  *bytes = b.off + per_system_bytes(N, nreg, P) * (cap + 32) + 16384;
+  *bytes = b.off + per_system_bytes(N, nreg, P) * (cap + 32) + 16384 + cov_scratch_bytes(R, N);
   return VI_OK;
 }
 
 // cap actually available inside a given workspace
-static int64_t cap_for_workspace(int64_t ws_bytes, int64_t U, int n, int nreg, int P) {
+static int64_t cap_for_workspace(int64_t ws_bytes, int64_t U, int n, int nreg, int P, int64_t Rcov) {
   Bump b{nullptr, 0, 0};
   UnitBuf Ub;
   unit_carve(b, Ub, U);
   b.take<double>(VI_NALPHA);
-  int64_t left = ws_bytes - b.off - 8192;
+  int64_t left = ws_bytes - b.off - 8192 - (Rcov > 0 ? cov_scratch_bytes(Rcov, n) : 0);
   int64_t per = per_system_bytes(n, nreg, P);
   int64_t cap = left / per;
   cap = cap / 32 * 32;
@@ -715,7 +820,7 @@ extern "C" int vi_solve_batched(const double* G, const double* y, const int32_t*
   VI_REQUIRE(nreg == 0 || (regmats && lam), "regmats/lam missing");
   if (S == 0) return VI_OK;
   cudaStream_t st = vi_stream(stream);
-  int64_t cap = cap_for_workspace(workspace_bytes, 0, N, nreg, 1);
+  int64_t cap = cap_for_workspace(workspace_bytes, 0, N, nreg, 1, 0);
   if (cap < 32) { vi_set_error("workspace too small (%lld bytes)", (long long)workspace_bytes); return VI_EWORKSPACE; }
   if (cap > vi_align_up(S, 32)) cap = vi_align_up(S, 32);
   Bump b{reinterpret_cast<char*>(workspace), 0, workspace_bytes};
@@ -742,7 +847,10 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
   VI_REQUIRE(R >= 0 && P >= 1 && N >= 1 && N <= 1024 && nreg >= 0, "bad shape");
   VI_REQUIRE(method == VI_METHOD_NONE || method == VI_METHOD_CHI2, "unknown method %d", method);
   VI_REQUIRE(method == VI_METHOD_NONE || (nreg >= 1 && regmats && lam), "chi2 method needs regularisation matrices");
-  if (dC != nullptr) { vi_set_error("covariance output not available in this build"); return VI_EUNSUPPORTED; }
+  if (dC != nullptr && N > VI_NMAX_SMEM) {
+    vi_set_error("covariance output needs nbasis <= %d (got %d)", VI_NMAX_SMEM, N);
+    return VI_EUNSUPPORTED;
+  }
   if (nsolve) *nsolve = 0;
   if (R == 0) return VI_OK;
   if (method == VI_METHOD_NONE) nreg = 0;
@@ -750,7 +858,7 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
   const double rcond = VI_EPS;
   const int64_t U = (int64_t)R * (nreg > 0 ? nreg : 1);
 
-  int64_t cap = cap_for_workspace(workspace_bytes, U, N, nreg, P);
+  int64_t cap = cap_for_workspace(workspace_bytes, U, N, nreg, P, R);
   if (cap < 32) { vi_set_error("workspace too small (%lld bytes)", (long long)workspace_bytes); return VI_EWORKSPACE; }
   int64_t most = vi_align_up(method == VI_METHOD_CHI2 ? U * VI_NALPHA : (int64_t)R, 32);
   if (cap > most) cap = most;
@@ -758,6 +866,11 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
   UnitBuf Ub;
   unit_carve(b, Ub, U);
   double* pow10tab = b.take<double>(VI_NALPHA);
+  const int64_t cc = R < kCovChunk ? R : kCovChunk;
+  double* covE = b.take<double>(cc * (int64_t)N * N);
+  double* covH = b.take<double>(cc * (int64_t)N * N);
+  double* covT = b.take<double>(cc * (int64_t)N * N);
+  double* covD = b.take<double>(cc * (int64_t)N);
   SysBuf B;
   sysbuf_carve(b, B, cap, N, nreg, P);
   int64_t solved = 0;
@@ -812,6 +925,22 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
     VI_LAUNCH_CHECK();
     if (int rc = run_systems(cnt, G, y, regmats, B, rcond, C + r0 * N, B.rank, st)) return rc;
     if (int rc = run_chi2(cnt, At, Wm, bm, P, B, C + r0 * N, B.chi2, st)) return rc;
+    if (dC != nullptr) {
+      const int64_t NN = (int64_t)N * N;
+      const size_t smem_e = (size_t)N * B.ld * sizeof(double);
+      VI_CUDA(cudaFuncSetAttribute(k_eigvec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+      const unsigned tiles = (unsigned)((N + 63) / 64);
+      for (int64_t c0 = 0; c0 < cnt; c0 += cc) {
+        const int64_t nc = (cnt - c0 < cc) ? cnt - c0 : cc;
+        VI_CUDA(cudaMemsetAsync(covD, 0, nc * N * sizeof(double), st));
+        VI_KERNEL(VI_K_COV, st, k_eigvec<<<(unsigned)nc, (N + 31) / 32 * 32, smem_e, st>>>(c0, B, (double)N * VI_EPS, covE, covD));
+        dim3 grid(tiles, tiles, (unsigned)nc);
+        VI_KERNEL(VI_K_COV, st, k_bgemm<true><<<grid, 256, 0, st>>>(covE, NN, covE, NN, nullptr, covD, covH, NN, N));
+        VI_KERNEL(VI_K_COV, st, k_bgemm<false><<<grid, 256, 0, st>>>(covH, NN, G, NN, B.rec + c0, nullptr, covT, NN, N));
+        VI_KERNEL(VI_K_COV, st, k_bgemm<false><<<grid, 256, 0, st>>>(covT, NN, covH, NN, nullptr, nullptr, dC + (r0 + c0) * NN, NN, N));
+        VI_KERNEL(VI_K_COV, st, k_cov_nan<<<(unsigned)nc, 256, 0, st>>>(c0, r0, N, B, dC));
+      }
+    }
     VI_KERNEL(VI_K_MISC, st, k_finalize<<<(unsigned)cnt, 64, 0, st>>>(r0, cnt, N, B, C, chi2, rank, status));
     VI_LAUNCH_CHECK();
     solved += cnt;
@@ -826,7 +955,6 @@ extern "C" int vi_fit_host(const double* A, const double* value, const double* e
                            int32_t* status) {
   VI_REQUIRE(A && value && error && C && chi2 && rank && status, "NULL argument");
   VI_REQUIRE(R >= 0 && P >= 1 && N >= 1, "bad shape");
-  if (dC != nullptr) { vi_set_error("covariance output not available in this build"); return VI_EUNSUPPORTED; }
   if (R == 0) return VI_OK;
   cudaStream_t s = nullptr;
   int64_t ws_bytes = 0;
@@ -851,6 +979,7 @@ extern "C" int vi_fit_host(const double* A, const double* value, const double* e
   double* dy = (double*)dalloc((size_t)R * N * 8);
   double* dreg = (double*)dalloc((size_t)(nreg > 0 ? nreg : 1) * NN * 8);
   double* dC_ = (double*)dalloc((size_t)R * N * 8);
+  double* ddC = dC ? (double*)dalloc((size_t)R * NN * 8) : nullptr;
   double* dchi = (double*)dalloc((size_t)R * 8);
   double* dlam = (double*)dalloc((size_t)R * (nreg > 0 ? nreg : 1) * 8);
   int32_t* dnp = (int32_t*)dalloc((size_t)R * 4);
@@ -858,7 +987,7 @@ extern "C" int vi_fit_host(const double* A, const double* value, const double* e
   int32_t* dst = (int32_t*)dalloc((size_t)R * 4);
   void* ws = dalloc((size_t)ws_bytes);
   if (!dA || !dAt || !dval || !derr || !dWm || !dbm || !dG || !dy || !dreg || !dC_ || !dchi || !dlam || !dnp ||
-      !drank || !dst || !ws || (weight && !dwt)) {
+      !drank || !dst || !ws || (weight && !dwt) || (dC && !ddC)) {
     cleanup();
     vi_set_error("cudaMalloc failed (workspace %lld bytes)", (long long)ws_bytes);
     return VI_ECUDA;
@@ -875,9 +1004,10 @@ extern "C" int vi_fit_host(const double* A, const double* value, const double* e
     rc = vi_normal_eq_batched(dA, dval, derr, dwt, R, P, N, ne_mode, dG, dy, nullptr, dnp, dWm, dbm, s);
   }
   if (rc == VI_OK)
-    rc = vi_fit_batched(dAt, dWm, dbm, dG, dy, dnp, R, P, N, dreg, nreg, method, dC_, nullptr, dchi, dlam, drank, dst,
+    rc = vi_fit_batched(dAt, dWm, dbm, dG, dy, dnp, R, P, N, dreg, nreg, method, dC_, ddC, dchi, dlam, drank, dst,
                         nullptr, ws, ws_bytes, s);
   VI_TRY(cudaMemcpyAsync(C, dC_, (size_t)R * N * 8, cudaMemcpyDeviceToHost, s));
+  if (dC) VI_TRY(cudaMemcpyAsync(dC, ddC, (size_t)R * NN * 8, cudaMemcpyDeviceToHost, s));
   VI_TRY(cudaMemcpyAsync(chi2, dchi, (size_t)R * 8, cudaMemcpyDeviceToHost, s));
   if (lam && nreg > 0) VI_TRY(cudaMemcpyAsync(lam, dlam, (size_t)R * nreg * 8, cudaMemcpyDeviceToHost, s));
   VI_TRY(cudaMemcpyAsync(rank, drank, (size_t)R * 4, cudaMemcpyDeviceToHost, s));
