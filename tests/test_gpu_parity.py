@@ -366,3 +366,108 @@ def test_estimate_many_records_paths_agree(cuda):
     for r in (0, 7, 19):
         one = est.evaluate_device(_t(cuda, C[r:r + 1]), la, lo, al).cpu().numpy()[0]
         assert np.allclose(big[r], one, rtol=1e-12, atol=0, equal_nan=True)
+
+
+# ------------------------------------------------------------------ literal drop-in path: CLI -> file -> Estimate
+def test_cli_file_roundtrip_and_estimate(cuda, tmp_path):
+    """`volumetricinterp config.ini` on a synthetic AMISR file, then Estimate(file)(time, lat, lon, alt):
+    every stage checked against the oracle run on the same file contents."""
+    import datetime as dt
+    from test_io_cli import _config
+    from volumetricinterp_b200 import Estimate, h5lite, synth
+    from volumetricinterp_b200 import run_volumetricinterp as cli
+    om = rp.SphHarmLag(2, 2, 10, 78, 262)
+    fn_in, fn_out = str(tmp_path / "amisr.h5"), str(tmp_path / "coeffs.h5")
+    arrays = synth.write_amisr_file(fn_in, 7, 30, 5, A_of=om.basis, seed=21, noise_scale=0.85)
+    cfg = _config(tmp_path, fn_in, fn_out)
+    assert cli.main([cfg]) == 0
+    # oracle on the same inputs
+    lat, lon, alt, value, error = rp.quality_filter(
+        arrays["/Geomag/Latitude"], arrays["/Geomag/Longitude"], arrays["/Geomag/Altitude"], arrays["/FittedParams/Ne"],
+        arrays["/FittedParams/dNe"], arrays["/FittedParams/FitInfo/chi2"], arrays["/FittedParams/FitInfo/fitcode"],
+        [1e10, 1e13], [0.1, 10.0], [1, 2, 3, 4])
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        omega = om.omega()
+    Cref, dCref, c2ref, lamref = rp.fit_records(om, lat, lon, alt, value, error, {"curvature": omega}, ["curvature"])
+    with h5lite.File(fn_out) as h5:
+        assert h5.keys("/") == ["Coeffs", "ConfigFile", "FitParams", "RawData", "UnixTime"]
+        C, dC, chi2 = h5["/Coeffs/C"], h5["/Coeffs/dC"], h5["/FitParams/chi2"]
+        assert np.array_equal(h5["/UnixTime"], arrays["/Time/UnixTime"])
+        assert list(h5["/FitParams/reglist"]) == [b"curvature"] and h5["/FitParams/regmethod"] == b"chi2"
+        assert np.array_equal(h5["/FitParams/hull_vert"], rp.hull_vertices(lat, lon, alt))
+        assert h5["/RawData/filename"] == fn_in.encode()
+        assert h5["/ConfigFile/Contents"].decode() == open(cfg).read()
+    nanref = np.isnan(Cref).all(axis=1)
+    assert np.array_equal(np.isnan(C).all(axis=1), nanref) and C.shape == Cref.shape and dC.shape == dCref.shape
+    for r in np.nonzero(~nanref)[0]:
+        if lamref[r, 0] == 0:
+            continue
+        assert np.max(np.abs(C[r] - Cref[r])) <= 5e-8 * np.abs(Cref[r]).max()
+        assert abs(chi2[r] - c2ref[r]) <= 1e-6 * c2ref[r]
+    # Estimate from the file, nearest record, hull mask on
+    est = Estimate(fn_out)
+    r = int(np.nonzero(~nanref)[0][0])
+    when = dt.datetime.utcfromtimestamp(0) + dt.timedelta(seconds=float(arrays["/Time/UnixTime"][r].mean()))
+    rng = np.random.default_rng(5)
+    qlat = rng.uniform(lat.min() + 0.3, lat.max() - 0.3, (4, 8))
+    qlon = rng.uniform(lon.min() + 1.0, lon.max() - 1.0, (4, 8))
+    qalt = rng.uniform(150e3, 600e3, (4, 8))
+    out = est(when, qlat, qlon, qalt)
+    ref = rp.estimate(om, C[r], rp.hull_vertices(lat, lon, alt), qlat, qlon, qalt)
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    ok = np.isfinite(ref)
+    assert ok.any() and np.max(np.abs(out[ok] - ref[ok]) / np.abs(ref[ok])) < 1e-8
+    # --validate fits only the [VALIDATE] window (validate.py:53-61): records fully inside 22:46..22:49
+    assert cli.main(["--validate", cfg]) == 0
+    with h5lite.File(fn_out) as h5:
+        ut = h5["/UnixTime"]
+        assert ut.shape[0] == 3 and h5["/Coeffs/C"].shape[0] == 3
+
+
+# ------------------------------------------------------------------ size-independent properties at bench scale
+def test_properties_at_full_gate_count(cuda):
+    """51 x 100 gates (BASELINE configs[1] geometry), a few hundred records: properties the domain
+    offers without an oracle run: G symmetric PSD on valid gates, linearity of y in the data, record
+    independence (a record's result does not depend on its batch), scaling invariance of lambda."""
+    import torch
+    import bench
+    from volumetricinterp_b200 import _native, fit
+    from volumetricinterp_b200.models import sphharmlag
+    model = sphharmlag.Model(io.StringIO(bench.config_text()))
+    lat, lon, alt = bench.make_geometry(seed=100)
+    la, lo, al = (_t(cuda, a) for a in (lat, lon, alt))
+    P, N = len(lat), model.nbasis
+    A = torch.empty((P, N), dtype=torch.float64, device=cuda)
+    At = torch.empty((N, P), dtype=torch.float64, device=cuda)
+    model.basis_device(la, lo, al, out=A, out_t=At)
+    R = 96
+    value, error = bench.make_workload(A.cpu().numpy(), R, seed=7)
+    v, e = _t(cuda, value), _t(cuda, error)
+    G, y, sw, npts, Wm, bm = fit.normal_equations_device(A, v, e, None, _native.NE_FAST)
+    Gs, ys, *_ = fit.normal_equations_device(A, v, e, None, _native.NE_STRICT)
+    assert torch.equal(G, G.transpose(1, 2))
+    assert torch.max(torch.abs(G - Gs)) <= 1e-13 * torch.max(torch.abs(Gs))
+    assert int(npts.sum()) == int(np.isfinite(value).sum())
+    # linearity: y(2 v) = 2 y(v), G unchanged
+    G2, y2, *_ = fit.normal_equations_device(A, 2.0 * v, e, None, _native.NE_FAST)
+    assert torch.equal(G2, G) and torch.equal(y2, 2.0 * y)
+    # chi2 of the fitted densities recomputed from C with torch: sum W (A C - b)^2
+    omega = bench.curvature_matrix()
+    regs = _t(cuda, omega[None])
+    Cf, dC, chi2, lam, rank, status, nsolve = fit.fit_batch_device(At, Wm, bm, G, y, npts, regs, _native.METHOD_CHI2)
+    okrec = (status == 0) | (status == 1)
+    resid = (Cf[okrec] @ At - bm[okrec]) ** 2 * Wm[okrec]
+    assert torch.allclose(resid.sum(1), chi2[okrec], rtol=1e-9, atol=0)
+    assert torch.isnan(Cf[~okrec]).all() and torch.isnan(chi2[~okrec]).all()
+    # found lambdas satisfy chi2 = nu for one of the reference's scale factors (sign-change tolerance)
+    ratio = (chi2[status == 0] / npts[status == 0]).cpu().numpy()
+    assert (np.min(np.abs(ratio[:, None] - np.array([0.6, 0.7, 0.8, 0.9, 1.0])[None, :]), axis=1) < 2e-2).all()
+    # record independence: refit a sub-batch in another order
+    idx = torch.tensor([5, 3, 90, 41], device=cuda)
+    Cs, _, chi2s, lams, _, sts, _ = fit.fit_batch_device(At, Wm[idx].contiguous(), bm[idx].contiguous(),
+                                                         G[idx].contiguous(), y[idx].contiguous(),
+                                                         npts[idx].contiguous(), regs, _native.METHOD_CHI2)
+    assert torch.equal(Cs, Cf[idx]) or torch.allclose(Cs, Cf[idx], rtol=0, atol=0, equal_nan=True)
+    assert torch.equal(sts, status[idx])

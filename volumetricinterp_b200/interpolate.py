@@ -174,7 +174,10 @@ class Interpolate(object):
                 m = {'O': 16, 'O2': 32, 'NO': 30, 'N2': 28, 'N': 14}[ion]
                 i = {'frac': 0, 'temp': 1, 'colfreq': 2}[kind]
                 mass = h5['/FittedParams/IonMass']
-                mi = int(np.argwhere(mass == m).flatten()[0])
+                try:
+                    mi = int(np.where(mass == m)[0][0])
+                except IndexError:
+                    mi = -1            # reference falls back to the last species (interpolate.py:626-629)
                 val = h5['/FittedParams/Fits'][:, :, :, mi, i]
                 err = h5['/FittedParams/Errors'][:, :, :, mi, i]
         lat, lon, alt, value, error = self.quality_filter(lat, lon, alt, val, err, c2, fc)

@@ -136,3 +136,35 @@ def flatten_valid(lat, lon, alt):
     la, lo, al = lat.ravel(), lon.ravel(), alt.ravel()
     keep = np.isfinite(al)
     return la[keep], lo[keep], al[keep], keep
+
+
+def write_amisr_file(filename, nbeams, ngates, nrecords, A_of=None, seed=0, noise_scale=1.0):
+    """Write a synthetic AMISR fitted file with the layout `Interpolate.read_datafile` expects
+    (reference interpolate.py:605-632).  `A_of(lat, lon, alt) -> (P, N)` is the
+    design-matrix evaluator used to generate the densities (GPU kernel or oracle, caller's choice).
+    Returns the arrays written (for tests)."""
+    from . import h5lite
+    lat2, lon2, alt2 = make_geometry(nbeams, ngates, seed=seed)
+    lat, lon, alt, keep = flatten_valid(lat2, lon2, alt2)
+    A = A_of(lat, lon, alt)
+    value, error, _ = make_records(A, nrecords, seed=seed + 1, noise_scale=noise_scale, bad_frac=0.0)
+    ne = np.full((nrecords, nbeams * ngates), np.nan)
+    dne = np.full((nrecords, nbeams * ngates), np.nan)
+    ne[:, keep], dne[:, keep] = value, error
+    chi2, fitcode = make_fitinfo((nrecords, nbeams, ngates), seed=seed + 2)
+    rng = np.random.default_rng(seed + 3)
+    # ~10 % of the gates fail the quality filter: bad fit code, chi2 or error out of range
+    bad = rng.uniform(size=chi2.shape)
+    fitcode[bad < 0.04] = 5
+    chi2[(bad >= 0.04) & (bad < 0.07)] = 25.0
+    dne3 = dne.reshape(nrecords, nbeams, ngates)
+    dne3[(bad >= 0.07) & (bad < 0.10)] = 5e13
+    utime = make_unixtime(nrecords)
+    arrays = {"/Time/UnixTime": utime, "/Geomag/Altitude": alt2, "/Geomag/Latitude": lat2, "/Geomag/Longitude": lon2,
+              "/FittedParams/Ne": ne.reshape(nrecords, nbeams, ngates), "/FittedParams/dNe": dne3,
+              "/FittedParams/FitInfo/chi2": chi2, "/FittedParams/FitInfo/fitcode": fitcode,
+              "/FittedParams/IonMass": np.array([16.0, 32.0, 30.0])}
+    with h5lite.Writer(filename, pytables_attrs=False) as h5:
+        for k, v in arrays.items():
+            h5.array(k, v)
+    return arrays
