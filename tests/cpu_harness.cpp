@@ -113,8 +113,7 @@ int h_system_solve(int n, const double* G, const double* y, const double* regs, 
   vi_tri_ws S;
   double* a = aux.data();
   S.X = X.data(); S.ld = ld;
-  S.v = a; S.w = a + n; S.yv = a + 2 * n; S.red2 = a + 3 * n; S.d = a + 4 * n; S.e = a + 5 * n;
-  S.tau = a + 6 * n; S.sc = a + 7 * n; S.red1 = a + 7 * n + 8; S.psum = S.red1 + (nt > n ? nt : n);
+  vi_tri_carve(S, a, n, nt);
   vi_tri_load(S, n, G, y, regs, lam, nreg, 0, nt);
   *bad = S.sc[1] != 0.0;
   if (*bad) return 0;

@@ -57,11 +57,13 @@ struct SysBuf {
 constexpr int kChiGates = 1024;    // gates per CTA in k_chi2 (partial sums combined in fixed order)
 
 int tri_threads(int n) {
-  int ng = 1024 / n;
-  if (ng > 4) ng = 4;
+  const int npair = vi_tri_npair(n);
+  int ng = 1024 / npair;
+  if (ng > 8) ng = 8;
   if (ng < 1) ng = 1;
-  int nt = (ng * n + 31) / 32 * 32;
+  int nt = (ng * npair + 31) / 32 * 32;
   if (nt > 1024) nt = 1024;
+  if (nt < ((n + 31) & ~31)) nt = (n + 31) & ~31;     // one thread per row/column index is assumed by phases A, C
   return nt;
 }
 
@@ -161,8 +163,7 @@ k_tridiag(const double* __restrict__ G, const double* __restrict__ y, const doub
   S.ld = B.ld;
   if (GX) { S.X = B.Xg + s * (int64_t)n * S.ld; aux = sm; }
   else { S.X = sm; aux = sm + (size_t)n * S.ld; }      // X stays a provable shared-memory pointer (LDS/STS)
-  S.v = aux; S.w = aux + n; S.yv = aux + 2 * n; S.red2 = aux + 3 * n; S.d = aux + 4 * n; S.e = aux + 5 * n;
-  S.tau = aux + 6 * n; S.sc = aux + 7 * n; S.red1 = aux + 7 * n + 8; S.psum = S.red1 + (nt > n ? nt : n);
+  vi_tri_carve(S, aux, n, nt);
   vi_tri_load(S, n, G + (int64_t)r * n * n, y + (int64_t)r * n, regs, B.lam + s * (B.nreg > 0 ? B.nreg : 1), B.nreg, tid, nt);
   const bool bad = S.sc[1] != 0.0;
   if (!bad) vi_tri_reduce(S, n, B.V + s * (int64_t)n * n, tid, nt);

@@ -65,31 +65,57 @@ VI_HD double vi_warp_sum(int a, int b, int lane, F f) {
 #endif
 }
 
+#if defined(__CUDA_ARCH__)
+typedef double2 vi_d2;
+#else
+struct vi_d2 { double x, y; };
+#endif
+
 // CTA-shared working set of one system.
 struct vi_tri_ws {
-  double* X;      // n x ld (ld odd: conflict-free column walks), full symmetric storage
+  double* X;      // n x ld, ld even (rows 16-byte aligned: two columns per thread move as one 128-bit access)
   int ld;
-  double* v;      // n  current reflector
-  double* w;      // n
+  double* vw;     // 4 x (n + 2): per index i the quadruple (v[i], w[i], vnext[i], -) of the deferred / next reflector
+  double* p;      // n + 2
   double* yv;     // n  right-hand side being transformed (ends as g = Q^T y)
+  double* col;    // n  the pivot column, already carrying the deferred update
   double* red1;   // max(n, nt)
   double* red2;   // n
-  double* psum;   // ng x n partial mat-vec sums
+  double* psum;   // ng x npad partial mat-vec sums, npad = 2 * ceil(n/2)
   double* d;      // n   diagonal of T
   double* e;      // n   sub-diagonal of T (e[n-1] unused)
   double* tau;    // n
-  double* sc;     // 4 scalars: [0] scale 2^-ex, [1] nonfinite flag
+  double* sc;     // 8 scalars: [0] scale 2^-ex, [1] nonfinite flag
 };
 
-VI_HD int vi_tri_ld(int n) { return (n & 1) ? n : n + 1; }
+VI_HD int vi_tri_ld(int n) { return (n + 2) & ~1; }
+VI_HD int vi_tri_npair(int n) { return (n + 1) / 2; }
+VI_HD int vi_tri_groups(int n, int nt) { int ng = nt / vi_tri_npair(n); return ng < 1 ? 1 : ng; }
 // doubles of CTA-shared storage needed besides X
-VI_HD int vi_tri_aux_doubles(int n, int nt) { int ng = nt / n; if (ng < 1) ng = 1; return 8 * n + (nt > n ? nt : n) + ng * n + 8; }
+VI_HD int vi_tri_aux_doubles(int n, int nt) {
+  return 4 * (n + 2) + (n + 2) + 6 * n + (nt > n ? nt : n) + vi_tri_groups(n, nt) * 2 * vi_tri_npair(n) + 8;
+}
+// carve the auxiliary arrays out of one block of vi_tri_aux_doubles(n, nt) doubles (16-byte aligned)
+VI_HD void vi_tri_carve(vi_tri_ws& S, double* aux, int n, int nt) {
+  S.vw = aux; aux += 4 * (n + 2);
+  S.p = aux; aux += n + 2;
+  S.yv = aux; aux += n;
+  S.col = aux; aux += n;
+  S.red2 = aux; aux += n;
+  S.d = aux; aux += n;
+  S.e = aux; aux += n;
+  S.tau = aux; aux += n;
+  S.sc = aux; aux += 8;
+  S.red1 = aux; aux += (nt > n ? nt : n);
+  S.psum = aux;
+}
 
-// X <- scl * (0.5 (G + G^T) + sum_r lam[r] Reg_r),  scl = 2^-exponent(max|X|);  yv <- y.
-// Returns (in ws.sc[1]) 1.0 if a non-finite entry was met.
+// X <- scl * (0.5 (G + G^T) + sum_r lam[r] Reg_r),  scl = 2^-exponent(max|X|);  yv <- y;  col <- X[:,0];
+// (v, w) <- 0.  Returns (in ws.sc[1]) 1.0 if a non-finite entry was met.
 VI_HD void vi_tri_load(const vi_tri_ws& S, int n, const double* G, const double* y, const double* regs,
                        const double* lam, int nreg, int tid, int nt) {
   (void)tid;
+  const int ld = S.ld;
   VI_PHASE(
     double mx = 0.0; double bad = 0.0;
     for (int idx = tid; idx < n * n; idx += nt) {
@@ -101,9 +127,16 @@ VI_HD void vi_tri_load(const vi_tri_ws& S, int n, const double* G, const double*
       }
       if (!(fabs(x) <= 1.79769313486231570e308)) bad = 1.0;
       mx = fmax(mx, fabs(x));
-      S.X[i * S.ld + c] = x;
+      S.X[i * ld + c] = x;
     }
-    for (int i = tid; i < n; i += nt) { double t = y[i]; if (!(fabs(t) <= 1.79769313486231570e308)) bad = 1.0; S.yv[i] = t; }
+    for (int i = tid; i < n; i += nt) {
+      double t = y[i];
+      if (!(fabs(t) <= 1.79769313486231570e308)) bad = 1.0;
+      S.yv[i] = t;
+      for (int c = n; c < ld; ++c) S.X[i * ld + c] = 0.0;      // padding columns
+    }
+    for (int i = tid; i < 4 * (n + 2); i += nt) S.vw[i] = 0.0;
+    for (int i = tid; i < n + 2; i += nt) S.p[i] = 0.0;
     S.red1[tid] = (bad != 0.0) ? -1.0 : mx;
   )
   VI_PHASE(
@@ -119,115 +152,126 @@ VI_HD void vi_tri_load(const vi_tri_ws& S, int n, const double* G, const double*
   VI_PHASE(
     double scl = S.sc[0];
     if (scl != 1.0)
-      for (int idx = tid; idx < n * n; idx += nt) { int i = idx / n; int c = idx - i * n; S.X[i * S.ld + c] *= scl; }
+      for (int idx = tid; idx < n * n; idx += nt) { int i = idx / n; int c = idx - i * n; S.X[i * ld + c] *= scl; }
+  )
+  VI_PHASE(
+    for (int i = tid; i < n; i += nt) S.col[i] = S.X[i * ld];
   )
 }
 
-// Reduction proper.  V (global or host): (n x n) row j holds reflector j in columns j+1..n-1
-// (v[j+1] = 1 stored explicitly).  After the call S.d, S.e, S.tau, S.yv (= Q^T y) are final.
-// Per step: [every warp: column norm by warp-sum -> reflector] | [all: partial mat-vec] |
-// [column owners: p, products] | [their warps: two dot products by warp-sum, w, rhs update] |
-// [all: rank-2 update]  -> 5 CTA barriers, no single-warp section.
+// Reduction proper, FUSED form: the rank-2 update of reflector k-1 is deferred and applied in the same
+// pass over the trailing matrix that forms the mat-vec for reflector k (one read + one write of X per
+// Householder step instead of two reads + one write).  Iteration k = 0 .. n-2:
+//   A  every warp: norm of the pivot column (warp-sum) -> reflector k (vnext), d[k], e[k], tau[k]
+//   B  all threads, two columns each: x = X[i][c] - v[i] w[c] - w[i] v[c]; store; acc_c += x vnext[i]
+//   C1 column owners: p = tau * sum of partials; products for the two dot products
+//   C2 their warps: dot products (warp-sum), w for reflector k, rhs update, and the NEXT pivot column
+//      (column k+1 with the update of reflector k already applied), then (v, w) <- (vnext, wnext)
+// 4 CTA barriers per step.  V (global or host): row k holds reflector k in columns k+1..n-1
+// (v[k+1] = 1 stored explicitly).  After the call S.d, S.e, S.tau, S.yv (= Q^T y) are final.
 VI_HD void vi_tri_reduce(const vi_tri_ws& S, int n, double* V, int tid, int nt) {
   (void)tid;
-  const int ng = (nt / n) < 1 ? 1 : (nt / n);
   const int ld = S.ld;
-  for (int j = 0; j + 2 < n; ++j) {
-    const int lo = j + 1;
+  const int npair = vi_tri_npair(n), npad = 2 * npair;
+  const int ng = vi_tri_groups(n, nt);
+  for (int k = 0; k + 1 < n; ++k) {
+    const int lo1 = k + 1;
+    // ---- A: reflector k from the pivot column --------------------------------------------------
     VI_PHASE(
-      const double* col = S.X + j;
-      double xn2 = vi_warp_sum(lo + 1, n, tid & 31, [&](int k) { double x = col[k * ld]; return x * x; });
-      double alpha = col[lo * ld];
-      double tau = 0.0; double beta = alpha; double scale = 0.0;
-      if (xn2 != 0.0) {
-        beta = -copysign(sqrt(alpha * alpha + xn2), alpha);
-        tau = (beta - alpha) / beta;
-        scale = 1.0 / (alpha - beta);
+      double tau = 0.0; double beta = 0.0; double scale = 0.0;
+      const bool last = (k == n - 2);
+      if (!last) {
+        const double xn2 = vi_warp_sum(k + 2, n, tid & 31, [&](int i) { double x = S.col[i]; return x * x; });
+        const double alpha = S.col[k + 1];
+        beta = alpha;
+        if (xn2 != 0.0) {
+          const double r2 = alpha * alpha + xn2;
+#if defined(__CUDA_ARCH__)
+          const double ri = rsqrt(r2);
+#else
+          const double ri = 1.0 / sqrt(r2);
+#endif
+          const double nrm = r2 * ri;
+          beta = -copysign(nrm, alpha);
+          tau = 1.0 + fabs(alpha) * ri;                      // (beta - alpha) / beta
+          scale = copysign(1.0, alpha) / (fabs(alpha) + nrm);  // 1 / (alpha - beta)
+        }
+      } else {
+        beta = S.col[n - 1];
       }
-      if (tid >= lo && tid < n) {
-        double vv = (tid == lo) ? 1.0 : col[tid * ld] * scale;
-        if (tau == 0.0) vv = (tid == lo) ? 1.0 : 0.0;
-        S.v[tid] = vv;
-        V[(int64_t)j * n + tid] = vv;
+      if (tid >= lo1 && tid < n) {
+        double vv = 0.0;
+        if (tau != 0.0) vv = (tid == lo1) ? 1.0 : S.col[tid] * scale;
+        S.vw[4 * tid + 2] = vv;
+        if (!last) V[(int64_t)k * n + tid] = (tau == 0.0 && tid == lo1) ? 1.0 : vv;
       }
-      if (tid == lo) { S.e[j] = beta; S.tau[j] = tau; S.d[j] = S.X[j * ld + j]; }
+      if (tid == 0) { S.d[k] = S.col[k]; S.e[k] = beta; S.tau[k] = tau; }
     )
-    const double tau = S.tau[j];
-    if (tau == 0.0) continue;   // H_j = I (uniform across the CTA: tau lives in shared memory)
+    const double tau = S.tau[k];
+    // ---- B: deferred update of reflector k-1 fused with the mat-vec for reflector k -------------
     VI_PHASE(
       {
-        int g = tid / n; int c = tid - g * n;
-        if (g < ng && c >= lo) {
+        const int g = tid / npair; const int cp = tid - g * npair;
+        const int c0 = 2 * cp;
+        if (g < ng && c0 + 1 >= lo1) {
+          const double vc0 = S.vw[4 * c0]; const double wc0 = S.vw[4 * c0 + 1];
+          const double vc1 = S.vw[4 * c0 + 4]; const double wc1 = S.vw[4 * c0 + 5];
+          double a0 = 0.0; double a1 = 0.0;
           const int step = ng * ld;
-          const double* xp = S.X + (lo + g) * ld + c;
-          const double* vp = S.v + lo + g;
-          const int cnt = (n - lo - g + ng - 1) / ng;
-          double a0 = 0.0; double a1 = 0.0; double a2 = 0.0; double a3 = 0.0;
-          int k = 0;
-          for (; k + 3 < cnt; k += 4) {
-            a0 += xp[0] * vp[0];
-            a1 += xp[step] * vp[ng];
-            a2 += xp[2 * step] * vp[2 * ng];
-            a3 += xp[3 * step] * vp[3 * ng];
-            xp += 4 * step; vp += 4 * ng;
-          }
-          for (; k < cnt; ++k) { a0 += xp[0] * vp[0]; xp += step; vp += ng; }
-          S.psum[g * n + c] = (a0 + a1) + (a2 + a3);
-        }
-      }
-    )
-    VI_PHASE(
-      if (tid >= lo && tid < n) {
-        double p = 0.0;
-        for (int g = 0; g < ng; ++g) p += S.psum[g * n + tid];
-        p = tau * p;
-        const double vc = S.v[tid];
-        S.w[tid] = p;
-        S.red1[tid] = p * vc;
-        S.red2[tid] = vc * S.yv[tid];
-      }
-    )
-    VI_PHASE(
-      if (tid < ((n + 31) & ~31)) {      // the warps that own an element: each forms both dot products itself
-        const double dot = vi_warp_sum(lo, n, tid & 31, [&](int k) { return S.red1[k]; });
-        const double dot2 = vi_warp_sum(lo, n, tid & 31, [&](int k) { return S.red2[k]; });
-        if (tid >= lo && tid < n) {
-          const double vc = S.v[tid];
-          S.w[tid] = S.w[tid] + (-0.5 * tau * dot) * vc;
-          S.yv[tid] = S.yv[tid] - (tau * dot2) * vc;
-        }
-      }
-    )
-    VI_PHASE(
-      {
-        int g = tid / n; int c = tid - g * n;
-        if (g < ng && c >= lo) {
-          const double wc = S.w[c]; const double vc = S.v[c];
-          const int step = ng * ld;
-          double* xp = S.X + (lo + g) * ld + c;
-          const double* vp = S.v + lo + g;
-          const double* wp = S.w + lo + g;
-          const int cnt = (n - lo - g + ng - 1) / ng;
+          double* xp = S.X + (lo1 + g) * ld + c0;
+          const double* q = S.vw + 4 * (lo1 + g);
           VI_UNROLL4
-          for (int k = 0; k < cnt; ++k) {
-            double x = xp[0];
-            x = x - vp[0] * wc;
-            x = x - wp[0] * vc;
-            xp[0] = x;
-            xp += step; vp += ng; wp += ng;
+          for (int i = lo1 + g; i < n; i += ng) {
+            const vi_d2 vwi = *reinterpret_cast<const vi_d2*>(q);
+            const double vni = q[2];
+            vi_d2 x = *reinterpret_cast<vi_d2*>(xp);
+            x.x = x.x - vwi.x * wc0; x.x = x.x - vwi.y * vc0;
+            x.y = x.y - vwi.x * wc1; x.y = x.y - vwi.y * vc1;
+            *reinterpret_cast<vi_d2*>(xp) = x;
+            a0 += x.x * vni; a1 += x.y * vni;
+            xp += step; q += 4 * ng;
           }
+          S.psum[g * npad + c0] = a0;
+          S.psum[g * npad + c0 + 1] = a1;
+        }
+      }
+    )
+    // ---- C1: p = tau * (X v), products ---------------------------------------------------------
+    VI_PHASE(
+      if (tid >= lo1 && tid < n) {
+        double p = 0.0;
+        for (int g = 0; g < ng; ++g) p += S.psum[g * npad + tid];
+        p = tau * p;
+        const double vn = S.vw[4 * tid + 2];
+        S.p[tid] = p;
+        S.red1[tid] = p * vn;
+        S.red2[tid] = vn * S.yv[tid];
+      }
+    )
+    // ---- C2: dot products, w, rhs, next pivot column, rotate (v, w) <- (vnext, wnext) ------------
+    VI_PHASE(
+      if (tid < ((n + 31) & ~31)) {
+        const double dot = vi_warp_sum(lo1, n, tid & 31, [&](int i) { return S.red1[i]; });
+        const double dot2 = vi_warp_sum(lo1, n, tid & 31, [&](int i) { return S.red2[i]; });
+        if (tid >= lo1 && tid < n) {
+          const double a2 = -0.5 * tau * dot;
+          const double vn = S.vw[4 * tid + 2];
+          const double wn = S.p[tid] + a2 * vn;
+          S.yv[tid] = S.yv[tid] - (tau * dot2) * vn;
+          // column k+1 of the matrix with reflector k applied (vnext[k+1] = 1 when tau != 0)
+          const double wlo = S.p[lo1] + a2 * S.vw[4 * lo1 + 2];
+          const double vlo = S.vw[4 * lo1 + 2];
+          S.col[tid] = (S.X[tid * ld + lo1] - vn * wlo) - wn * vlo;
+          S.vw[4 * tid] = vn;
+          S.vw[4 * tid + 1] = wn;
         }
       }
     )
   }
   VI_PHASE(
     if (tid == 0) {
-      if (n >= 2) {
-        S.d[n - 2] = S.X[(n - 2) * ld + (n - 2)];
-        S.e[n - 2] = S.X[(n - 1) * ld + (n - 2)];
-        S.tau[n - 2] = 0.0;
-      }
-      S.d[n - 1] = S.X[(n - 1) * ld + (n - 1)];
+      if (n == 1) S.d[0] = S.X[0];
+      else S.d[n - 1] = S.col[n - 1];
       S.e[n - 1] = 0.0; S.tau[n - 1] = 0.0;
     }
   )
