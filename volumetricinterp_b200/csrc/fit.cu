@@ -746,8 +746,7 @@ __global__ void k_transpose(const double* __restrict__ A, int P, int N, double* 
 // ------------------------------------------------------------------------------------------
 inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
-int run_systems(int64_t cnt, const double* G, const double* y, const double* regs, const SysBuf& B, double rcond,
-                double* Cout, int32_t* rank_out, cudaStream_t s) {
+int run_tridiag(int64_t cnt, const double* G, const double* y, const double* regs, const SysBuf& B, cudaStream_t s) {
   if (cnt <= 0) return VI_OK;
   if (B.use_gx) {
     VI_CUDA(cudaFuncSetAttribute(k_tridiag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
@@ -756,11 +755,24 @@ int run_systems(int64_t cnt, const double* G, const double* y, const double* reg
     VI_CUDA(cudaFuncSetAttribute(k_tridiag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
     VI_KERNEL(VI_K_TRIDIAG, s, k_tridiag<false><<<(unsigned)cnt, B.nt, B.smem, s>>>(G, y, regs, B));
   }
-  // threads per block for the shared-memory QL: as many as 2n doubles per thread allow (<= 96)
-  int T = (int)((227 * 1024) / ((size_t)2 * B.n * sizeof(double))) / 32 * 32;
+  return VI_OK;
+}
+
+// QL + apply.  `coresident`: size the QL blocks so that one of them fits NEXT TO a k_tridiag CTA on the
+// same SM (the pipelined table phase runs the two kernels concurrently on two streams).
+int run_post(int64_t cnt, const SysBuf& B, double rcond, double* Cout, int32_t* rank_out, cudaStream_t s,
+             bool coresident) {
+  if (cnt <= 0) return VI_OK;
+  const size_t per_thread = (size_t)2 * B.n * sizeof(double);
+  int T = (int)((227 * 1024) / per_thread) / 32 * 32;     // as many as 2n doubles per thread allow (<= 96)
   if (T > 96) T = 96;
-  if (T >= 32) {
-    size_t smem = (size_t)2 * B.n * T * sizeof(double);
+  if (coresident && !B.use_gx && T >= 32) {
+    const size_t left = (size_t)227 * 1024 - B.smem - 2048;
+    int Tc = (int)(left / per_thread) / 8 * 8;
+    if (Tc >= 8) T = Tc < 96 ? Tc : 96;
+  }
+  if (T >= 8 && (size_t)T * per_thread <= (size_t)227 * 1024 && ((227 * 1024) / per_thread) >= 32) {
+    size_t smem = (size_t)T * per_thread;
     VI_CUDA(cudaFuncSetAttribute(k_tql_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VI_KERNEL(VI_K_TQL, s, k_tql_smem<<<blocks(cnt, T), T, smem, s>>>(cnt, B));
     size_t smem2 = (size_t)kApplyWarps * B.n * sizeof(double);
@@ -769,6 +781,12 @@ int run_systems(int64_t cnt, const double* G, const double* y, const double* reg
     VI_KERNEL(VI_K_TQL, s, k_tql<<<blocks(cnt, 64), 64, 0, s>>>(cnt, B, rcond, Cout, rank_out));
   }
   return VI_OK;
+}
+
+int run_systems(int64_t cnt, const double* G, const double* y, const double* regs, const SysBuf& B, double rcond,
+                double* Cout, int32_t* rank_out, cudaStream_t s) {
+  if (int rc = run_tridiag(cnt, G, y, regs, B, s)) return rc;
+  return run_post(cnt, B, rcond, Cout, rank_out, s, false);
 }
 
 int run_chi2(int64_t cnt, const double* At, const double* Wm, const double* bm, int P, const SysBuf& B,
@@ -872,8 +890,13 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
   double* covH = b.take<double>(cc * (int64_t)N * N);
   double* covT = b.take<double>(cc * (int64_t)N * N);
   double* covD = b.take<double>(cc * (int64_t)N);
-  SysBuf B;
+  // two system buffers of cap/2: the table phase ping-pongs between them so that the QL / apply / chi2
+  // kernels of one chunk (second stream) overlap the tridiagonalisation of the next (caller's stream)
+  cap = (cap / 2) / 32 * 32;
+  if (cap < 32) { vi_set_error("workspace too small (%lld bytes)", (long long)workspace_bytes); return VI_EWORKSPACE; }
+  SysBuf B, B2;
   sysbuf_carve(b, B, cap, N, nreg, P);
+  sysbuf_carve(b, B2, cap, N, nreg, P);
   int64_t solved = 0;
 
   if (method == VI_METHOD_CHI2) {
@@ -888,12 +911,40 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
     int64_t T = 0;
     VI_CUDA(cudaMemcpyAsync(&T, Ub.off + U, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     VI_CUDA(cudaStreamSynchronize(st));
-    for (int64_t t0 = 0; t0 < T; t0 += cap) {
-      int64_t cnt = (T - t0 < cap) ? T - t0 : cap;
-      VI_KERNEL(VI_K_MISC, st, k_setup_table<<<blocks(cap, 256), 256, 0, st>>>(t0, cnt, U, nreg, pow10tab, Ub.off, B));
-      if (int rc = run_systems(cnt, G, y, regmats, B, rcond, B.Csys, B.rank, st)) return rc;
-      if (int rc = run_chi2(cnt, At, Wm, bm, P, B, B.Csys, B.chi2, st)) return rc;
-      VI_KERNEL(VI_K_MISC, st, k_scatter_table<<<blocks(cnt, 256), 256, 0, st>>>(cnt, B, Ub));
+    {
+      cudaStream_t s2 = nullptr;
+      int lo_pri = 0, hi_pri = 0;
+      VI_CUDA(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+      VI_CUDA(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, hi_pri));
+      cudaEvent_t ev_tri[2], ev_free[2];
+      for (int q = 0; q < 2; ++q) {
+        VI_CUDA(cudaEventCreateWithFlags(&ev_tri[q], cudaEventDisableTiming));
+        VI_CUDA(cudaEventCreateWithFlags(&ev_free[q], cudaEventDisableTiming));
+      }
+      int rc = VI_OK;
+      int64_t chunk = 0;
+      for (int64_t t0 = 0; t0 < T && rc == VI_OK; t0 += cap, ++chunk) {
+        const int q = (int)(chunk & 1);
+        const SysBuf& Bc = q ? B2 : B;
+        int64_t cnt = (T - t0 < cap) ? T - t0 : cap;
+        if (chunk >= 2) VI_CUDA(cudaStreamWaitEvent(st, ev_free[q], 0));
+        VI_KERNEL(VI_K_MISC, st, k_setup_table<<<blocks(cap, 256), 256, 0, st>>>(t0, cnt, U, nreg, pow10tab, Ub.off, Bc));
+        rc = run_tridiag(cnt, G, y, regmats, Bc, st);
+        if (rc) break;
+        VI_CUDA(cudaEventRecord(ev_tri[q], st));
+        VI_CUDA(cudaStreamWaitEvent(s2, ev_tri[q], 0));
+        rc = run_post(cnt, Bc, rcond, Bc.Csys, Bc.rank, s2, true);
+        if (rc) break;
+        rc = run_chi2(cnt, At, Wm, bm, P, Bc, Bc.Csys, Bc.chi2, s2);
+        if (rc) break;
+        VI_KERNEL(VI_K_MISC, s2, k_scatter_table<<<blocks(cnt, 256), 256, 0, s2>>>(cnt, Bc, Ub));
+        VI_CUDA(cudaEventRecord(ev_free[q], s2));
+      }
+      for (int q = 0; q < 2 && q < chunk; ++q) cudaStreamWaitEvent(st, ev_free[q], 0);
+      cudaStreamSynchronize(s2);
+      for (int q = 0; q < 2; ++q) { cudaEventDestroy(ev_tri[q]); cudaEventDestroy(ev_free[q]); }
+      cudaStreamDestroy(s2);
+      if (rc) return rc;
     }
     solved += T;
     VI_KERNEL(VI_K_MISC, st, k_fill_table<<<blocks(U, 128), 128, 0, st>>>(U, Ub.kstar, Ub));
