@@ -809,6 +809,7 @@ extern "C" int vi_fit_workspace_bytes(int32_t R, int32_t P, int32_t N, int32_t n
   int64_t wanted = U * VI_NALPHA;
   if (wanted < R) wanted = R;
   int64_t cap = systems > 0 ? vi_align_up(systems, 32) : default_system_cap(wanted, N, nreg, P);
+  if (cap < 64) cap = 64;      // the fit keeps two buffers of cap/2 systems
   Bump b{nullptr, 0, 0};
   UnitBuf Ub;
   unit_carve(b, Ub, U);
@@ -880,7 +881,6 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
   int64_t cap = cap_for_workspace(workspace_bytes, U, N, nreg, P, R);
   if (cap < 32) { vi_set_error("workspace too small (%lld bytes)", (long long)workspace_bytes); return VI_EWORKSPACE; }
   int64_t most = vi_align_up(method == VI_METHOD_CHI2 ? U * VI_NALPHA : (int64_t)R, 32);
-  if (cap > most) cap = most;
   Bump b{reinterpret_cast<char*>(workspace), 0, workspace_bytes};
   UnitBuf Ub;
   unit_carve(b, Ub, U);
@@ -893,6 +893,7 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
   // two system buffers of cap/2: the table phase ping-pongs between them so that the QL / apply / chi2
   // kernels of one chunk (second stream) overlap the tridiagonalisation of the next (caller's stream)
   cap = (cap / 2) / 32 * 32;
+  if (cap > most) cap = most;
   if (cap < 32) { vi_set_error("workspace too small (%lld bytes)", (long long)workspace_bytes); return VI_EWORKSPACE; }
   SysBuf B, B2;
   sysbuf_carve(b, B, cap, N, nreg, P);
@@ -912,26 +913,33 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
     VI_CUDA(cudaMemcpyAsync(&T, Ub.off + U, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     VI_CUDA(cudaStreamSynchronize(st));
     {
-      cudaStream_t s2 = nullptr;
+      // s1 (high priority): set-up + tridiagonalisation; s2 (low priority): QL, apply, chi2, scatter.  The
+      // priorities make the block scheduler give every SM its k_tridiag CTA first (185 KB of shared memory)
+      // and fill the remaining ~40 KB with one QL block, instead of letting the QL blocks take whole SMs.
+      cudaStream_t s1 = nullptr, s2 = nullptr;
       int lo_pri = 0, hi_pri = 0;
       VI_CUDA(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
-      VI_CUDA(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, hi_pri));
-      cudaEvent_t ev_tri[2], ev_free[2];
+      VI_CUDA(cudaStreamCreateWithPriority(&s1, cudaStreamNonBlocking, hi_pri));
+      VI_CUDA(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, lo_pri));
+      cudaEvent_t ev_tri[2], ev_free[2], ev_start;
+      VI_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
       for (int q = 0; q < 2; ++q) {
         VI_CUDA(cudaEventCreateWithFlags(&ev_tri[q], cudaEventDisableTiming));
         VI_CUDA(cudaEventCreateWithFlags(&ev_free[q], cudaEventDisableTiming));
       }
+      VI_CUDA(cudaEventRecord(ev_start, st));
+      VI_CUDA(cudaStreamWaitEvent(s1, ev_start, 0));
       int rc = VI_OK;
       int64_t chunk = 0;
       for (int64_t t0 = 0; t0 < T && rc == VI_OK; t0 += cap, ++chunk) {
         const int q = (int)(chunk & 1);
         const SysBuf& Bc = q ? B2 : B;
         int64_t cnt = (T - t0 < cap) ? T - t0 : cap;
-        if (chunk >= 2) VI_CUDA(cudaStreamWaitEvent(st, ev_free[q], 0));
-        VI_KERNEL(VI_K_MISC, st, k_setup_table<<<blocks(cap, 256), 256, 0, st>>>(t0, cnt, U, nreg, pow10tab, Ub.off, Bc));
-        rc = run_tridiag(cnt, G, y, regmats, Bc, st);
+        if (chunk >= 2) VI_CUDA(cudaStreamWaitEvent(s1, ev_free[q], 0));
+        VI_KERNEL(VI_K_MISC, s1, k_setup_table<<<blocks(cap, 256), 256, 0, s1>>>(t0, cnt, U, nreg, pow10tab, Ub.off, Bc));
+        rc = run_tridiag(cnt, G, y, regmats, Bc, s1);
         if (rc) break;
-        VI_CUDA(cudaEventRecord(ev_tri[q], st));
+        VI_CUDA(cudaEventRecord(ev_tri[q], s1));
         VI_CUDA(cudaStreamWaitEvent(s2, ev_tri[q], 0));
         rc = run_post(cnt, Bc, rcond, Bc.Csys, Bc.rank, s2, true);
         if (rc) break;
@@ -941,8 +949,11 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
         VI_CUDA(cudaEventRecord(ev_free[q], s2));
       }
       for (int q = 0; q < 2 && q < chunk; ++q) cudaStreamWaitEvent(st, ev_free[q], 0);
+      cudaStreamSynchronize(s1);
       cudaStreamSynchronize(s2);
+      cudaEventDestroy(ev_start);
       for (int q = 0; q < 2; ++q) { cudaEventDestroy(ev_tri[q]); cudaEventDestroy(ev_free[q]); }
+      cudaStreamDestroy(s1);
       cudaStreamDestroy(s2);
       if (rc) return rc;
     }
