@@ -758,23 +758,25 @@ int run_tridiag(int64_t cnt, const double* G, const double* y, const double* reg
   return VI_OK;
 }
 
-// QL + apply.  `coresident`: size the QL blocks so that one of them fits NEXT TO a k_tridiag CTA on the
-// same SM (the pipelined table phase runs the two kernels concurrently on two streams).
-int run_post(int64_t cnt, const SysBuf& B, double rcond, double* Cout, int32_t* rank_out, cudaStream_t s,
-             bool coresident) {
-  if (cnt <= 0) return VI_OK;
+// QL (thread per system) on stream s_ql, apply (warp per system) on stream s_apply.  The QL kernel takes
+// the whole shared memory of an SM, so it serialises with k_tridiag; k_apply and k_chi2 are small and can
+// run next to the tridiagonalisation of the following chunk (pipelined table phase: s_apply != s_ql, the
+// caller orders the two streams with events).
+int run_ql(int64_t cnt, const SysBuf& B, cudaStream_t s, bool* split) {
   const size_t per_thread = (size_t)2 * B.n * sizeof(double);
   int T = (int)((227 * 1024) / per_thread) / 32 * 32;     // as many as 2n doubles per thread allow (<= 96)
   if (T > 96) T = 96;
-  if (coresident && !B.use_gx && T >= 32) {
-    const size_t left = (size_t)227 * 1024 - B.smem - 2048;
-    int Tc = (int)(left / per_thread) / 8 * 8;
-    if (Tc >= 8) T = Tc < 96 ? Tc : 96;
-  }
-  if (T >= 8 && (size_t)T * per_thread <= (size_t)227 * 1024 && ((227 * 1024) / per_thread) >= 32) {
-    size_t smem = (size_t)T * per_thread;
-    VI_CUDA(cudaFuncSetAttribute(k_tql_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VI_KERNEL(VI_K_TQL, s, k_tql_smem<<<blocks(cnt, T), T, smem, s>>>(cnt, B));
+  *split = T >= 32;
+  if (cnt <= 0 || !*split) return VI_OK;
+  size_t smem = (size_t)T * per_thread;
+  VI_CUDA(cudaFuncSetAttribute(k_tql_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VI_KERNEL(VI_K_TQL, s, k_tql_smem<<<blocks(cnt, T), T, smem, s>>>(cnt, B));
+  return VI_OK;
+}
+
+int run_apply(int64_t cnt, const SysBuf& B, double rcond, double* Cout, int32_t* rank_out, cudaStream_t s, bool split) {
+  if (cnt <= 0) return VI_OK;
+  if (split) {
     size_t smem2 = (size_t)kApplyWarps * B.n * sizeof(double);
     VI_KERNEL(VI_K_APPLY, s, k_apply<<<blocks(cnt, kApplyWarps), kApplyWarps * 32, smem2, s>>>(cnt, B, rcond, Cout, rank_out));
   } else {
@@ -783,10 +785,16 @@ int run_post(int64_t cnt, const SysBuf& B, double rcond, double* Cout, int32_t* 
   return VI_OK;
 }
 
+int run_post(int64_t cnt, const SysBuf& B, double rcond, double* Cout, int32_t* rank_out, cudaStream_t s) {
+  bool split = false;
+  if (int rc = run_ql(cnt, B, s, &split)) return rc;
+  return run_apply(cnt, B, rcond, Cout, rank_out, s, split);
+}
+
 int run_systems(int64_t cnt, const double* G, const double* y, const double* regs, const SysBuf& B, double rcond,
                 double* Cout, int32_t* rank_out, cudaStream_t s) {
   if (int rc = run_tridiag(cnt, G, y, regs, B, s)) return rc;
-  return run_post(cnt, B, rcond, Cout, rank_out, s, false);
+  return run_post(cnt, B, rcond, Cout, rank_out, s);
 }
 
 int run_chi2(int64_t cnt, const double* At, const double* Wm, const double* bm, int P, const SysBuf& B,
@@ -913,9 +921,8 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
     VI_CUDA(cudaMemcpyAsync(&T, Ub.off + U, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     VI_CUDA(cudaStreamSynchronize(st));
     {
-      // s1 (high priority): set-up + tridiagonalisation; s2 (low priority): QL, apply, chi2, scatter.  The
-      // priorities make the block scheduler give every SM its k_tridiag CTA first (185 KB of shared memory)
-      // and fill the remaining ~40 KB with one QL block, instead of letting the QL blocks take whole SMs.
+      // s1 (high priority): set-up, tridiagonalisation, QL (both need a whole SM's shared memory);
+      // s2 (low priority): apply, chi2, scatter of the previous chunk, which fit next to a k_tridiag CTA.
       cudaStream_t s1 = nullptr, s2 = nullptr;
       int lo_pri = 0, hi_pri = 0;
       VI_CUDA(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
@@ -939,9 +946,12 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
         VI_KERNEL(VI_K_MISC, s1, k_setup_table<<<blocks(cap, 256), 256, 0, s1>>>(t0, cnt, U, nreg, pow10tab, Ub.off, Bc));
         rc = run_tridiag(cnt, G, y, regmats, Bc, s1);
         if (rc) break;
+        bool split = false;
+        rc = run_ql(cnt, Bc, s1, &split);
+        if (rc) break;
         VI_CUDA(cudaEventRecord(ev_tri[q], s1));
         VI_CUDA(cudaStreamWaitEvent(s2, ev_tri[q], 0));
-        rc = run_post(cnt, Bc, rcond, Bc.Csys, Bc.rank, s2, true);
+        rc = run_apply(cnt, Bc, rcond, Bc.Csys, Bc.rank, s2, split);
         if (rc) break;
         rc = run_chi2(cnt, At, Wm, bm, P, Bc, Bc.Csys, Bc.chi2, s2);
         if (rc) break;
