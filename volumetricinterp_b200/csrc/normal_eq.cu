@@ -290,6 +290,141 @@ k_ne_dmma(const double* __restrict__ A, const double* __restrict__ value, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fast, version 2: m16n8k16 DMMA, operands staged TRANSPOSED (column-major over the gates of a
+// stage, gate index permuted so that the four k-values a lane feeds to one instruction are adjacent:
+// every fragment is two 128-bit shared loads), masked weights / data streamed by cp.async from the
+// arrays k_prep wrote (no division in the pipeline), 3 stages, one CTA barrier per 32 gates.
+// ---------------------------------------------------------------------------------------------
+constexpr int kEJ = 32;          // gates per stage (two k16 steps)
+constexpr int kELD = 34;         // doubles per staged column: 34 = 2 (mod 16) -> conflict-free 128-bit fragment loads
+constexpr int kEStages = 3;
+
+__device__ __forceinline__ void dmma_16x8x16(double (&d)[4], const double (&a)[8], const double (&b)[4]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+      "{%12,%13,%14,%15}, {%0,%1,%2,%3};\n"
+      : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3])
+      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]),
+        "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]));
+}
+
+// position of gate jj (0..31) inside a staged column: within each block of 16 gates, k -> 4 (k % 4) + k / 4
+__device__ __forceinline__ int gate_slot(int jj) { return (jj & 16) | ((jj & 3) << 2) | ((jj >> 2) & 3); }
+
+template <int DT>
+__global__ void __launch_bounds__(kDW * 32)
+k_ne_dmma2(const double* __restrict__ A, const double* __restrict__ Wm, const double* __restrict__ bm,
+           int P, int N, int mt, int nt, int cols, int ntiles, int tpw, double* __restrict__ G, double* __restrict__ y) {
+  extern __shared__ __align__(16) double sm[];
+  double* S = sm;                                              // kEStages x cols x kELD
+  double* sw = sm + (size_t)kEStages * cols * kELD;            // kEStages x kEJ (slot order)
+  unsigned char* tmi = reinterpret_cast<unsigned char*>(sw + kEStages * kEJ);
+  unsigned char* tni = tmi + 256;
+  const int r = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  if (tid == 0) {
+    int c = 0;
+    for (int mi = 0; mi < mt; ++mi) {
+      for (int ni = 0; ni < nt - 1; ++ni)
+        if (8 * ni <= 16 * mi + 15 && 8 * ni < N) { tmi[c] = (unsigned char)mi; tni[c] = (unsigned char)ni; ++c; }
+      tmi[c] = (unsigned char)mi; tni[c] = (unsigned char)(nt - 1); ++c;
+    }
+  }
+  for (int e = tid; e < kEStages * cols * kELD + kEStages * kEJ; e += blockDim.x) sm[e] = 0.0;
+  __syncthreads();
+  const int t0 = warp * tpw;
+  const int t1 = min(ntiles, t0 + tpw);
+  int tinfo[DT];
+  double acc[DT][4];
+#pragma unroll
+  for (int q = 0; q < DT; ++q) {
+    const int tt = t0 + q;
+    tinfo[q] = (tt < t1) ? ((int)tmi[tt] | ((int)tni[tt] << 8)) : -1;
+    acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0;
+  }
+  const int bcol = 8 * (nt - 1);
+  const int nchunk = (P + kEJ - 1) / kEJ;
+  const double* Wr = Wm + (int64_t)r * P;
+  const double* br = bm + (int64_t)r * P;
+
+  auto stage_load = [&](int chunk) {
+    const int st = chunk % kEStages;
+    double* dst = S + (size_t)st * cols * kELD;
+    const int j0 = chunk * kEJ;
+    for (int e = tid; e < kEJ * N; e += blockDim.x) {
+      const int jj = e / N, c = e - jj * N;
+      const int j = j0 + jj;
+      double* d = dst + c * kELD + gate_slot(jj);
+      if (j < P) cp_async8(d, A + (int64_t)j * N + c);
+      else *d = 0.0;
+    }
+    if (tid < kEJ) {
+      const int j = j0 + tid, sl = gate_slot(tid);
+      if (j < P) { cp_async8(sw + st * kEJ + sl, Wr + j); cp_async8(dst + bcol * kELD + sl, br + j); }
+      else { sw[st * kEJ + sl] = 0.0; dst[bcol * kELD + sl] = 0.0; }
+    }
+    cp_async_commit();
+  };
+
+  stage_load(0);
+  if (nchunk > 1) stage_load(1);
+  for (int ch = 0; ch < nchunk; ++ch) {
+    if (ch + 1 < nchunk) cp_async_wait<1>(); else cp_async_wait<0>();
+    __syncthreads();
+    if (ch + 2 < nchunk) stage_load(ch + 2);
+    const int st = ch % kEStages;
+    const double* Sst = S + (size_t)st * cols * kELD;
+    const double* Wst = sw + st * kEJ;
+#pragma unroll
+    for (int ks = 0; ks < kEJ / 16; ++ks) {
+      const int kb = 16 * ks + 4 * t;
+      const double2 w01 = *reinterpret_cast<const double2*>(Wst + kb);
+      const double2 w23 = *reinterpret_cast<const double2*>(Wst + kb + 2);
+      int cur_mi = -1;
+      double a[8];
+#pragma unroll
+      for (int q = 0; q < DT; ++q) {
+        if (tinfo[q] >= 0) {
+          const int mi = tinfo[q] & 255, ni = tinfo[q] >> 8;
+          if (mi != cur_mi) {
+            cur_mi = mi;
+            const double* p0 = Sst + (16 * mi + g) * kELD + kb;
+            const double* p1 = p0 + 8 * kELD;
+            const double2 x01 = *reinterpret_cast<const double2*>(p0), x23 = *reinterpret_cast<const double2*>(p0 + 2);
+            const double2 z01 = *reinterpret_cast<const double2*>(p1), z23 = *reinterpret_cast<const double2*>(p1 + 2);
+            a[0] = x01.x * w01.x; a[2] = x01.y * w01.y; a[4] = x23.x * w23.x; a[6] = x23.y * w23.y;
+            a[1] = z01.x * w01.x; a[3] = z01.y * w01.y; a[5] = z23.x * w23.x; a[7] = z23.y * w23.y;
+          }
+          const double* pb = Sst + (8 * ni + g) * kELD + kb;
+          const double2 b01 = *reinterpret_cast<const double2*>(pb), b23 = *reinterpret_cast<const double2*>(pb + 2);
+          const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+          dmma_16x8x16(acc[q], a, b);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < DT; ++q) {
+    if (tinfo[q] < 0) continue;
+    const int mi = tinfo[q] & 255, ni = tinfo[q] >> 8;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int i = 16 * mi + g + ((v & 2) ? 8 : 0);
+      const int k = 8 * ni + 2 * t + (v & 1);
+      if (i >= N) continue;
+      const double val = acc[q][v];
+      if (ni == nt - 1) {
+        if (k == bcol) y[(int64_t)r * N + i] = val;
+      } else if (k <= i) {
+        G[((int64_t)r * N + i) * N + k] = val;
+        if (k != i) G[((int64_t)r * N + k) * N + i] = val;
+      }
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int vi_normal_eq_batched(const double* A, const double* value, const double* error, const double* weight,
@@ -325,8 +460,22 @@ extern "C" int vi_normal_eq_batched(const double* A, const double* value, const 
     return VI_EUNSUPPORTED;
   }
   const int cols = (16 * mt > 8 * nt) ? 16 * mt : 8 * nt;
-  const int ld = dmma_ld(cols);
   const int tpw = (ntiles + kDW - 1) / kDW;
+  if (Wm && bm) {
+    // masked weights / data already materialised by k_prep: streaming variant
+    size_t smem2 = ((size_t)kEStages * cols * kELD + kEStages * kEJ) * sizeof(double) + 512;
+    if (smem2 <= 227 * 1024) {
+      if (tpw <= 9) {
+        VI_CUDA(cudaFuncSetAttribute(k_ne_dmma2<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        VI_KERNEL(VI_K_NORMAL_EQ, s, k_ne_dmma2<9><<<(unsigned)R, kDW * 32, smem2, s>>>(A, Wm, bm, P, N, mt, nt, cols, ntiles, tpw, G, y));
+      } else {
+        VI_CUDA(cudaFuncSetAttribute(k_ne_dmma2<kDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        VI_KERNEL(VI_K_NORMAL_EQ, s, k_ne_dmma2<kDT><<<(unsigned)R, kDW * 32, smem2, s>>>(A, Wm, bm, P, N, mt, nt, cols, ntiles, tpw, G, y));
+      }
+      return VI_OK;
+    }
+  }
+  const int ld = dmma_ld(cols);
   size_t smem = ((size_t)kDStages * kDJ * ld + kDStages * kDJ) * sizeof(double) + 512;
   VI_CUDA(cudaFuncSetAttribute(k_ne_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   VI_KERNEL(VI_K_NORMAL_EQ, s, k_ne_dmma<<<(unsigned)R, kDW * 32, smem, s>>>(A, value, error, weight, P, N, mt, nt, ld, ntiles, tpw, G, y));
