@@ -183,6 +183,43 @@ __device__ __forceinline__ vi_tape tape_of(const SysBuf& B, int64_t s) {
   return vi_tape{{cs, 2}, {cs + 1, 2}, {B.tix + s * (int64_t)B.tapecap, 1}, B.tapecap};
 }
 
+// Tape replays for k_apply: the tape of one system is contiguous ((c, s) pairs + index), so a batch of
+// eight entries is fetched with 128-bit loads while the previous batch is being applied (the rotations
+// themselves are a dependent chain on the shared vector w).  dir = +1: w <- Z^T w, dir = -1: w <- Z w.
+template <int DIR>
+__device__ __forceinline__ void tape_replay(double* __restrict__ w, const double2* __restrict__ cs,
+                                            const int32_t* __restrict__ ix, int32_t nrot) {
+  constexpr int NB = 8;
+  double2 cur[NB], nxt[NB];
+  int32_t icur[NB], inxt[NB];
+  const int32_t nbatch = (nrot + NB - 1) / NB;
+  auto fetch = [&](int32_t bidx, double2 (&c)[NB], int32_t (&id)[NB]) {
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int32_t t = bidx * NB + q;
+      const int32_t tt = (DIR > 0) ? t : nrot - 1 - t;
+      const bool ok = t < nrot;
+      c[q] = ok ? cs[tt] : make_double2(1.0, 0.0);
+      id[q] = ok ? ix[tt] : 0;
+    }
+  };
+  if (nbatch > 0) fetch(0, cur, icur);
+  for (int32_t b = 0; b < nbatch; ++b) {
+    if (b + 1 < nbatch) fetch(b + 1, nxt, inxt);
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int pi = icur[q] >> 1;
+      const int pj = (icur[q] & 1) ? pi - 1 : pi + 1;
+      const double c = cur[q].x, sn = cur[q].y;
+      const double a = w[pi], bb = w[pj];
+      if (DIR > 0) { w[pj] = sn * a + c * bb; w[pi] = c * a - sn * bb; }
+      else { w[pi] = c * a + sn * bb; w[pj] = c * bb - sn * a; }
+    }
+#pragma unroll
+    for (int q = 0; q < NB; ++q) { cur[q] = nxt[q]; icur[q] = inxt[q]; }
+  }
+}
+
 // QL proper, one THREAD per system: eigenvalues + rotation tape (vi_tql_values).  d and e (2n doubles)
 // sit on the dependency chain of every rotation, so they live in shared memory laid out [i][thread]
 // (a lane always hits its own bank pair whatever i it is at).  Leaves the eigenvalues in B.d, the
@@ -230,9 +267,10 @@ k_apply(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, int32_t
   const int64_t base = ileave(s, n);
   for (int i = lane; i < n; i += 32) w[i] = B.g[base + (int64_t)i * 32];
   __syncwarp();
-  const vi_tape tape = tape_of(B, s);
+  const double2* tcs = reinterpret_cast<const double2*>(B.tcs + s * (int64_t)B.tapecap * 2);
+  const int32_t* tix = B.tix + s * (int64_t)B.tapecap;
   const int32_t nrot = B.nrot[s];
-  vi_tape_apply_zt(vi_svec{w, 1}, tape, nrot);
+  tape_replay<+1>(w, tcs, tix, nrot);
   __syncwarp();
   // truncated division by the eigenvalues
   double lmax = 0.0;
@@ -249,7 +287,7 @@ k_apply(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, int32_t
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
   __syncwarp();
-  vi_tape_apply_z(vi_svec{w, 1}, tape, nrot);
+  tape_replay<-1>(w, tcs, tix, nrot);
   __syncwarp();
   for (int i = lane; i < n; i += 32) w[i] *= scl;
   __syncwarp();

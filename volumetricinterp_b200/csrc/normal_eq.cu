@@ -346,6 +346,7 @@ k_ne_dmma2(const double* __restrict__ A, const double* __restrict__ Wm, const do
   }
   const int bcol = 8 * (nt - 1);
   const int nchunk = (P + kEJ - 1) / kEJ;
+  const int rj = tid / 48, cc = tid - 48 * rj;      // kDW * 32 = 384 threads = 8 x 48
   const double* Wr = Wm + (int64_t)r * P;
   const double* br = bm + (int64_t)r * P;
 
@@ -353,12 +354,19 @@ k_ne_dmma2(const double* __restrict__ A, const double* __restrict__ Wm, const do
     const int st = chunk % kEStages;
     double* dst = S + (size_t)st * cols * kELD;
     const int j0 = chunk * kEJ;
-    for (int e = tid; e < kEJ * N; e += blockDim.x) {
-      const int jj = e / N, c = e - jj * N;
+    // thread (rj, cc): gates rj, rj+8, rj+16, rj+24 x columns cc, cc+48, ... (no division in the loop;
+    // 48 consecutive lanes read 384 contiguous bytes of one row of A)
+#pragma unroll
+    for (int q = 0; q < kEJ / 8; ++q) {
+      const int jj = rj + 8 * q;
       const int j = j0 + jj;
-      double* d = dst + c * kELD + gate_slot(jj);
-      if (j < P) cp_async8(d, A + (int64_t)j * N + c);
-      else *d = 0.0;
+      const int sl = gate_slot(jj);
+      if (j < P) {
+        const double* src = A + (int64_t)j * N;
+        for (int c = cc; c < N; c += 48) cp_async8(dst + c * kELD + sl, src + c);
+      } else {
+        for (int c = cc; c < N; c += 48) dst[c * kELD + sl] = 0.0;
+      }
     }
     if (tid < kEJ) {
       const int j = j0 + tid, sl = gate_slot(tid);
