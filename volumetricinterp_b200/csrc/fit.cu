@@ -183,40 +183,39 @@ __device__ __forceinline__ vi_tape tape_of(const SysBuf& B, int64_t s) {
   return vi_tape{{cs, 2}, {cs + 1, 2}, {B.tix + s * (int64_t)B.tapecap, 1}, B.tapecap};
 }
 
-// Tape replays for k_apply: the tape of one system is contiguous ((c, s) pairs + index), so a batch of
-// eight entries is fetched with 128-bit loads while the previous batch is being applied (the rotations
-// themselves are a dependent chain on the shared vector w).  dir = +1: w <- Z^T w, dir = -1: w <- Z w.
+// Tape replays for k_apply: the tape of one system is contiguous ((c, s) pairs + index).  The warp
+// fetches 32 entries at a time, one per lane (coalesced 128-bit loads, next batch in flight while the
+// current one is applied), and broadcasts them lane by lane with shuffles; the rotations themselves are
+// a dependent chain on the shared vector w that every lane executes identically.
+// DIR = +1: w <- Z^T w (tape order), DIR = -1: w <- Z w (reverse order).
 template <int DIR>
 __device__ __forceinline__ void tape_replay(double* __restrict__ w, const double2* __restrict__ cs,
-                                            const int32_t* __restrict__ ix, int32_t nrot) {
-  constexpr int NB = 8;
-  double2 cur[NB], nxt[NB];
-  int32_t icur[NB], inxt[NB];
-  const int32_t nbatch = (nrot + NB - 1) / NB;
-  auto fetch = [&](int32_t bidx, double2 (&c)[NB], int32_t (&id)[NB]) {
-#pragma unroll
-    for (int q = 0; q < NB; ++q) {
-      const int32_t t = bidx * NB + q;
-      const int32_t tt = (DIR > 0) ? t : nrot - 1 - t;
-      const bool ok = t < nrot;
-      c[q] = ok ? cs[tt] : make_double2(1.0, 0.0);
-      id[q] = ok ? ix[tt] : 0;
-    }
+                                            const int32_t* __restrict__ ix, int32_t nrot, int lane) {
+  const int32_t nbatch = (nrot + 31) / 32;
+  auto fetch = [&](int32_t bidx, double2& c, int32_t& id) {
+    const int32_t t = bidx * 32 + lane;
+    const int32_t tt = (DIR > 0) ? t : nrot - 1 - t;
+    const bool ok = t < nrot;
+    c = ok ? cs[tt] : make_double2(1.0, 0.0);       // identity rotation past the end
+    id = ok ? ix[tt] : 0;
   };
+  double2 cur, nxt = make_double2(1.0, 0.0);
+  int32_t icur, inxt = 0;
   if (nbatch > 0) fetch(0, cur, icur);
   for (int32_t b = 0; b < nbatch; ++b) {
     if (b + 1 < nbatch) fetch(b + 1, nxt, inxt);
-#pragma unroll
-    for (int q = 0; q < NB; ++q) {
-      const int pi = icur[q] >> 1;
-      const int pj = (icur[q] & 1) ? pi - 1 : pi + 1;
-      const double c = cur[q].x, sn = cur[q].y;
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) {
+      const double c = __shfl_sync(0xffffffffu, cur.x, q);
+      const double sn = __shfl_sync(0xffffffffu, cur.y, q);
+      const int code = __shfl_sync(0xffffffffu, icur, q);
+      const int pi = code >> 1;
+      const int pj = (code & 1) ? pi - 1 : pi + 1;
       const double a = w[pi], bb = w[pj];
       if (DIR > 0) { w[pj] = sn * a + c * bb; w[pi] = c * a - sn * bb; }
       else { w[pi] = c * a + sn * bb; w[pj] = c * bb - sn * a; }
     }
-#pragma unroll
-    for (int q = 0; q < NB; ++q) { cur[q] = nxt[q]; icur[q] = inxt[q]; }
+    cur = nxt; icur = inxt;
   }
 }
 
@@ -270,7 +269,7 @@ k_apply(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, int32_t
   const double2* tcs = reinterpret_cast<const double2*>(B.tcs + s * (int64_t)B.tapecap * 2);
   const int32_t* tix = B.tix + s * (int64_t)B.tapecap;
   const int32_t nrot = B.nrot[s];
-  tape_replay<+1>(w, tcs, tix, nrot);
+  tape_replay<+1>(w, tcs, tix, nrot, lane);
   __syncwarp();
   // truncated division by the eigenvalues
   double lmax = 0.0;
@@ -287,7 +286,7 @@ k_apply(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, int32_t
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
   __syncwarp();
-  tape_replay<-1>(w, tcs, tix, nrot);
+  tape_replay<-1>(w, tcs, tix, nrot, lane);
   __syncwarp();
   for (int i = lane; i < n; i += 32) w[i] *= scl;
   __syncwarp();
