@@ -90,10 +90,7 @@ struct vi_tri_ws {
 
 VI_HD int vi_tri_ld(int n) { return (n + 2) & ~1; }
 VI_HD int vi_tri_npair(int n) { return (n + 1) / 2; }
-#define VI_TRI_NGMAX 24   // most row groups a step may use (bounds the partial-sum scratch)
-// row groups available when `pa` column pairs are still active: all nt threads stay busy as the matrix shrinks
-VI_HD int vi_tri_groups_for(int pa, int nt) { int ng = nt / (pa < 1 ? 1 : pa); ng = ng < 1 ? 1 : ng; return ng > VI_TRI_NGMAX ? VI_TRI_NGMAX : ng; }
-VI_HD int vi_tri_groups(int n, int nt) { (void)n; (void)nt; return VI_TRI_NGMAX; }
+VI_HD int vi_tri_groups(int n, int nt) { int ng = nt / vi_tri_npair(n); return ng < 1 ? 1 : ng; }
 // doubles of CTA-shared storage needed besides X
 VI_HD int vi_tri_aux_doubles(int n, int nt) {
   return 4 * (n + 2) + (n + 2) + 6 * n + (nt > n ? nt : n) + vi_tri_groups(n, nt) * 2 * vi_tri_npair(n) + 8;
@@ -176,13 +173,9 @@ VI_HD void vi_tri_reduce(const vi_tri_ws& S, int n, double* V, int tid, int nt) 
   (void)tid;
   const int ld = S.ld;
   const int npair = vi_tri_npair(n), npad = 2 * npair;
+  const int ng = vi_tri_groups(n, nt);
   for (int k = 0; k + 1 < n; ++k) {
     const int lo1 = k + 1;
-    // dense re-mapping: only the column pairs p0 .. npair-1 are still active; the threads freed by the
-    // dead pairs become additional row groups
-    const int p0 = lo1 / 2;
-    const int pa = npair - p0;
-    const int ng = vi_tri_groups_for(pa, nt);
     // ---- A: reflector k from the pivot column --------------------------------------------------
     VI_PHASE(
       double tau = 0.0; double beta = 0.0; double scale = 0.0;
@@ -218,9 +211,9 @@ VI_HD void vi_tri_reduce(const vi_tri_ws& S, int n, double* V, int tid, int nt) 
     // ---- B: deferred update of reflector k-1 fused with the mat-vec for reflector k -------------
     VI_PHASE(
       {
-        const int g = tid / pa; const int cp = p0 + (tid - g * pa);
+        const int g = tid / npair; const int cp = tid - g * npair;
         const int c0 = 2 * cp;
-        if (g < ng) {
+        if (g < ng && c0 + 1 >= lo1) {
           const double vc0 = S.vw[4 * c0]; const double wc0 = S.vw[4 * c0 + 1];
           const double vc1 = S.vw[4 * c0 + 4]; const double wc1 = S.vw[4 * c0 + 5];
           double a0 = 0.0; double a1 = 0.0;
