@@ -130,8 +130,33 @@ def fit_records(model, lat, lon, alt, value, error, reg_matrices=None, method='c
                                                                 systems, want_cov)
         nsolve += ns
         outs.append((Cf, dC, chi2, lam, rank, status))
-    cat = lambda i: torch.cat([o[i] for o in outs]) if outs and outs[0][i] is not None else None
+    cat = lambda i: (outs[0][i] if len(outs) == 1 else torch.cat([o[i] for o in outs])) \
+        if outs and outs[0][i] is not None else None
     res = [cat(i) for i in range(6)]
     if to_host:
-        res = [t.cpu().numpy() if t is not None else None for t in res]
+        res = _to_host(res, dev)
     return FitResult(*res, nsolve=nsolve)
+
+
+_pinned = {}
+
+
+def _to_host(tensors, dev):
+    """Device results -> numpy through cached pinned staging buffers (one async copy each, one sync).
+    The returned arrays own their memory (copied out of the staging buffers)."""
+    import torch
+    staged = []
+    for i, t in enumerate(tensors):
+        if t is None:
+            staged.append(None)
+            continue
+        key = (i, t.dtype)
+        buf = _pinned.get(key)
+        if buf is None or buf.numel() < t.numel():
+            buf = torch.empty((t.numel(),), dtype=t.dtype).pin_memory()
+            _pinned[key] = buf
+        view = buf[: t.numel()].view(t.shape)
+        view.copy_(t, non_blocking=True)
+        staged.append(view)
+    torch.cuda.synchronize(dev)
+    return [v.numpy().copy() if v is not None else None for v in staged]
