@@ -183,39 +183,83 @@ __device__ __forceinline__ vi_tape tape_of(const SysBuf& B, int64_t s) {
   return vi_tape{{cs, 2}, {cs + 1, 2}, {B.tix + s * (int64_t)B.tapecap, 1}, B.tapecap};
 }
 
-// Tape replays for k_apply: the tape of one system is contiguous ((c, s) pairs + index).  The warp
-// fetches 32 entries at a time, one per lane (coalesced 128-bit loads, next batch in flight while the
-// current one is applied), and broadcasts them lane by lane with shuffles; the rotations themselves are
-// a dependent chain on the shared vector w that every lane executes identically.
-// DIR = +1: w <- Z^T w (tape order), DIR = -1: w <- Z w (reverse order).
+// Tape replay, one THREAD per system (every lane does distinct work; a warp-per-system version spent
+// 26 warp-instructions per rotation on redundant lanes).  The lane's vector lives in shared memory laid
+// out [i][lane]; its tape is contiguous in global memory and is fetched four entries ahead.
+// DIR = +1: w <- Z^T w (tape order), DIR = -1: w <- Z w (reverse order).  Lanes whose tape is shorter
+// than the longest in the warp apply identity rotations.
 template <int DIR>
-__device__ __forceinline__ void tape_replay(double* __restrict__ w, const double2* __restrict__ cs,
-                                            const int32_t* __restrict__ ix, int32_t nrot, int lane) {
-  const int32_t nbatch = (nrot + 31) / 32;
-  auto fetch = [&](int32_t bidx, double2& c, int32_t& id) {
-    const int32_t t = bidx * 32 + lane;
-    const int32_t tt = (DIR > 0) ? t : nrot - 1 - t;
-    const bool ok = t < nrot;
-    c = ok ? cs[tt] : make_double2(1.0, 0.0);       // identity rotation past the end
-    id = ok ? ix[tt] : 0;
+__device__ __forceinline__ void tape_replay(vi_svec w, const double2* __restrict__ cs,
+                                            const int32_t* __restrict__ ix, int32_t nrot, int32_t nmax) {
+  constexpr int NB = 4;
+  double2 cur[NB], nxt[NB];
+  int32_t icur[NB], inxt[NB];
+  auto fetch = [&](int32_t base, double2 (&c)[NB], int32_t (&id)[NB]) {
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int32_t t = base + q;
+      const bool ok = t < nrot;
+      const int32_t tt = ok ? ((DIR > 0) ? t : nrot - 1 - t) : 0;
+      const double2 v = cs[tt];
+      const int32_t code = ix[tt];
+      c[q] = ok ? v : make_double2(1.0, 0.0);
+      id[q] = ok ? code : 0;
+    }
   };
-  double2 cur, nxt = make_double2(1.0, 0.0);
-  int32_t icur, inxt = 0;
-  if (nbatch > 0) fetch(0, cur, icur);
-  for (int32_t b = 0; b < nbatch; ++b) {
-    if (b + 1 < nbatch) fetch(b + 1, nxt, inxt);
-#pragma unroll 8
-    for (int q = 0; q < 32; ++q) {
-      const double c = __shfl_sync(0xffffffffu, cur.x, q);
-      const double sn = __shfl_sync(0xffffffffu, cur.y, q);
-      const int code = __shfl_sync(0xffffffffu, icur, q);
-      const int pi = code >> 1;
-      const int pj = (code & 1) ? pi - 1 : pi + 1;
+  fetch(0, cur, icur);
+  for (int32_t base = 0; base < nmax; base += NB) {
+    fetch(base + NB, nxt, inxt);
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int pi = icur[q] >> 1;
+      const int pj = (icur[q] & 1) ? pi - 1 : pi + 1;
+      const double c = cur[q].x, sn = cur[q].y;
       const double a = w[pi], bb = w[pj];
       if (DIR > 0) { w[pj] = sn * a + c * bb; w[pi] = c * a - sn * bb; }
       else { w[pi] = c * a + sn * bb; w[pj] = c * bb - sn * a; }
     }
-    cur = nxt; icur = inxt;
+#pragma unroll
+    for (int q = 0; q < NB; ++q) { cur[q] = nxt[q]; icur[q] = inxt[q]; }
+  }
+}
+
+// u = Z L^+ Z^T g, one thread per system: forward replay, spectral cut-off (|l| > rcond max|l|: gelsd's
+// rule), backward replay.  Result (scaled back by 2^-ex) returns to B.g; rank to B.rank.
+constexpr int kReplayThreads = 64;
+__global__ void __launch_bounds__(kReplayThreads)
+k_replay(int64_t nsys, SysBuf B, double rcond) {
+  extern __shared__ __align__(16) double sm[];
+  const int tid = threadIdx.x, n = B.n;
+  const int64_t s = (int64_t)blockIdx.x * kReplayThreads + tid;
+  const bool act = (s < nsys) && (B.st[s] == VI_ST_OK);
+  vi_svec w{sm + tid, kReplayThreads};
+  const int64_t sc = act ? s : 0;
+  const int64_t base = ileave(sc, n);
+  const int32_t nrot = act ? B.nrot[sc] : 0;
+  int32_t nmax = nrot;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+  if (nmax == 0 && !act) { /* whole warp may still need the divide for systems without rotations */ }
+  for (int i = 0; i < n; ++i) w[i] = act ? B.g[base + (int64_t)i * 32] : 0.0;
+  const double2* tcs = reinterpret_cast<const double2*>(B.tcs + sc * (int64_t)B.tapecap * 2);
+  const int32_t* tix = B.tix + sc * (int64_t)B.tapecap;
+  tape_replay<+1>(w, tcs, tix, nrot, nmax);
+  if (act) {
+    double lmax = 0.0;
+    for (int i = 0; i < n; ++i) lmax = fmax(lmax, fabs(B.d[base + (int64_t)i * 32]));
+    const double cut = rcond * lmax;
+    int rank = 0;
+    for (int i = 0; i < n; ++i) {
+      const double l = B.d[base + (int64_t)i * 32];
+      if (fabs(l) > cut) { w[i] = w[i] / l; ++rank; }
+      else w[i] = 0.0;
+    }
+    B.rank[s] = rank;
+  }
+  tape_replay<-1>(w, tcs, tix, nrot, nmax);
+  if (act) {
+    const double scl = B.scl[s];
+    for (int i = 0; i < n; ++i) B.g[base + (int64_t)i * 32] = w[i] * scl;
   }
 }
 
@@ -242,13 +286,11 @@ __global__ void k_tql_smem(int64_t nsys, SysBuf B) {
   for (int i = 0; i < n; ++i) B.d[base + (int64_t)i * 32] = d[i];
 }
 
-// c = Q Z L^+ Z^T (Q^T y), one WARP per system.  The two tape replays are dependent chains (all lanes
-// run them redundantly on the warp's shared vector; tape entries arrive as broadcast loads fetched four
-// ahead); the spectral cut-off (|l_i| > rcond max|l|: gelsd's rule) and the reflectors are applied
-// cooperatively (coalesced V rows, shuffle-tree dot products).
+// c = Q u, one WARP per system: the reflectors are applied cooperatively (coalesced V rows, shuffle-tree
+// dot products) to the vector k_replay left in B.g.
 constexpr int kApplyWarps = 8;
 __global__ void __launch_bounds__(kApplyWarps * 32)
-k_apply(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, int32_t* __restrict__ rank_out) {
+k_apply(int64_t nsys, SysBuf B, double* __restrict__ Cout, int32_t* __restrict__ rank_out) {
   extern __shared__ __align__(16) double sm[];
   const int n = B.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t s = (int64_t)blockIdx.x * kApplyWarps + warp;
@@ -266,30 +308,6 @@ k_apply(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, int32_t
   const int64_t base = ileave(s, n);
   for (int i = lane; i < n; i += 32) w[i] = B.g[base + (int64_t)i * 32];
   __syncwarp();
-  const double2* tcs = reinterpret_cast<const double2*>(B.tcs + s * (int64_t)B.tapecap * 2);
-  const int32_t* tix = B.tix + s * (int64_t)B.tapecap;
-  const int32_t nrot = B.nrot[s];
-  tape_replay<+1>(w, tcs, tix, nrot, lane);
-  __syncwarp();
-  // truncated division by the eigenvalues
-  double lmax = 0.0;
-  for (int i = lane; i < n; i += 32) lmax = fmax(lmax, fabs(B.d[base + (int64_t)i * 32]));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-  const double cut = rcond * lmax, scl = B.scl[s];
-  int rank = 0;
-  for (int i = lane; i < n; i += 32) {
-    const double l = B.d[base + (int64_t)i * 32];
-    if (fabs(l) > cut) { w[i] = w[i] / l; ++rank; }
-    else w[i] = 0.0;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
-  __syncwarp();
-  tape_replay<-1>(w, tcs, tix, nrot, lane);
-  __syncwarp();
-  for (int i = lane; i < n; i += 32) w[i] *= scl;
-  __syncwarp();
   const double* V = B.V + s * (int64_t)n * n;
   for (int j = n - 3; j >= 0; --j) {
     const double t = B.tau[base + (int64_t)j * 32];
@@ -304,7 +322,7 @@ k_apply(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, int32_t
     __syncwarp();
   }
   for (int i = lane; i < n; i += 32) Cs[i] = w[i];
-  if (lane == 0) rank_out[s] = rank;
+  if (lane == 0) rank_out[s] = B.rank[s];
 }
 
 // ---- covariance: dC = H (A^T W A) H, H = pinv(X)  (interpolate.py:464-467) ---------------------
@@ -814,8 +832,11 @@ int run_ql(int64_t cnt, const SysBuf& B, cudaStream_t s, bool* split) {
 int run_apply(int64_t cnt, const SysBuf& B, double rcond, double* Cout, int32_t* rank_out, cudaStream_t s, bool split) {
   if (cnt <= 0) return VI_OK;
   if (split) {
+    size_t smem1 = (size_t)kReplayThreads * B.n * sizeof(double);
+    VI_CUDA(cudaFuncSetAttribute(k_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    VI_KERNEL(VI_K_APPLY, s, k_replay<<<blocks(cnt, kReplayThreads), kReplayThreads, smem1, s>>>(cnt, B, rcond));
     size_t smem2 = (size_t)kApplyWarps * B.n * sizeof(double);
-    VI_KERNEL(VI_K_APPLY, s, k_apply<<<blocks(cnt, kApplyWarps), kApplyWarps * 32, smem2, s>>>(cnt, B, rcond, Cout, rank_out));
+    VI_KERNEL(VI_K_APPLY, s, k_apply<<<blocks(cnt, kApplyWarps), kApplyWarps * 32, smem2, s>>>(cnt, B, Cout, rank_out));
   } else {
     VI_KERNEL(VI_K_TQL, s, k_tql<<<blocks(cnt, 64), 64, 0, s>>>(cnt, B, rcond, Cout, rank_out));
   }
