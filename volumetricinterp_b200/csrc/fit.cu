@@ -191,7 +191,7 @@ __device__ __forceinline__ vi_tape tape_of(const SysBuf& B, int64_t s) {
 template <int DIR>
 __device__ __forceinline__ void tape_replay(vi_svec w, const double2* __restrict__ cs,
                                             const int32_t* __restrict__ ix, int32_t nrot, int32_t nmax) {
-  constexpr int NB = 4;
+  constexpr int NB = 8;
   double2 cur[NB], nxt[NB];
   int32_t icur[NB], inxt[NB];
   auto fetch = [&](int32_t base, double2 (&c)[NB], int32_t (&id)[NB]) {
