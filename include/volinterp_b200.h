@@ -51,6 +51,7 @@ extern "C" {
 /* regularisation-parameter method (REGULARIZATION_METHOD) */
 #define VI_METHOD_NONE 0    /* empty REGULARIZATION_LIST: plain lstsq per record */
 #define VI_METHOD_CHI2 1    /* interpolate.py:152-218 */
+#define VI_METHOD_GCV 2     /* interpolate.py:263-351 (leave-one-gate-out residual sum, Nelder-Mead) */
 
 /* normal-equation modes */
 #define VI_NE_STRICT 0      /* reference summation order, bit-identical to np.einsum (interpolate.py:456,458) */
@@ -102,10 +103,11 @@ int vi_solve_batched(const double* G, const double* y, const int32_t* rec, const
 
 /* interpolate.py:555-569 for R records: find_reg_param (:97-147, chi2 :152-218, chi2objfunct
  * :220-261), NaN-record rule (:558-563), final eval_C (:566) and chi^2 (:569).
- * At: N x P (transposed design matrix); Wm/bm: masked weights/data from vi_normal_eq_batched.
+ * At: N x P (transposed design matrix); A: P x N (row-major; needed by VI_METHOD_GCV only, else may be
+ * NULL); Wm/bm: masked weights/data from vi_normal_eq_batched.
  * regmats: nreg x N x N.  Outputs: C R x N, dC R x N x N (may be NULL), chi2 R, lam R x nreg,
  * rank R, status R, nsolve (optional, 1 int64: number of eigen-systems solved). */
-int vi_fit_batched(const double* At, const double* Wm, const double* bm,
+int vi_fit_batched(const double* At, const double* A, const double* Wm, const double* bm,
                    const double* G, const double* y, const int32_t* npts,
                    int32_t R, int32_t P, int32_t N,
                    const double* regmats, int32_t nreg, int32_t method,

@@ -10,6 +10,7 @@
 #include "../volumetricinterp_b200/csrc/vi_tql.h"
 #include "../volumetricinterp_b200/csrc/vi_brent.h"
 #include "../volumetricinterp_b200/csrc/vi_tridiag.h"
+#include "../volumetricinterp_b200/csrc/vi_nm.h"
 
 extern "C" {
 
@@ -95,6 +96,22 @@ int h_brentq(h_fn f, double xa, double xb, double* root, double* xs, int* nfev) 
   *root = b.root;
   *nfev = n;
   return b.done;
+}
+
+// Nelder-Mead state machine driven by a callback; xs receives every abscissa evaluated.
+int h_nm_minimize(h_fn f, double x0, double* xmin, double* xs, int* nfev, int* nit) {
+  vi_nm s;
+  vi_nm_init(s, x0);
+  double x;
+  int n = 0;
+  while (vi_nm_next(s, &x)) {
+    xs[n++] = x;
+    vi_nm_feed(s, f(x));
+  }
+  *xmin = s.x0;
+  *nfev = s.fcalls;
+  *nit = s.iters;
+  return s.success;
 }
 
 void h_chi2_bracket(const double* table, int npts, int* status, int* k_lo, double* nu) {

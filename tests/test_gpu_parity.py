@@ -239,6 +239,28 @@ def test_fit_host_entry_point(cuda):
     assert np.array_equal(status, ref.status)
 
 
+def test_fit_gcv_method(cuda):
+    """REGULARIZATION_METHOD = gcv (interpolate.py:263-351): Nelder-Mead on the leave-one-gate-out residual
+    sum.  The simplex abscissae depend on the objective only through comparisons, so the GPU search lands
+    on the reference's alpha exactly unless two objective values tie to ~1e-10."""
+    from volumetricinterp_b200 import fit
+    g = load_golden("lo8_gcv")
+    m = product_model(g)
+    res = fit.fit_records(m, g["lat"], g["lon"], g["alt"], g["value"], g["error"], g["regs"], "gcv",
+                          ne_mode=0, weight=g["error"] ** -2, device=cuda, want_cov=True)
+    assert (res.status == 0).all()
+    assert np.allclose(res.reg_params, g["lam"], rtol=1e-12, atol=0), (res.reg_params, g["lam"])
+    for r in range(g["value"].shape[0]):
+        cref = g["Coeffs"][r]
+        ok = np.isfinite(g["value"][r])
+        X = rp.normal_equations(g["A"][ok], g["error"][r][ok] ** -2, g["value"][r][ok])[0] + g["lam"][r, 0] * g["regs"][0]
+        s = np.linalg.svd(X, compute_uv=False)
+        tol = max(1e-9, 500 * EPS * s[0] / s[-1])
+        assert np.max(np.abs(res.Coeffs[r] - cref)) <= tol * np.abs(cref).max()
+        assert abs(res.chi_sq[r] - g["chi_sq"][r]) <= 1e-8 * g["chi_sq"][r]
+        assert np.max(np.abs(res.Covariance[r] - g["Covariance"][r])) <= max(1e-8, 2000 * EPS * s[0] / s[-1]) * np.abs(g["Covariance"][r]).max()
+
+
 def test_fit_status_codes(cuda):
     from volumetricinterp_b200 import _native
     g = load_golden("lo8")

@@ -207,3 +207,28 @@ def test_bracket_walk(harness):
         assert (st.value, k.value) == (est, ek)
         if est != 2:
             assert nu.value == enu
+
+
+def test_nelder_mead_state_machine_replays_scipy(harness):
+    """Same abscissae, same minimiser, same nit / nfev / success as scipy's Nelder-Mead (interpolate.py:291)."""
+    FN = C.CFUNCTYPE(C.c_double, C.c_double)
+    cases = [(lambda a: (a + 24.3) ** 2 + 3.0, -20.0),
+             (lambda a: np.cosh(0.3 * (a + 17.77)) * 1e3, -20.0),
+             (lambda a: abs(a + 31.4159) ** 1.5, -20.0),
+             (lambda a: 5.0 + 0.0 * a, -20.0),                       # flat: converges on the tolerances
+             (lambda a: -a * 1e3, -20.0),                            # unbounded: runs into maxiter/maxfev -> failure
+             (lambda a: float("nan") if a < -22 else (a + 21.5) ** 2, -20.0),
+             (lambda a: (a - 0.3) ** 2, 0.0)]                        # zero start: zdelt branch
+    for f, x0 in cases:
+        xs_ref = []
+        def fr(x):
+            xs_ref.append(float(x[0]))
+            return f(float(x[0]))
+        ref = scipy.optimize.minimize(fr, x0, method="Nelder-Mead")
+        xs = np.zeros(512)
+        xmin, nfev, nit = C.c_double(0), C.c_int(0), C.c_int(0)
+        ok = harness.h_nm_minimize(FN(lambda x: float(f(x))), C.c_double(x0), C.byref(xmin), dptr(xs), C.byref(nfev),
+                                   C.byref(nit))
+        assert list(xs[:nfev.value]) == xs_ref, (x0, xs[:5], xs_ref[:5])
+        assert xmin.value == ref.x[0] and nfev.value == ref.nfev and bool(ok) == bool(ref.success)
+        assert nit.value == ref.nit

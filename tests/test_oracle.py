@@ -8,7 +8,7 @@ import scipy.special as sp
 from conftest import load_golden, oracle_model
 import ref_port as rp
 
-CASES = ["lo8", "lo12", "lo12_two", "mid27", "rbf27"]
+CASES = ["lo8", "lo12", "lo12_two", "mid27", "rbf27", "lo8_gcv"]
 
 
 @pytest.mark.parametrize("name", CASES + ["c1_144"])
@@ -23,7 +23,8 @@ def test_fit_bit_identical(name):
     g = load_golden(name)
     m = oracle_model(g)
     regs = dict(zip(g["reglist"], g["regs"]))
-    C, dC, c2, lam = rp.fit_records(m, g["lat"], g["lon"], g["alt"], g["value"], g["error"], regs, g["reglist"])
+    C, dC, c2, lam = rp.fit_records(m, g["lat"], g["lon"], g["alt"], g["value"], g["error"], regs, g["reglist"],
+                                    method=g["default_keys"].get("REGULARIZATION_METHOD", "chi2"))
     assert np.array_equal(C, g["Coeffs"], equal_nan=True)
     assert np.array_equal(c2, g["chi_sq"], equal_nan=True)
     assert np.array_equal(dC, g["Covariance"], equal_nan=True)

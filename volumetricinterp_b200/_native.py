@@ -50,7 +50,7 @@ SIGNATURES = {
     "vi_normal_eq_batched": [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "vi_fit_workspace_bytes": [_i32, _i32, _i32, _i32, _i64, C.POINTER(_i64)],
     "vi_solve_batched": [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _dbl, _ptr, _ptr, _ptr, _ptr, _i64, _ptr],
-    "vi_fit_batched": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _ptr, _i32, _i32,
+    "vi_fit_batched": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _ptr, _i32, _i32,
                        _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, C.POINTER(_i64), _ptr, _i64, _ptr],
     "vi_estimate_sphharmlag": [_ptr, _ptr, _ptr, _i64, _shl, _ptr, _i32, _ptr, _i32, _ptr, _ptr],
     "vi_estimate_radbasfun": [_ptr, _ptr, _ptr, _i64, _ptr, _i32, _dbl, _ptr, _i32, _ptr, _i32, _ptr, _ptr],
@@ -72,7 +72,7 @@ def profile_read():
     check(lib().vi_profile_read(ms, cnt, n))
     return dict(zip(PROFILE_KINDS, list(ms))), dict(zip(PROFILE_KINDS, list(cnt)))
 NE_STRICT, NE_FAST = 0, 1
-METHOD_NONE, METHOD_CHI2 = 0, 1
+METHOD_NONE, METHOD_CHI2, METHOD_GCV = 0, 1, 2
 
 
 def lib():

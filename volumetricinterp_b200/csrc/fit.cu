@@ -24,6 +24,7 @@
 #include <math.h>
 #include <vector>
 #include "vi_brent.h"
+#include "vi_nm.h"
 #include "vi_tql.h"
 #include "vi_tridiag.h"
 
@@ -51,8 +52,11 @@ struct SysBuf {
   int n, nreg, tapecap, nt, use_gx, ld, nchunk;
   size_t smem;
   double *V, *d, *e, *g, *tau, *scl, *tcs, *lam, *Csys, *chi2, *chi2p, *Xg;
-  int32_t *tix, *st, *rec, *rank, *nrot, *unit, *kidx;
+  int32_t *tix, *st, *rec, *rank, *nrot, *unit, *kidx, *gate;
 };
+
+// leave-one-gate-out systems (GCV): system s is built from G - w a a^T, y - w b a with a = A[gate[s]]
+struct Downdate { const double* A; const double* Wm; const double* bm; int P; };
 
 constexpr int kChiGates = 1024;    // gates per CTA in k_chi2 (partial sums combined in fixed order)
 
@@ -95,6 +99,7 @@ void sysbuf_carve(Bump& b, SysBuf& S, int64_t cap, int n, int nreg, int P) {
   S.nrot = b.take<int32_t>(cap);
   S.unit = b.take<int32_t>(cap);
   S.kidx = b.take<int32_t>(cap);
+  S.gate = b.take<int32_t>(cap);
   S.Xg = S.use_gx ? b.take<double>(cap * n * S.ld) : nullptr;
 }
 
@@ -109,6 +114,9 @@ struct UnitBuf {      // one search unit = (record, regulariser)
   int32_t* tabbad;    // U
   int32_t* kstar;     // U
   int64_t* off;       // U + 1: exclusive prefix sum of the number of distinct table systems per unit
+  vi_nm* nm;          // U   Nelder-Mead state (GCV)
+  double* fsum;       // U   GCV objective being accumulated
+  double* alpha;      // U   abscissa under evaluation
   int32_t* count;     // 1
 };
 
@@ -121,6 +129,9 @@ void unit_carve(Bump& b, UnitBuf& Ub, int64_t U) {
   Ub.tabbad = b.take<int32_t>(U);
   Ub.kstar = b.take<int32_t>(U);
   Ub.off = b.take<int64_t>(U + 1);
+  Ub.nm = b.take<vi_nm>(U);
+  Ub.fsum = b.take<double>(U);
+  Ub.alpha = b.take<double>(U);
   Ub.count = b.take<int32_t>(8);
 }
 
@@ -128,6 +139,8 @@ int64_t cov_scratch_bytes(int64_t R, int n) {
   int64_t cc = R < kCovChunk ? R : kCovChunk;
   return (3 * cc * (int64_t)n * n + cc * n) * (int64_t)sizeof(double) + 4096;
 }
+
+int64_t gcv_scratch_bytes(int64_t R, int64_t P, int64_t U) { return R * P * 4 + R * 4 + U * 8 + 4096; }
 
 int64_t per_system_bytes(int n, int nreg, int P) {
   Bump b{nullptr, 0, 0};
@@ -152,7 +165,8 @@ __device__ __forceinline__ int64_t ileave(int64_t s, int n) { return (s >> 5) * 
 
 template <bool GX>
 __global__ void __launch_bounds__(1024)
-k_tridiag(const double* __restrict__ G, const double* __restrict__ y, const double* __restrict__ regs, SysBuf B) {
+k_tridiag(const double* __restrict__ G, const double* __restrict__ y, const double* __restrict__ regs, SysBuf B,
+          Downdate dd) {
   extern __shared__ __align__(16) double sm[];
   const int64_t s = blockIdx.x;
   const int r = B.rec[s];
@@ -164,7 +178,16 @@ k_tridiag(const double* __restrict__ G, const double* __restrict__ y, const doub
   if (GX) { S.X = B.Xg + s * (int64_t)n * S.ld; aux = sm; }
   else { S.X = sm; aux = sm + (size_t)n * S.ld; }      // X stays a provable shared-memory pointer (LDS/STS)
   vi_tri_carve(S, aux, n, nt);
-  vi_tri_load(S, n, G + (int64_t)r * n * n, y + (int64_t)r * n, regs, B.lam + s * (B.nreg > 0 ? B.nreg : 1), B.nreg, tid, nt);
+  const double* arow = nullptr;
+  double wj = 0.0, bj = 0.0;
+  if (dd.A != nullptr) {
+    const int j = B.gate[s];
+    arow = dd.A + (int64_t)j * n;
+    wj = dd.Wm[(int64_t)r * dd.P + j];
+    bj = dd.bm[(int64_t)r * dd.P + j];
+  }
+  vi_tri_load(S, n, G + (int64_t)r * n * n, y + (int64_t)r * n, regs, B.lam + s * (B.nreg > 0 ? B.nreg : 1), B.nreg, tid, nt,
+              arow, wj, bj);
   const bool bad = S.sc[1] != 0.0;
   if (!bad) vi_tri_reduce(S, n, B.V + s * (int64_t)n * n, tid, nt);
   const int64_t base = ileave(s, n);
@@ -719,6 +742,141 @@ __global__ void k_brent_feed(int64_t cnt, SysBuf B, UnitBuf Ub) {
   Ub.br[u] = b;
 }
 
+// ---- GCV (interpolate.py:263-351): leave-one-gate-out residual sum minimised by Nelder-Mead -------
+// validx[r][k] = index of the k-th gate of record r that carries weight (a zero-weight gate adds nothing
+// to the objective and leaves the system unchanged, so it is skipped)
+__global__ void __launch_bounds__(32)
+k_valid_index(int P, const double* __restrict__ Wm, int32_t* __restrict__ validx, int32_t* __restrict__ nvalid) {
+  const int r = blockIdx.x, lane = threadIdx.x;
+  int base = 0;
+  for (int j0 = 0; j0 < P; j0 += 32) {
+    const int j = j0 + lane;
+    const bool ok = (j < P) && (Wm[(int64_t)r * P + j] != 0.0);
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (ok) validx[(int64_t)r * P + base + __popc(m & ((1u << lane) - 1u))] = j;
+    base += __popc(m);
+  }
+  if (lane == 0) nvalid[r] = base;
+}
+
+__global__ void k_nm_init(int64_t U, int nreg, const int32_t* __restrict__ npts, UnitBuf Ub) {
+  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  vi_nm s;
+  vi_nm_init(s, -20.0);                      // alpha0, interpolate.py:288
+  Ub.nm[u] = s;
+  const bool ok = npts[u / nreg] > 0;
+  Ub.active[u] = ok ? 1 : 0;
+  Ub.status[u] = ok ? VI_ST_OK : VI_ST_EMPTY;
+}
+
+// one objective evaluation per active unit: next abscissa, number of systems it needs
+__global__ void k_nm_propose(int64_t U, int nreg, const int32_t* __restrict__ nvalid, UnitBuf Ub, int64_t* __restrict__ cnt) {
+  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  cnt[u] = 0;
+  if (!Ub.active[u]) return;
+  vi_nm s = Ub.nm[u];
+  double x = 0.0;
+  const bool more = vi_nm_next(s, &x);
+  Ub.nm[u] = s;
+  if (!more) {
+    Ub.active[u] = 0;
+    Ub.status[u] = s.success ? VI_ST_OK : VI_ST_NOCONV;   // 'Minima of GCV function could not be found' -> NaN
+    Ub.br[u].root = s.x0;
+    return;
+  }
+  Ub.alpha[u] = x;
+  Ub.fsum[u] = 0.0;
+  cnt[u] = nvalid[u / nreg];
+}
+
+__global__ void __launch_bounds__(1024)
+k_scan_counts(int64_t U, const int64_t* __restrict__ cnt, int64_t* __restrict__ off) {
+  __shared__ int64_t part[1024];
+  const int t = threadIdx.x;
+  const int64_t per = (U + 1023) / 1024;
+  const int64_t a = t * per, b = (a + per < U) ? a + per : U;
+  int64_t sum = 0;
+  for (int64_t u = a; u < b; ++u) sum += cnt[u];
+  part[t] = sum;
+  __syncthreads();
+  if (t == 0) {
+    int64_t run = 0;
+    for (int i = 0; i < 1024; ++i) { int64_t v = part[i]; part[i] = run; run += v; }
+    off[U] = run;
+  }
+  __syncthreads();
+  int64_t run = part[t];
+  for (int64_t u = a; u < b; ++u) { off[u] = run; run += cnt[u]; }
+}
+
+__global__ void k_gcv_setup(int64_t t0, int64_t cnt, int64_t U, int nreg, int P, const int64_t* __restrict__ off,
+                            const int32_t* __restrict__ validx, SysBuf B, UnitBuf Ub) {
+  int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B.cap) return;
+  if (s >= cnt) { B.rec[s] = kSkip; return; }
+  const int64_t t = t0 + s;
+  int64_t lo = 0, hi = U;
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (off[mid] <= t) lo = mid; else hi = mid;
+  }
+  const int64_t u = lo;
+  const int k = (int)(t - off[u]);
+  const int r = (int)(u / nreg), q = (int)(u - (int64_t)r * nreg);
+  B.rec[s] = r;
+  B.unit[s] = (int32_t)u;
+  B.kidx[s] = k;
+  B.gate[s] = validx[(int64_t)r * P + k];
+  const double lamv = exp10(Ub.alpha[u]);
+  for (int i = 0; i < nreg; ++i) B.lam[s * nreg + i] = (i == q) ? lamv : 0.0;
+}
+
+// residual of the left-out gate: (a_j . C - b_j)^2 w_j   (interpolate.py:347-349), one warp per system
+__global__ void __launch_bounds__(256)
+k_gcv_resid(int64_t cnt, int n, Downdate dd, SysBuf B, const double* __restrict__ Csys, double* __restrict__ res) {
+  const int lane = threadIdx.x & 31;
+  const int64_t s = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (s >= cnt) return;
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  if (B.st[s] != VI_ST_OK) { if (lane == 0) res[s] = nan; return; }
+  const int r = B.rec[s], j = B.gate[s];
+  const double* a = dd.A + (int64_t)j * n;
+  const double* c = Csys + s * (int64_t)n;
+  double acc = 0.0;
+  for (int i = lane; i < n; i += 32) acc += a[i] * c[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    const double d = acc - dd.bm[(int64_t)r * dd.P + j];
+    res[s] = (d * d) * dd.Wm[(int64_t)r * dd.P + j];
+  }
+}
+
+// objective[u] += residuals of the unit's systems inside this chunk, in gate order (the reference sums
+// them with Python's sequential sum, interpolate.py:351)
+__global__ void k_gcv_accumulate(int64_t U, int64_t t0, int64_t cnt, const int64_t* __restrict__ off,
+                                 const double* __restrict__ res, UnitBuf Ub) {
+  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  int64_t a = off[u], b = off[u + 1];
+  if (a < t0) a = t0;
+  if (b > t0 + cnt) b = t0 + cnt;
+  if (a >= b) return;
+  double acc = Ub.fsum[u];
+  for (int64_t t = a; t < b; ++t) acc += res[t - t0];
+  Ub.fsum[u] = acc;
+}
+
+__global__ void k_nm_feed(int64_t U, UnitBuf Ub) {
+  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= U || !Ub.active[u]) return;
+  vi_nm s = Ub.nm[u];
+  vi_nm_feed(s, Ub.fsum[u]);
+  Ub.nm[u] = s;
+}
+
 // final phase: records [r0, r0+cnt), slot s = r - r0
 __global__ void k_setup_final(int64_t r0, int64_t cnt, int nreg, int method, const int32_t* __restrict__ npts,
                               SysBuf B, UnitBuf Ub, double* __restrict__ lam_out, int32_t* __restrict__ status_out) {
@@ -730,7 +888,7 @@ __global__ void k_setup_final(int64_t r0, int64_t cnt, int nreg, int method, con
   int worst = VI_ST_OK;
   bool bad = false;
   if (npts[r] <= 0) { worst = VI_ST_EMPTY; bad = true; }
-  if (method == VI_METHOD_CHI2) {
+  if (method != VI_METHOD_NONE) {
     for (int q = 0; q < nreg; ++q) {
       int64_t u = r * nreg + q;
       int st = Ub.status[u];
@@ -801,14 +959,15 @@ __global__ void k_transpose(const double* __restrict__ A, int P, int N, double* 
 // ------------------------------------------------------------------------------------------
 inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
-int run_tridiag(int64_t cnt, const double* G, const double* y, const double* regs, const SysBuf& B, cudaStream_t s) {
+int run_tridiag(int64_t cnt, const double* G, const double* y, const double* regs, const SysBuf& B, cudaStream_t s,
+                Downdate dd = Downdate{nullptr, nullptr, nullptr, 0}) {
   if (cnt <= 0) return VI_OK;
   if (B.use_gx) {
     VI_CUDA(cudaFuncSetAttribute(k_tridiag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
-    VI_KERNEL(VI_K_TRIDIAG, s, k_tridiag<true><<<(unsigned)cnt, B.nt, B.smem, s>>>(G, y, regs, B));
+    VI_KERNEL(VI_K_TRIDIAG, s, k_tridiag<true><<<(unsigned)cnt, B.nt, B.smem, s>>>(G, y, regs, B, dd));
   } else {
     VI_CUDA(cudaFuncSetAttribute(k_tridiag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
-    VI_KERNEL(VI_K_TRIDIAG, s, k_tridiag<false><<<(unsigned)cnt, B.nt, B.smem, s>>>(G, y, regs, B));
+    VI_KERNEL(VI_K_TRIDIAG, s, k_tridiag<false><<<(unsigned)cnt, B.nt, B.smem, s>>>(G, y, regs, B, dd));
   }
   return VI_OK;
 }
@@ -879,7 +1038,7 @@ extern "C" int vi_fit_workspace_bytes(int32_t R, int32_t P, int32_t N, int32_t n
   UnitBuf Ub;
   unit_carve(b, Ub, U);
   b.take<double>(VI_NALPHA);
-  *bytes = b.off + per_system_bytes(N, nreg, P) * (cap + 32) + 16384 + cov_scratch_bytes(R, N);
+  *bytes = b.off + per_system_bytes(N, nreg, P) * (cap + 32) + 16384 + cov_scratch_bytes(R, N) + gcv_scratch_bytes(R, P, U);
   return VI_OK;
 }
 
@@ -922,7 +1081,7 @@ extern "C" int vi_solve_batched(const double* G, const double* y, const int32_t*
   return VI_OK;
 }
 
-extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* bm,
+extern "C" int vi_fit_batched(const double* At, const double* A, const double* Wm, const double* bm,
                               const double* G, const double* y, const int32_t* npts,
                               int32_t R, int32_t P, int32_t N,
                               const double* regmats, int32_t nreg, int32_t method,
@@ -930,8 +1089,9 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
                               int64_t* nsolve, void* workspace, int64_t workspace_bytes, void* stream) {
   VI_REQUIRE(At && Wm && bm && G && y && npts && C && chi2 && rank && status && workspace, "NULL argument");
   VI_REQUIRE(R >= 0 && P >= 1 && N >= 1 && N <= 1024 && nreg >= 0, "bad shape");
-  VI_REQUIRE(method == VI_METHOD_NONE || method == VI_METHOD_CHI2, "unknown method %d", method);
-  VI_REQUIRE(method == VI_METHOD_NONE || (nreg >= 1 && regmats && lam), "chi2 method needs regularisation matrices");
+  VI_REQUIRE(method == VI_METHOD_NONE || method == VI_METHOD_CHI2 || method == VI_METHOD_GCV, "unknown method %d", method);
+  VI_REQUIRE(method == VI_METHOD_NONE || (nreg >= 1 && regmats && lam), "chi2 / gcv need regularisation matrices");
+  VI_REQUIRE(method != VI_METHOD_GCV || A != nullptr, "gcv needs the row-major design matrix A");
   if (dC != nullptr && N > VI_NMAX_SMEM) {
     vi_set_error("covariance output needs nbasis <= %d (got %d)", VI_NMAX_SMEM, N);
     return VI_EUNSUPPORTED;
@@ -943,10 +1103,14 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
   const double rcond = VI_EPS;
   const int64_t U = (int64_t)R * (nreg > 0 ? nreg : 1);
 
-  int64_t cap = cap_for_workspace(workspace_bytes, U, N, nreg, P, R);
+  const int64_t gcv_bytes = gcv_scratch_bytes(R, P, U);
+  int64_t cap = cap_for_workspace(workspace_bytes - gcv_bytes, U, N, nreg, P, R);
   if (cap < 32) { vi_set_error("workspace too small (%lld bytes)", (long long)workspace_bytes); return VI_EWORKSPACE; }
-  int64_t most = vi_align_up(method == VI_METHOD_CHI2 ? U * VI_NALPHA : (int64_t)R, 32);
+  int64_t most = vi_align_up(method == VI_METHOD_CHI2 ? U * VI_NALPHA : (method == VI_METHOD_GCV ? U * (int64_t)P : (int64_t)R), 32);
   Bump b{reinterpret_cast<char*>(workspace), 0, workspace_bytes};
+  int32_t* validx = b.take<int32_t>((int64_t)R * P);
+  int32_t* nvalid = b.take<int32_t>(R);
+  int64_t* ucount = b.take<int64_t>(U);
   UnitBuf Ub;
   unit_carve(b, Ub, U);
   double* pow10tab = b.take<double>(VI_NALPHA);
@@ -1003,6 +1167,33 @@ extern "C" int vi_fit_batched(const double* At, const double* Wm, const double* 
       }
       if (round_total == 0) break;
       solved += round_total;
+    }
+  }
+  if (method == VI_METHOD_GCV) {
+    // ---- GCV: Nelder-Mead on alpha in lock step; one objective evaluation = one leave-one-gate-out
+    // system per weighted gate of the record (interpolate.py:332-351) -----------------------------
+    const Downdate dd{A, Wm, bm, P};
+    VI_KERNEL(VI_K_MISC, st, k_valid_index<<<(unsigned)R, 32, 0, st>>>(P, Wm, validx, nvalid));
+    VI_KERNEL(VI_K_MISC, st, k_nm_init<<<blocks(U, 128), 128, 0, st>>>(U, nreg, nvalid, Ub));
+    for (int it = 0; it < 4 * VI_NM_MAXFUN + 8; ++it) {
+      VI_KERNEL(VI_K_MISC, st, k_nm_propose<<<blocks(U, 128), 128, 0, st>>>(U, nreg, nvalid, Ub, ucount));
+      VI_KERNEL(VI_K_MISC, st, k_scan_counts<<<1, 1024, 0, st>>>(U, ucount, Ub.off));
+      int64_t T = 0;
+      int32_t any_active = 0;
+      VI_CUDA(cudaMemcpyAsync(&T, Ub.off + U, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      VI_CUDA(cudaStreamSynchronize(st));
+      (void)any_active;
+      if (T == 0) break;       // every unit has terminated (a unit with zero weighted gates never starts)
+      for (int64_t t0 = 0; t0 < T; t0 += cap) {
+        int64_t cnt = (T - t0 < cap) ? T - t0 : cap;
+        VI_KERNEL(VI_K_MISC, st, k_gcv_setup<<<blocks(cap, 256), 256, 0, st>>>(t0, cnt, U, nreg, P, Ub.off, validx, B, Ub));
+        if (int rc = run_tridiag(cnt, G, y, regmats, B, st, dd)) return rc;
+        if (int rc = run_post(cnt, B, rcond, B.Csys, B.rank, st)) return rc;
+        VI_KERNEL(VI_K_CHI2, st, k_gcv_resid<<<blocks(cnt, 8), 256, 0, st>>>(cnt, N, dd, B, B.Csys, B.chi2));
+        VI_KERNEL(VI_K_MISC, st, k_gcv_accumulate<<<blocks(U, 128), 128, 0, st>>>(U, t0, cnt, Ub.off, B.chi2, Ub));
+      }
+      solved += T;
+      VI_KERNEL(VI_K_MISC, st, k_nm_feed<<<blocks(U, 128), 128, 0, st>>>(U, Ub));
     }
   }
   // ---- phase 3: final solve with the found parameters (interpolate.py:566-569) -----------
@@ -1091,7 +1282,7 @@ extern "C" int vi_fit_host(const double* A, const double* value, const double* e
     rc = vi_normal_eq_batched(dA, dval, derr, dwt, R, P, N, ne_mode, dG, dy, nullptr, dnp, dWm, dbm, s);
   }
   if (rc == VI_OK)
-    rc = vi_fit_batched(dAt, dWm, dbm, dG, dy, dnp, R, P, N, dreg, nreg, method, dC_, ddC, dchi, dlam, drank, dst,
+    rc = vi_fit_batched(dAt, dA, dWm, dbm, dG, dy, dnp, R, P, N, dreg, nreg, method, dC_, ddC, dchi, dlam, drank, dst,
                         nullptr, ws, ws_bytes, s);
   VI_TRY(cudaMemcpyAsync(C, dC_, (size_t)R * N * 8, cudaMemcpyDeviceToHost, s));
   if (dC) VI_TRY(cudaMemcpyAsync(dC, ddC, (size_t)R * NN * 8, cudaMemcpyDeviceToHost, s));

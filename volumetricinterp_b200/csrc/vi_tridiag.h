@@ -112,8 +112,11 @@ VI_HD void vi_tri_carve(vi_tri_ws& S, double* aux, int n, int nt) {
 
 // X <- scl * (0.5 (G + G^T) + sum_r lam[r] Reg_r),  scl = 2^-exponent(max|X|);  yv <- y;  col <- X[:,0];
 // (v, w) <- 0.  Returns (in ws.sc[1]) 1.0 if a non-finite entry was met.
+// Optional rank-one downdate (leave-one-gate-out systems of the GCV objective, interpolate.py:332-349):
+// with arow != NULL the system is built from G - wj a a^T and y - wj bj a, a = arow (one row of A).
 VI_HD void vi_tri_load(const vi_tri_ws& S, int n, const double* G, const double* y, const double* regs,
-                       const double* lam, int nreg, int tid, int nt) {
+                       const double* lam, int nreg, int tid, int nt,
+                       const double* arow = nullptr, double wj = 0.0, double bj = 0.0) {
   (void)tid;
   const int ld = S.ld;
   VI_PHASE(
@@ -125,12 +128,14 @@ VI_HD void vi_tri_load(const vi_tri_ws& S, int n, const double* G, const double*
         double l = lam[r];
         if (l != 0.0) x = fma(l, regs[((int64_t)r * n + i) * n + c], x);
       }
+      if (arow) x = x - wj * (arow[i] * arow[c]);
       if (!(fabs(x) <= 1.79769313486231570e308)) bad = 1.0;
       mx = fmax(mx, fabs(x));
       S.X[i * ld + c] = x;
     }
     for (int i = tid; i < n; i += nt) {
       double t = y[i];
+      if (arow) t = t - (wj * bj) * arow[i];
       if (!(fabs(t) <= 1.79769313486231570e308)) bad = 1.0;
       S.yv[i] = t;
       for (int c = n; c < ld; ++c) S.X[i * ld + c] = 0.0;      // padding columns

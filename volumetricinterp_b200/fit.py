@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _native
 
-METHODS = {None: _native.METHOD_CHI2, 'chi2': _native.METHOD_CHI2}
+METHODS = {None: _native.METHOD_CHI2, 'chi2': _native.METHOD_CHI2, 'gcv': _native.METHOD_GCV}
 
 
 @dataclass
@@ -72,7 +72,7 @@ def _workspace(dev, R, P, N, nreg, systems):
     return ws
 
 
-def fit_batch_device(At, Wm, bm, G, y, npts, regs, method, systems=0, want_cov=False):
+def fit_batch_device(At, Wm, bm, G, y, npts, regs, method, systems=0, want_cov=False, A=None):
     """vi_fit_batched on device tensors.  regs: (nreg,N,N) tensor or None."""
     import torch
     R, N = y.shape
@@ -89,7 +89,8 @@ def fit_batch_device(At, Wm, bm, G, y, npts, regs, method, systems=0, want_cov=F
     ws = _workspace(dev, R, P, N, nreg, systems)
     nsolve = C.c_int64(0)
     _native.check(_native.lib().vi_fit_batched(
-        At.data_ptr(), Wm.data_ptr(), bm.data_ptr(), G.data_ptr(), y.data_ptr(), npts.data_ptr(),
+        At.data_ptr(), A.data_ptr() if A is not None else None, Wm.data_ptr(), bm.data_ptr(), G.data_ptr(),
+        y.data_ptr(), npts.data_ptr(),
         R, P, N, regs.data_ptr() if nreg else None, nreg, meth,
         Cf.data_ptr(), dC.data_ptr() if want_cov else None, chi2.data_ptr(), lam.data_ptr(),
         rank.data_ptr(), status.data_ptr(), C.byref(nsolve), ws.data_ptr(), ws.numel(), _cuda_stream(dev)))
@@ -106,7 +107,7 @@ def fit_records(model, lat, lon, alt, value, error, reg_matrices=None, method='c
     weight: optional (R,P) precomputed error**-2 (bit-exact parity with numpy's pow)."""
     import torch
     if method not in METHODS:
-        raise ValueError(f"REGULARIZATION_METHOD {method!r} is not available on the device path (chi2 only)")
+        raise ValueError(f"REGULARIZATION_METHOD {method!r} is not available on the device path (chi2, gcv)")
     dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
     f64 = lambda a: a.to(dev, torch.float64) if isinstance(a, torch.Tensor) else \
         torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev, non_blocking=True)
@@ -127,7 +128,7 @@ def fit_records(model, lat, lon, alt, value, error, reg_matrices=None, method='c
         w = f64(weight[r0:r1]) if weight is not None else None
         G, y, _, npts, Wm, bm = normal_equations_device(A, v, e, w, ne_mode)
         Cf, dC, chi2, lam, rank, status, ns = fit_batch_device(At, Wm, bm, G, y, npts, regs, METHODS[method],
-                                                                systems, want_cov)
+                                                                systems, want_cov, A=A)
         nsolve += ns
         outs.append((Cf, dC, chi2, lam, rank, status))
     cat = lambda i: (outs[0][i] if len(outs) == 1 else torch.cat([o[i] for o in outs])) \

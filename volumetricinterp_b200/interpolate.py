@@ -67,10 +67,12 @@ class Interpolate(object):
             t1 = (endtime - dt.datetime.utcfromtimestamp(0)).total_seconds()
             idx = np.argwhere((utime[:, 0] >= t0) & (utime[:, 1] <= t1)).flatten()
             utime, value, error = utime[idx, :], value[idx], error[idx]
-        if self.reg_method not in ('chi2',) and self.regularization_list:
-            raise ValueError('REGULARIZATION_METHOD {} is not available (chi2 only)'.format(self.reg_method))
+        if self.reg_method not in ('chi2', 'gcv') and self.regularization_list:
+            # 'manual' and 'prompt' are broken in the reference itself (7-argument signatures called with 5,
+            # interpolate.py:141 vs :353,:383)
+            raise ValueError('REGULARIZATION_METHOD {} is not available (chi2, gcv)'.format(self.reg_method))
         res = _fit.fit_records(self.model, lat, lon, alt, value, error,
-                               [reg_matricies[r] for r in self.regularization_list], 'chi2',
+                               [reg_matricies[r] for r in self.regularization_list], self.reg_method,
                                ne_mode=self.ne_mode, want_cov=self.calc_covariance)
         self.time = utime
         self.Coeffs = res.Coeffs
@@ -118,14 +120,15 @@ class Interpolate(object):
     def find_reg_param(self, A, b, W, reg_matrices, method=None):
         """interpolate.py:97-147 for one record: {name: lambda or NaN}."""
         import torch
-        if method not in (None, 'chi2'):
-            raise ValueError('only the chi2 method is available')
+        if method not in (None, 'chi2', 'gcv'):
+            raise ValueError('only the chi2 and gcv methods are available')
+        meth = _native.METHOD_GCV if method == 'gcv' else _native.METHOD_CHI2
         Ad, At, bd, Wd = self._one_record(A, b, W)
         G, y, _, npts, Wm, bm = _fit.normal_equations_device(Ad, bd, None, Wd, self.ne_mode)
         out = {}
         for name in self.regularization_list:
             regs = torch.from_numpy(np.asarray(reg_matrices[name], dtype=np.float64)[None]).to(Ad.device)
-            _, _, _, lam, _, status, _ = _fit.fit_batch_device(At, Wm, bm, G, y, npts, regs, _native.METHOD_CHI2)
+            _, _, _, lam, _, status, _ = _fit.fit_batch_device(At, Wm, bm, G, y, npts, regs, meth, A=Ad)
             out[name] = float(lam[0, 0].item())
         return out
 
