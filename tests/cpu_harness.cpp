@@ -81,6 +81,28 @@ int h_tql_values_solve(int n, const double* d0, const double* e0, const double* 
   return st;
 }
 
+// nested-loop QL (vi_tql_values) vs flattened state machine (vi_tql_values_flat): eigenvalues and tape
+// must be bit-identical.  Returns 0 if identical, a positive code otherwise.
+int h_tql_flat_identical(int n, const double* d0, const double* e0, int* nrot_out) {
+  std::vector<double> d1(d0, d0 + n), e1(n, 0.0), d2(d0, d0 + n), e2(n, 0.0);
+  for (int i = 0; i + 1 < n; ++i) { e1[i] = e0[i]; e2[i] = e0[i]; }
+  int cap = n * n + 64;
+  std::vector<double> t1(2 * (size_t)cap, 0.0), t2(2 * (size_t)cap, 0.0);
+  std::vector<int32_t> i1(cap, 0), i2(cap, 0);
+  vi_tape ta{{t1.data(), 2}, {t1.data() + 1, 2}, {i1.data(), 1}, cap};
+  vi_tape tb{{t2.data(), 2}, {t2.data() + 1, 2}, {i2.data(), 1}, cap};
+  int32_t n1 = 0, n2 = 0;
+  int s1 = vi_tql_values(n, {d1.data(), 1}, {e1.data(), 1}, ta, &n1);
+  int s2 = vi_tql_values_flat(n, {d2.data(), 1}, {e2.data(), 1}, tb, &n2, true);
+  *nrot_out = n2;
+  if (s1 != s2) return 1;
+  if (n1 != n2) return 2;
+  if (std::memcmp(d1.data(), d2.data(), n * sizeof(double)) != 0) return 3;
+  if (std::memcmp(t1.data(), t2.data(), 2 * (size_t)n1 * sizeof(double)) != 0) return 4;
+  if (std::memcmp(i1.data(), i2.data(), (size_t)n1 * sizeof(int32_t)) != 0) return 5;
+  return 0;
+}
+
 typedef double (*h_fn)(double);
 // brentq driven through the state machine; xs receives every abscissa evaluated.
 int h_brentq(h_fn f, double xa, double xb, double* root, double* xs, int* nfev) {

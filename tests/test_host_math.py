@@ -232,3 +232,33 @@ def test_nelder_mead_state_machine_replays_scipy(harness):
         assert list(xs[:nfev.value]) == xs_ref, (x0, xs[:5], xs_ref[:5])
         assert xmin.value == ref.x[0] and nfev.value == ref.nfev and bool(ok) == bool(ref.success)
         assert nit.value == ref.nit
+
+
+def test_flattened_ql_is_bit_identical_to_nested(harness):
+    """vi_tql_values_flat (the per-lane state machine the GPU runs) == vi_tql_values, bit for bit, on random
+    graded tridiagonals, on matrices with exact zeros (splits), and on the real N = 144 systems."""
+    from scipy.linalg import lapack
+    rng = np.random.default_rng(11)
+    mats = []
+    for n in (1, 2, 3, 5, 17, 64, 144):
+        for _ in range(6):
+            d = rng.standard_normal(n) * 10.0 ** rng.uniform(-12, 0, n)
+            e = rng.standard_normal(max(n - 1, 0)) * 10.0 ** rng.uniform(-12, 0, max(n - 1, 0))
+            if n > 4:
+                e[rng.integers(0, n - 1, 2)] = 0.0          # exact splits
+            if n > 8:
+                d[n // 2:] *= 1e-18                           # graded: many negligible eigenvalues
+                e[n // 2:] *= 1e-18
+            mats.append((d, e))
+    g = load_golden("c1_144")
+    ok = np.isfinite(g["value"][0])
+    G, y = rp.normal_equations(g["A"][ok], g["error"][0][ok] ** -2, g["value"][0][ok])
+    for alpha in (0.0, -10.0, -22.4, -30.0, -60.0):
+        X = 0.5 * (G + G.T) + 10.0 ** alpha * g["regs"][0]
+        c, d, e, tau, info = lapack.dsytrd(X / np.abs(X).max(), lower=1)
+        mats.append((np.ascontiguousarray(d), np.ascontiguousarray(e)))
+    for d, e in mats:
+        n = d.size
+        nrot = C.c_int(0)
+        rc = harness.h_tql_flat_identical(n, dptr(np.ascontiguousarray(d)), dptr(np.append(e, 0.0)), C.byref(nrot))
+        assert rc == 0, (n, rc)

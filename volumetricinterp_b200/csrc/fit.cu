@@ -294,16 +294,18 @@ __global__ void k_tql_smem(int64_t nsys, SysBuf B) {
   extern __shared__ __align__(16) double sm[];
   const int T = blockDim.x, tid = threadIdx.x, n = B.n;
   const int64_t s = (int64_t)blockIdx.x * T + tid;
-  if (s >= nsys) return;
-  if (B.st[s] != VI_ST_OK) return;
+  const bool act = (s < nsys) && (B.st[s] == VI_ST_OK);     // idle lanes still take part in the warp votes
+  const int64_t sc = act ? s : 0;
   vi_svec d{sm + tid, T}, e{sm + (size_t)n * T + tid, T};
-  const int64_t base = ileave(s, n);
-  for (int i = 0; i < n; ++i) {
-    d[i] = B.d[base + (int64_t)i * 32];
-    e[i] = B.e[base + (int64_t)i * 32];
-  }
+  const int64_t base = ileave(sc, n);
+  if (act)
+    for (int i = 0; i < n; ++i) {
+      d[i] = B.d[base + (int64_t)i * 32];
+      e[i] = B.e[base + (int64_t)i * 32];
+    }
   int32_t nrot = 0;
-  const int q = vi_tql_values(n, d, e, tape_of(B, s), &nrot);
+  const int q = vi_tql_values_flat(n, d, e, tape_of(B, sc), &nrot, act);
+  if (!act) return;
   if (q != 0) { B.st[s] = VI_ST_NOCONV; return; }
   B.nrot[s] = nrot;
   for (int i = 0; i < n; ++i) B.d[base + (int64_t)i * 32] = d[i];
