@@ -353,6 +353,15 @@ VI_HD int vi_tql_values_flat(int n, vi_svec d, vi_svec e, vi_tape tape, int32_t*
   bool valid = false, cand_valid = false;
   double s = 1.0, c = 1.0, p = 0.0, gg = 0.0, dnext = 0.0;
   for (;;) {
+    // The sweep set-up (shift: two divisions and a square root) is batched: lanes that reach it idle until
+    // eight of them are waiting or no lane is rotating, so its ~120 instructions are not paid on every trip.
+#if defined(__CUDA_ARCH__)
+    const unsigned m_iter = __ballot_sync(0xffffffffu, phase == VI_QL_ITER);
+    const unsigned m_rot = __ballot_sync(0xffffffffu, phase == VI_QL_ROT);
+    const bool do_iter = (__popc(m_iter) >= 8) || (m_rot == 0u);
+#else
+    const bool do_iter = true;
+#endif
     if (phase == VI_QL_ROT) {
       double* dp = D + (int64_t)i * sd;
       double* ep = E + (int64_t)i * se;
@@ -407,28 +416,27 @@ VI_HD int vi_tql_values_flat(int n, vi_svec d, vi_svec e, vi_tape tape, int32_t*
           phase = VI_QL_ITER;
         }
       }
-    } else if (phase == VI_QL_ITER) {
-      if (!valid) {
-        mm = l;
-        while (mm < nb - 1 && !vi_ql_negl(E[(int64_t)mm * se], D[(int64_t)mm * sd], D[(int64_t)(mm + 1) * sd])) ++mm;
-        valid = true;
-        cand_valid = false;
-      }
-      if (mm < nb - 1) E[(int64_t)mm * se] = 0.0;
-      if (mm == l) {
-        ++l;
-        if (l >= nb) {
-          phase = VI_QL_UNBLOCK;
-        } else if (cand_valid && cand >= l) {
-          mm = cand;              // known from the last sweep; anything beyond it is not
+    } else if (phase == VI_QL_ITER && do_iter) {
+      for (;;) {
+        if (!valid) {
+          mm = l;
+          while (mm < nb - 1 && !vi_ql_negl(E[(int64_t)mm * se], D[(int64_t)mm * sd], D[(int64_t)(mm + 1) * sd])) ++mm;
+          valid = true;
           cand_valid = false;
-        } else {
-          valid = false;
         }
-      } else if (budget-- <= 0) {
-        status = 1;
-        phase = VI_QL_UNBLOCK;
-      } else {
+        if (mm < nb - 1) E[(int64_t)mm * se] = 0.0;
+        if (mm == l) {
+          ++l;
+          if (l >= nb) { phase = VI_QL_UNBLOCK; break; }
+          if (cand_valid && cand >= l) {
+            mm = cand;              // known from the last sweep; anything beyond it is not
+            cand_valid = false;
+          } else {
+            valid = false;
+          }
+          continue;
+        }
+        if (budget-- <= 0) { status = 1; phase = VI_QL_UNBLOCK; break; }
         const double el = E[(int64_t)l * se];
         const double dl = D[(int64_t)l * sd];
         double g0 = (D[(int64_t)(l + 1) * sd] - dl) / (2.0 * el);
@@ -439,6 +447,7 @@ VI_HD int vi_tql_values_flat(int n, vi_svec d, vi_svec e, vi_tape tape, int32_t*
         dnext = D[(int64_t)(i + 1) * sd];
         mt1 = -1;
         phase = VI_QL_ROT;
+        break;
       }
     } else if (phase == VI_QL_BLOCK) {
       if (l1 >= n) {
