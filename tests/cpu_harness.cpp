@@ -175,48 +175,5 @@ int h_system_solve(int n, const double* G, const double* y, const double* regs, 
   return 0;
 }
 
-}  // extern "C"
-
-// Same pipeline through the register-resident tridiagonalisation (the variant the GPU runs for n <= 8*RPT).
-template <int RPT>
-static int system_solve_reg(int n, const double* G, const double* y, const double* regs, const double* lam, int nreg,
-                            double rcond, double* C, int* rank, double* dd, double* ee, int* bad) {
-  const int npair = vi_tri_npair(n);
-  const int nt = (VI_TRI_NG * npair + 31) / 32 * 32 > ((n + 31) & ~31) ? (VI_TRI_NG * npair + 31) / 32 * 32 : ((n + 31) & ~31);
-  std::vector<double> aux(vi_tri_aux_doubles(n, nt) + 16), V((size_t)n * n, 0.0), xreg((size_t)nt * 2 * RPT, 0.0);
-  vi_tri_ws S;
-  S.X = nullptr; S.ld = 0;
-  vi_tri_carve(S, aux.data(), n, nt);
-  vi_tri_load_reg<RPT>(S, n, G, y, regs, lam, nreg, xreg.data(), 0, nt);
-  *bad = S.sc[1] != 0.0;
-  if (*bad) return 0;
-  vi_tri_reduce_reg<RPT>(S, n, V.data(), xreg.data(), 0, nt);
-  for (int i = 0; i < n; ++i) { dd[i] = S.d[i]; ee[i] = S.e[i]; }
-  std::vector<double> d(S.d, S.d + n), e(S.e, S.e + n), g(S.yv, S.yv + n), tau(S.tau, S.tau + n);
-  int cap = n * n + 64;
-  std::vector<double> tcs(2 * (size_t)cap);
-  std::vector<int32_t> ti(cap);
-  vi_tape tape{{tcs.data(), 2}, {tcs.data() + 1, 2}, {ti.data(), 1}, cap};
-  int32_t nr = 0;
-  int st = vi_tql_values_flat(n, {d.data(), 1}, {e.data(), 1}, tape, &nr, true);
-  if (st != 0) return st;
-  vi_tape_apply_zt({g.data(), 1}, tape, nr);
-  *rank = vi_spectral_divide(n, {d.data(), 1}, {g.data(), 1}, rcond);
-  vi_tape_apply_z({g.data(), 1}, tape, nr);
-  for (int i = 0; i < n; ++i) g[i] *= S.sc[0];
-  vi_tri_backtransform(n, V.data(), tau.data(), 1, g.data(), 1);
-  std::memcpy(C, g.data(), n * sizeof(double));
-  return 0;
-}
-
-extern "C" {
-
-int h_system_solve_reg(int n, const double* G, const double* y, const double* regs, const double* lam, int nreg,
-                       double rcond, double* C, int* rank, double* dd, double* ee, int* bad) {
-  if (n <= 8 * 4) return system_solve_reg<4>(n, G, y, regs, lam, nreg, rcond, C, rank, dd, ee, bad);
-  if (n <= 8 * 18) return system_solve_reg<18>(n, G, y, regs, lam, nreg, rcond, C, rank, dd, ee, bad);
-  return system_solve_reg<20>(n, G, y, regs, lam, nreg, rcond, C, rank, dd, ee, bad);
-}
-
 int h_sizeof_shl_params() { return (int)sizeof(vi_shl_params); }
 }

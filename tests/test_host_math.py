@@ -47,17 +47,7 @@ def test_radbasfun_rows_match_reference_basis(harness):
 
 
 def _system(harness, G, y, regs, lam, nt):
-    """nt > 0: shared-memory tridiagonalisation emulated with nt threads; nt == 0: register-resident variant."""
     n = G.shape[0]
-    if nt == 0:
-        Cq = np.zeros(n)
-        rank, bad = C.c_int(0), C.c_int(0)
-        dd, ee = np.zeros(n), np.zeros(n)
-        regs = np.ascontiguousarray(regs)
-        lam = np.ascontiguousarray(lam, dtype=float)
-        st = harness.h_system_solve_reg(n, dptr(G), dptr(y), dptr(regs), dptr(lam), len(lam), C.c_double(EPS),
-                                        dptr(Cq), C.byref(rank), dptr(dd), dptr(ee), C.byref(bad))
-        return st, bad.value, rank.value, Cq, dd, ee
     Cq = np.zeros(n)
     rank, bad = C.c_int(0), C.c_int(0)
     dd, ee = np.zeros(n), np.zeros(n)
@@ -68,8 +58,7 @@ def _system(harness, G, y, regs, lam, nt):
     return st, bad.value, rank.value, Cq, dd, ee
 
 
-@pytest.mark.parametrize("name,nt", [("lo8", 8), ("lo8", 32), ("lo12", 48), ("lo12_two", 12), ("lo8", 0), ("lo12", 0),
-                                     ("lo12_two", 0)])
+@pytest.mark.parametrize("name,nt", [("lo8", 8), ("lo8", 32), ("lo12", 48), ("lo12_two", 12)])
 def test_system_pipeline_matches_lstsq_low_order(harness, name, nt):
     """tridiagonalise (CTA phases run thread by thread) + tape QL + truncated solve + back-transform
     == scipy.linalg.lstsq (interpolate.py:462) on full-rank systems."""
@@ -105,21 +94,18 @@ def test_system_pipeline_rank_deficient(harness):
         X = G + 10.0 ** alpha * g["regs"][0]
         ref = scipy.linalg.lstsq(X, y)[0]
         s = np.linalg.svd(X, compute_uv=False)
-        for nt in (576, 0):
-            st, bad, rank, Cq, _, _ = _system(harness, np.ascontiguousarray(G), np.ascontiguousarray(y),
-                                              np.stack(g["regs"]), [10.0 ** alpha], nt)
-            assert st == 0 and bad == 0
-            assert abs(rank - int((s > EPS * s[0]).sum())) <= 1
-            dens, dref = A @ Cq, A @ ref
-            assert np.max(np.abs(dens - dref)) <= 1e-5 * np.abs(dref).max()
+        st, bad, rank, Cq, _, _ = _system(harness, np.ascontiguousarray(G), np.ascontiguousarray(y),
+                                          np.stack(g["regs"]), [10.0 ** alpha], 576)
+        assert st == 0 and bad == 0
+        assert abs(rank - int((s > EPS * s[0]).sum())) <= 1
+        dens, dref = A @ Cq, A @ ref
+        assert np.max(np.abs(dens - dref)) <= 1e-5 * np.abs(dref).max()
 
 
 def test_nonfinite_system_is_flagged(harness):
     G = np.eye(4)
     G[1, 2] = np.inf
     st, bad, *_ = _system(harness, G, np.ones(4), np.zeros((1, 4, 4)), [0.0], 4)
-    assert bad == 1
-    st, bad, *_ = _system(harness, G, np.ones(4), np.zeros((1, 4, 4)), [0.0], 0)
     assert bad == 1
 
 

@@ -201,44 +201,6 @@ k_tridiag(const double* __restrict__ G, const double* __restrict__ y, const doub
   if (tid == 0) { B.scl[s] = S.sc[0]; B.st[s] = bad ? VI_ST_NONFINITE : VI_ST_OK; }
 }
 
-// Register-resident variant (vi_tri_reduce_reg): the matrix lives in the registers of the CTA's threads,
-// shared memory only holds the vectors.  Used for n <= 144.
-template <int RPT>
-__global__ void __launch_bounds__(32 * RPT)
-k_tridiag_reg(const double* __restrict__ G, const double* __restrict__ y, const double* __restrict__ regs, SysBuf B,
-              Downdate dd) {
-  extern __shared__ __align__(16) double sm[];
-  const int64_t s = blockIdx.x;
-  const int r = B.rec[s];
-  if (r < 0) { if (threadIdx.x == 0) B.st[s] = kSkip; return; }
-  const int n = B.n, nt = blockDim.x, tid = threadIdx.x;
-  vi_tri_ws S;
-  S.X = nullptr; S.ld = 0;
-  vi_tri_carve(S, sm, n, nt);
-  double xreg[2 * RPT];
-  const double* arow = nullptr;
-  double wj = 0.0, bj = 0.0;
-  if (dd.A != nullptr) {
-    const int j = B.gate[s];
-    arow = dd.A + (int64_t)j * n;
-    wj = dd.Wm[(int64_t)r * dd.P + j];
-    bj = dd.bm[(int64_t)r * dd.P + j];
-  }
-  vi_tri_load_reg<RPT>(S, n, G + (int64_t)r * n * n, y + (int64_t)r * n, regs, B.lam + s * (B.nreg > 0 ? B.nreg : 1),
-                       B.nreg, xreg, tid, nt, arow, wj, bj);
-  const bool bad = S.sc[1] != 0.0;
-  if (!bad) vi_tri_reduce_reg<RPT>(S, n, B.V + s * (int64_t)n * n, xreg, tid, nt);
-  const int64_t base = ileave(s, n);
-  if (!bad)
-    for (int i = tid; i < n; i += nt) {
-      B.d[base + (int64_t)i * 32] = S.d[i];
-      B.e[base + (int64_t)i * 32] = S.e[i];
-      B.g[base + (int64_t)i * 32] = S.yv[i];
-      B.tau[base + (int64_t)i * 32] = S.tau[i];
-    }
-  if (tid == 0) { B.scl[s] = S.sc[0]; B.st[s] = bad ? VI_ST_NONFINITE : VI_ST_OK; }
-}
-
 __device__ __forceinline__ vi_tape tape_of(const SysBuf& B, int64_t s) {
   double* cs = B.tcs + s * (int64_t)B.tapecap * 2;
   return vi_tape{{cs, 2}, {cs + 1, 2}, {B.tix + s * (int64_t)B.tapecap, 1}, B.tapecap};
@@ -1002,24 +964,6 @@ inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / p
 int run_tridiag(int64_t cnt, const double* G, const double* y, const double* regs, const SysBuf& B, cudaStream_t s,
                 Downdate dd = Downdate{nullptr, nullptr, nullptr, 0}) {
   if (cnt <= 0) return VI_OK;
-  if (!B.use_gx && B.n <= 144) {
-    // register-resident variant
-    const int npair = vi_tri_npair(B.n);
-    int nt = (VI_TRI_NG * npair + 31) / 32 * 32;
-    if (nt < ((B.n + 31) & ~31)) nt = (B.n + 31) & ~31;
-    const size_t smem = (size_t)vi_tri_aux_doubles(B.n, nt) * sizeof(double);
-    if (B.n <= 32) {
-      VI_CUDA(cudaFuncSetAttribute(k_tridiag_reg<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      VI_KERNEL(VI_K_TRIDIAG, s, k_tridiag_reg<4><<<(unsigned)cnt, nt, smem, s>>>(G, y, regs, B, dd));
-    } else if (B.n <= 64) {
-      VI_CUDA(cudaFuncSetAttribute(k_tridiag_reg<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      VI_KERNEL(VI_K_TRIDIAG, s, k_tridiag_reg<8><<<(unsigned)cnt, nt, smem, s>>>(G, y, regs, B, dd));
-    } else {
-      VI_CUDA(cudaFuncSetAttribute(k_tridiag_reg<18>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      VI_KERNEL(VI_K_TRIDIAG, s, k_tridiag_reg<18><<<(unsigned)cnt, nt, smem, s>>>(G, y, regs, B, dd));
-    }
-    return VI_OK;
-  }
   if (B.use_gx) {
     VI_CUDA(cudaFuncSetAttribute(k_tridiag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
     VI_KERNEL(VI_K_TRIDIAG, s, k_tridiag<true><<<(unsigned)cnt, B.nt, B.smem, s>>>(G, y, regs, B, dd));

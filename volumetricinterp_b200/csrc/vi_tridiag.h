@@ -27,12 +27,8 @@
 
 #if defined(__CUDA_ARCH__)
 #define VI_UNROLL4 _Pragma("unroll 4")
-#define VI_UNROLL_FULL _Pragma("unroll")
-#define VI_WARP_FENCE __syncwarp();
 #else
 #define VI_UNROLL4
-#define VI_UNROLL_FULL
-#define VI_WARP_FENCE
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -85,7 +81,6 @@ struct vi_tri_ws {
   double* col;    // n  the pivot column, already carrying the deferred update
   double* red1;   // max(n, nt)
   double* red2;   // n
-  double* red3;   // n
   double* psum;   // ng x npad partial mat-vec sums, npad = 2 * ceil(n/2)
   double* d;      // n   diagonal of T
   double* e;      // n   sub-diagonal of T (e[n-1] unused)
@@ -98,7 +93,7 @@ VI_HD int vi_tri_npair(int n) { return (n + 1) / 2; }
 VI_HD int vi_tri_groups(int n, int nt) { int ng = nt / vi_tri_npair(n); return ng < 1 ? 1 : ng; }
 // doubles of CTA-shared storage needed besides X
 VI_HD int vi_tri_aux_doubles(int n, int nt) {
-  return 4 * (n + 2) + (n + 2) + 7 * n + (nt > n ? nt : n) + vi_tri_groups(n, nt) * 2 * vi_tri_npair(n) + 8;
+  return 4 * (n + 2) + (n + 2) + 6 * n + (nt > n ? nt : n) + vi_tri_groups(n, nt) * 2 * vi_tri_npair(n) + 8;
 }
 // carve the auxiliary arrays out of one block of vi_tri_aux_doubles(n, nt) doubles (16-byte aligned)
 VI_HD void vi_tri_carve(vi_tri_ws& S, double* aux, int n, int nt) {
@@ -107,7 +102,6 @@ VI_HD void vi_tri_carve(vi_tri_ws& S, double* aux, int n, int nt) {
   S.yv = aux; aux += n;
   S.col = aux; aux += n;
   S.red2 = aux; aux += n;
-  S.red3 = aux; aux += n;
   S.d = aux; aux += n;
   S.e = aux; aux += n;
   S.tau = aux; aux += n;
@@ -282,198 +276,6 @@ VI_HD void vi_tri_reduce(const vi_tri_ws& S, int n, double* V, int tid, int nt) 
   VI_PHASE(
     if (tid == 0) {
       if (n == 1) S.d[0] = S.X[0];
-      else S.d[n - 1] = S.col[n - 1];
-      S.e[n - 1] = 0.0; S.tau[n - 1] = 0.0;
-    }
-  )
-}
-
-// =================================================================================================
-// Register-resident variant (the one the GPU runs for n <= 8 * RPT): thread (g, cp), g = tid / npair in
-// 0..7, cp = tid % npair, OWNS the elements X[g + 8 kk][2 cp .. 2 cp + 1], kk = 0..RPT-1, for the whole
-// reduction and keeps them in registers; shared memory only carries the vectors (v, w, vnext), the pivot
-// column and the partial sums.  Same phases and the same arithmetic per element as the fused form above
-// (the partial mat-vec sums group rows differently, so results differ in the last bits only).
-// On the host the "registers" of all emulated threads live in one array, thread tid at offset
-// tid * 2 * RPT; on the device xreg is the thread's own local array.
-// =================================================================================================
-#if defined(__CUDA_ARCH__)
-#define VI_TREG(tid, RPT) 0
-#else
-#define VI_TREG(tid, RPT) ((tid) * 2 * (RPT))
-#endif
-#define VI_TRI_NG 8
-
-template <int RPT>
-VI_HD void vi_tri_load_reg(const vi_tri_ws& S, int n, const double* G, const double* y, const double* regs,
-                           const double* lam, int nreg, double* xreg, int tid, int nt,
-                           const double* arow = nullptr, double wj = 0.0, double bj = 0.0) {
-  (void)tid;
-  const int npair = vi_tri_npair(n);
-  VI_PHASE(
-    double* xr = xreg + VI_TREG(tid, RPT);
-    const int g = tid / npair; const int cp = tid - g * npair; const int c0 = 2 * cp;
-    double mx = 0.0; double bad = 0.0;
-    if (g < VI_TRI_NG) {
-      VI_UNROLL_FULL
-      for (int kk = 0; kk < RPT; ++kk) {
-        const int i = g + VI_TRI_NG * kk;
-        VI_UNROLL_FULL
-        for (int q = 0; q < 2; ++q) {
-          const int c = c0 + q;
-          double x = 0.0;
-          if (i < n && c < n) {
-            x = 0.5 * (G[(int64_t)i * n + c] + G[(int64_t)c * n + i]);
-            for (int r = 0; r < nreg; ++r) {
-              double l = lam[r];
-              if (l != 0.0) x = fma(l, regs[((int64_t)r * n + i) * n + c], x);
-            }
-            if (arow) x = x - wj * (arow[i] * arow[c]);
-            if (!(fabs(x) <= 1.79769313486231570e308)) bad = 1.0;
-            mx = fmax(mx, fabs(x));
-          }
-          xr[2 * kk + q] = x;
-        }
-      }
-    }
-    for (int i = tid; i < n; i += nt) {
-      double t = y[i];
-      if (arow) t = t - (wj * bj) * arow[i];
-      if (!(fabs(t) <= 1.79769313486231570e308)) bad = 1.0;
-      S.yv[i] = t;
-    }
-    for (int i = tid; i < 4 * (n + 2); i += nt) S.vw[i] = 0.0;
-    for (int i = tid; i < n + 2; i += nt) S.p[i] = 0.0;
-    S.red1[tid] = (bad != 0.0) ? -1.0 : mx;
-  )
-  VI_PHASE(
-    if (tid == 0) {
-      double mx = 0.0; double bad = 0.0;
-      for (int t = 0; t < nt; ++t) { double r = S.red1[t]; if (r < 0.0) bad = 1.0; else mx = fmax(mx, r); }
-      int ex = 0;
-      double scl = 1.0;
-      if (bad == 0.0 && mx > 0.0) { frexp(mx, &ex); scl = ldexp(1.0, -ex); }
-      S.sc[0] = scl; S.sc[1] = bad;
-    }
-  )
-  VI_PHASE(
-    double* xr = xreg + VI_TREG(tid, RPT);
-    const int g = tid / npair; const int cp = tid - g * npair;
-    const double scl = S.sc[0];
-    if (g < VI_TRI_NG) {
-      VI_UNROLL_FULL
-      for (int kk = 0; kk < RPT; ++kk) {
-        xr[2 * kk] *= scl; xr[2 * kk + 1] *= scl;
-        if (cp == 0 && g + VI_TRI_NG * kk < n) S.col[g + VI_TRI_NG * kk] = xr[2 * kk];      // pivot column 0
-      }
-    }
-  )
-}
-
-template <int RPT>
-VI_HD void vi_tri_reduce_reg(const vi_tri_ws& S, int n, double* V, double* xreg, int tid, int nt) {
-  (void)tid;
-  const int npair = vi_tri_npair(n), npad = 2 * npair;
-  for (int k = 0; k + 1 < n; ++k) {
-    const int lo1 = k + 1;
-    // ---- A: reflector k from the pivot column (as in vi_tri_reduce) ------------------------------
-    VI_PHASE(
-      double tau = 0.0; double beta = 0.0; double scale = 0.0;
-      const bool last = (k == n - 2);
-      if (!last) {
-        const double xn2 = vi_warp_sum(k + 2, n, tid & 31, [&](int i) { double x = S.col[i]; return x * x; });
-        const double alpha = S.col[k + 1];
-        beta = alpha;
-        if (xn2 != 0.0) {
-          const double r2 = alpha * alpha + xn2;
-#if defined(__CUDA_ARCH__)
-          const double ri = rsqrt(r2);
-#else
-          const double ri = 1.0 / sqrt(r2);
-#endif
-          const double nrm = r2 * ri;
-          beta = -copysign(nrm, alpha);
-          tau = 1.0 + fabs(alpha) * ri;
-          scale = copysign(1.0, alpha) / (fabs(alpha) + nrm);
-        }
-      } else {
-        beta = S.col[n - 1];
-      }
-      if (tid >= lo1 && tid < n) {
-        double vv = 0.0;
-        if (tau != 0.0) vv = (tid == lo1) ? 1.0 : S.col[tid] * scale;
-        S.vw[4 * tid + 2] = vv;
-        if (!last) V[(int64_t)k * n + tid] = (tau == 0.0 && tid == lo1) ? 1.0 : vv;
-      }
-      if (tid == 0) { S.d[k] = S.col[k]; S.e[k] = beta; S.tau[k] = tau; }
-    )
-    const double tau = S.tau[k];
-    // ---- B: deferred update of reflector k-1 + mat-vec for reflector k, X in registers -----------
-    VI_PHASE(
-      {
-        double* xr = xreg + VI_TREG(tid, RPT);
-        const int g = tid / npair; const int cp = tid - g * npair;
-        const int c0 = 2 * cp;
-        if (g < VI_TRI_NG && c0 + 1 >= lo1) {
-          const double vc0 = S.vw[4 * c0]; const double wc0 = S.vw[4 * c0 + 1];
-          const double vc1 = S.vw[4 * c0 + 4]; const double wc1 = S.vw[4 * c0 + 5];
-          double a0 = 0.0; double a1 = 0.0;
-          const bool pub = (cp == lo1 / 2);        // this thread owns the next pivot column
-          const int pq = lo1 & 1;
-          VI_UNROLL_FULL
-          for (int kk = 0; kk < RPT; ++kk) {
-            const int i = g + VI_TRI_NG * kk;
-            if (i >= lo1 && i < n) {
-              const double* q = S.vw + 4 * i;
-              const vi_d2 vwi = *reinterpret_cast<const vi_d2*>(q);
-              const double vni = q[2];
-              double x0 = xr[2 * kk]; double x1 = xr[2 * kk + 1];
-              x0 = x0 - vwi.x * wc0; x0 = x0 - vwi.y * vc0;
-              x1 = x1 - vwi.x * wc1; x1 = x1 - vwi.y * vc1;
-              xr[2 * kk] = x0; xr[2 * kk + 1] = x1;
-              a0 += x0 * vni; a1 += x1 * vni;
-              if (pub) S.red2[i] = pq ? x1 : x0;     // column lo1 with reflector k-1 applied (read in C2)
-            }
-          }
-          S.psum[g * npad + c0] = a0;
-          S.psum[g * npad + c0 + 1] = a1;
-        }
-      }
-    )
-    // ---- C1 ------------------------------------------------------------------------------------
-    VI_PHASE(
-      if (tid >= lo1 && tid < n) {
-        double p = 0.0;
-        for (int g = 0; g < VI_TRI_NG; ++g) p += S.psum[g * npad + tid];
-        p = tau * p;
-        const double vn = S.vw[4 * tid + 2];
-        S.p[tid] = p;
-        S.red1[tid] = p * vn;
-        S.red3[tid] = vn * S.yv[tid];
-      }
-    )
-    // ---- C2 ------------------------------------------------------------------------------------
-    VI_PHASE(
-      if (tid < ((n + 31) & ~31)) {
-        const double dot = vi_warp_sum(lo1, n, tid & 31, [&](int i) { return S.red1[i]; });
-        const double dot2 = vi_warp_sum(lo1, n, tid & 31, [&](int i) { return S.red3[i]; });
-        if (tid >= lo1 && tid < n) {
-          const double a2 = -0.5 * tau * dot;
-          const double vn = S.vw[4 * tid + 2];
-          const double wn = S.p[tid] + a2 * vn;
-          S.yv[tid] = S.yv[tid] - (tau * dot2) * vn;
-          const double vlo = S.vw[4 * lo1 + 2];
-          const double wlo = S.p[lo1] + a2 * vlo;
-          S.col[tid] = (S.red2[tid] - vn * wlo) - wn * vlo;     // next pivot column
-          S.vw[4 * tid] = vn;
-          S.vw[4 * tid + 1] = wn;
-        }
-      }
-    )
-  }
-  VI_PHASE(
-    if (tid == 0) {
-      if (n == 1) S.d[0] = xreg[VI_TREG(0, RPT)];
       else S.d[n - 1] = S.col[n - 1];
       S.e[n - 1] = 0.0; S.tau[n - 1] = 0.0;
     }
