@@ -491,3 +491,59 @@ def test_properties_at_full_gate_count(cuda):
                                                          npts[idx].contiguous(), regs, _native.METHOD_CHI2)
     assert torch.equal(Cs, Cf[idx]) or torch.allclose(Cs, Cf[idx], rtol=0, atol=0, equal_nan=True)
     assert torch.equal(sts, status[idx])
+
+
+# ------------------------------------------------------------------ high order (BASELINE configs[2] shape: N = 500)
+def test_high_order_n500_functional(cuda):
+    """sphharmlag MAXK=5, MAXL=10, CAP_LIM=11 -> N = 500: the systems no longer fit one SM's shared memory,
+    the global-memory variants of the tridiagonalisation / QL run.  Stage parity of the solver against
+    lstsq on the fitted densities, normal equations against einsum, and an end-to-end fit that must
+    terminate with a defined status for every record."""
+    import torch
+    from volumetricinterp_b200 import _native, fit
+    from volumetricinterp_b200.models import sphharmlag
+    from volumetricinterp_b200 import synth
+    cfg = ("[DEFAULT]\nPARAM = dens\n[MODEL]\nNAME = sphharmlag\nMAXK = 5\nMAXL = 10\nCAP_LIM = 11\nMAX_Z_INT = INF\n"
+           "LATCP = 78\nLONCP = 262\n")
+    model = sphharmlag.Model(io.StringIO(cfg))
+    assert model.nbasis == 500
+    lat2, lon2, alt2 = synth.make_geometry(21, 60, seed=4)
+    lat, lon, alt, _ = synth.flatten_valid(lat2, lon2, alt2)
+    la, lo, al = (_t(cuda, a) for a in (lat, lon, alt))
+    P, N = len(lat), 500
+    A = torch.empty((P, N), dtype=torch.float64, device=cuda)
+    At = torch.empty((N, P), dtype=torch.float64, device=cuda)
+    model.basis_device(la, lo, al, out=A, out_t=At)
+    Ah = A.cpu().numpy()
+    om = rp.SphHarmLag(5, 10, 11, 78, 262)
+    Aref = om.basis(lat, lon, alt)
+    for c in range(N):
+        assert np.max(np.abs(Ah[:, c] - Aref[:, c])) <= 5e-12 * max(np.abs(Aref[:, c]).max(), 1e-300), c
+    R = 2
+    value, error, _ = synth.make_records(Ah, R, seed=9, maxl=10)
+    v, e = _t(cuda, value), _t(cuda, error)
+    with np.errstate(invalid="ignore"):
+        W = error ** -2
+    Gs, ys, _, npts, Wm, bm = fit.normal_equations_device(A, v, e, _t(cuda, W), _native.NE_STRICT)
+    ok = np.isfinite(value[0])
+    Gr, yr = rp.normal_equations(Ah[ok], W[0][ok], value[0][ok])
+    assert np.array_equal(Gs[0].cpu().numpy(), Gr) and np.array_equal(ys[0].cpu().numpy(), yr)
+    # a symmetric positive semidefinite stand-in regulariser (the solver does not care what it means)
+    rng = np.random.default_rng(1)
+    B = rng.standard_normal((N, 40))
+    reg = (B @ B.T) * 1e-20
+    lam = np.array([[1.0], [1e-3]])
+    Cf, rank, status = _solve(cuda, Gs.cpu().numpy(), ys.cpu().numpy(), reg[None], lam)
+    assert (status == 0).all()
+    for r in range(R):
+        okr = np.isfinite(value[r])
+        X = Gs[r].cpu().numpy() + lam[r, 0] * reg
+        ref = scipy.linalg.lstsq(X, ys[r].cpu().numpy())[0]
+        s = np.linalg.svd(X, compute_uv=False)
+        assert abs(int(rank[r]) - int((s > EPS * s[0]).sum())) <= 3
+        dref, dgpu = Ah[okr] @ ref, Ah[okr] @ Cf[r]
+        assert np.max(np.abs(dgpu - dref)) <= 1e-4 * np.abs(dref).max()
+    res = fit.fit_records(model, lat, lon, alt, value, error, [reg], "chi2", ne_mode=_native.NE_STRICT, device=cuda)
+    assert set(res.status.tolist()) <= {0, 1, 2}
+    good = (res.status == 0) | (res.status == 1)
+    assert np.isfinite(res.Coeffs[good]).all() and np.isnan(res.Coeffs[~good]).all()

@@ -121,17 +121,34 @@ VI_HD void vi_tri_load(const vi_tri_ws& S, int n, const double* G, const double*
   const int ld = S.ld;
   VI_PHASE(
     double mx = 0.0; double bad = 0.0;
-    for (int idx = tid; idx < n * n; idx += nt) {
-      int i = idx / n; int c = idx - i * n;
-      double x = 0.5 * (G[(int64_t)i * n + c] + G[(int64_t)c * n + i]);
-      for (int r = 0; r < nreg; ++r) {
-        double l = lam[r];
-        if (l != 0.0) x = fma(l, regs[((int64_t)r * n + i) * n + c], x);
+    // four elements per trip: the (up to 3 + nreg) global loads of each are independent, so their
+    // latencies overlap instead of adding up
+    for (int idx0 = tid; idx0 < n * n; idx0 += 4 * nt) {
+      double x[4]; int ii[4]; int cc[4];
+      VI_UNROLL4
+      for (int u = 0; u < 4; ++u) {
+        const int idx = idx0 + u * nt;
+        const bool ok = idx < n * n;
+        const int i = ok ? idx / n : 0; const int c = ok ? idx - i * n : 0;
+        ii[u] = ok ? i : -1; cc[u] = c;
+        x[u] = 0.5 * (G[(int64_t)i * n + c] + G[(int64_t)c * n + i]);
       }
-      if (arow) x = x - wj * (arow[i] * arow[c]);
-      if (!(fabs(x) <= 1.79769313486231570e308)) bad = 1.0;
-      mx = fmax(mx, fabs(x));
-      S.X[i * ld + c] = x;
+      for (int r = 0; r < nreg; ++r) {
+        const double l = lam[r];
+        if (l != 0.0) {
+          VI_UNROLL4
+          for (int u = 0; u < 4; ++u) x[u] = fma(l, regs[((int64_t)r * n + (ii[u] < 0 ? 0 : ii[u])) * n + cc[u]], x[u]);
+        }
+      }
+      VI_UNROLL4
+      for (int u = 0; u < 4; ++u) {
+        if (ii[u] < 0) continue;
+        double xv = x[u];
+        if (arow) xv = xv - wj * (arow[ii[u]] * arow[cc[u]]);
+        if (!(fabs(xv) <= 1.79769313486231570e308)) bad = 1.0;
+        mx = fmax(mx, fabs(xv));
+        S.X[ii[u] * ld + cc[u]] = xv;
+      }
     }
     for (int i = tid; i < n; i += nt) {
       double t = y[i];
