@@ -296,9 +296,9 @@ k_ne_dmma(const double* __restrict__ A, const double* __restrict__ value, const 
 // every fragment is two 128-bit shared loads), masked weights / data streamed by cp.async from the
 // arrays k_prep wrote (no division in the pipeline), 3 stages, one CTA barrier per 32 gates.
 // ---------------------------------------------------------------------------------------------
-constexpr int kEJ = 32;          // gates per stage (two k16 steps)
-constexpr int kELD = 34;         // doubles per staged column: 34 = 2 (mod 16) -> conflict-free 128-bit fragment loads
-constexpr int kEStages = 3;
+constexpr int kEJ = 64;          // gates per stage (four k16 steps)
+constexpr int kELD = 66;         // doubles per staged column: 66 = 2 (mod 16) -> conflict-free 128-bit fragment loads
+constexpr int kEStages = 2;
 
 __device__ __forceinline__ void dmma_16x8x16(double (&d)[4], const double (&a)[8], const double (&b)[4]) {
   asm volatile(
@@ -309,8 +309,8 @@ __device__ __forceinline__ void dmma_16x8x16(double (&d)[4], const double (&a)[8
         "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]));
 }
 
-// position of gate jj (0..31) inside a staged column: within each block of 16 gates, k -> 4 (k % 4) + k / 4
-__device__ __forceinline__ int gate_slot(int jj) { return (jj & 16) | ((jj & 3) << 2) | ((jj >> 2) & 3); }
+// position of gate jj (0..kEJ-1) inside a staged column: within each block of 16 gates, k -> 4 (k % 4) + k / 4
+__device__ __forceinline__ int gate_slot(int jj) { return (jj & ~15) | ((jj & 3) << 2) | ((jj >> 2) & 3); }
 
 template <int DT>
 __global__ void __launch_bounds__(kDW * 32)
@@ -376,12 +376,12 @@ k_ne_dmma2(const double* __restrict__ A, const double* __restrict__ Wm, const do
     cp_async_commit();
   };
 
-  stage_load(0);
-  if (nchunk > 1) stage_load(1);
+  // kEStages - 1 chunks in flight ahead of the one being consumed
+  for (int c = 0; c < kEStages - 1 && c < nchunk; ++c) stage_load(c);
   for (int ch = 0; ch < nchunk; ++ch) {
-    if (ch + 1 < nchunk) cp_async_wait<1>(); else cp_async_wait<0>();
-    __syncthreads();
-    if (ch + 2 < nchunk) stage_load(ch + 2);
+    if (kEStages >= 3 && ch + 1 < nchunk) cp_async_wait<kEStages - 2>(); else cp_async_wait<0>();
+    __syncthreads();       // chunk ch visible to all; everybody is done with the stage chunk ch + kEStages - 1 reuses
+    if (ch + kEStages - 1 < nchunk) stage_load(ch + kEStages - 1);
     const int st = ch % kEStages;
     const double* Sst = S + (size_t)st * cols * kELD;
     const double* Wst = sw + st * kEJ;
