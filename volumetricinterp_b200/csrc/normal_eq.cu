@@ -334,8 +334,12 @@ k_ne_dmma2(const double* __restrict__ A, const double* __restrict__ Wm, const do
   }
   for (int e = tid; e < kEStages * cols * kELD + kEStages * kEJ; e += blockDim.x) sm[e] = 0.0;
   __syncthreads();
-  const int t0 = warp * tpw;
-  const int t1 = min(ntiles, t0 + tpw);
+  // balanced split: ntiles / 12 tiles per warp, the remainder one each to the first warps (warps w, w+4, w+8
+  // share a tensor pipe, so the extras land on different sub-partitions)
+  (void)tpw;
+  const int tbase = ntiles / kDW, textra = ntiles % kDW;
+  const int t0 = warp * tbase + min(warp, textra);
+  const int t1 = t0 + tbase + (warp < textra ? 1 : 0);
   int tinfo[DT];
   double acc[DT][4];
 #pragma unroll
