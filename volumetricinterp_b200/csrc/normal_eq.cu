@@ -296,8 +296,8 @@ k_ne_dmma(const double* __restrict__ A, const double* __restrict__ value, const 
 // every fragment is two 128-bit shared loads), masked weights / data streamed by cp.async from the
 // arrays k_prep wrote (no division in the pipeline), 3 stages, one CTA barrier per 32 gates.
 // ---------------------------------------------------------------------------------------------
-constexpr int kEJ = 64;          // gates per stage (four k16 steps)
-constexpr int kELD = 66;         // doubles per staged column: 66 = 2 (mod 16) -> conflict-free 128-bit fragment loads
+constexpr int kEJ = 80;          // gates per stage (five k16 steps)
+constexpr int kELD = 82;         // doubles per staged column: 82 = 2 (mod 16) -> conflict-free 128-bit fragment loads
 constexpr int kEStages = 2;
 
 __device__ __forceinline__ void dmma_16x8x16(double (&d)[4], const double (&a)[8], const double (&b)[4]) {
