@@ -134,6 +134,114 @@ k_est_shl_tile(const double* __restrict__ lat, const double* __restrict__ lon, c
   }
 }
 
+// Many records on the FP64 tensor cores: out[r][p] = sum_n basis(p)[n] C[r][n] is a GEMM
+// [points x N] . [N x records].  The CTA evaluates the basis rows of its 128 points ONCE into shared
+// memory, then streams the coefficient vectors through in chunks of 32 records (double buffered) and
+// contracts with mma.sync.m16n8k16.f64.  Both operands are stored with the k index permuted inside each
+// group of 16 (k -> 4 (k % 4) + k / 4) and a row stride = 2 (mod 16) doubles, so that every fragment is
+// two conflict-free 128-bit shared loads (same scheme as k_ne_dmma2).
+constexpr int kMmaRC = 32;          // records per chunk
+
+__device__ __forceinline__ int k_slot(int k) { return (k & ~15) | ((k & 3) << 2) | ((k >> 2) & 3); }
+
+__device__ __forceinline__ void est_dmma(double (&d)[4], const double (&a)[8], const double (&b)[4]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+      "{%12,%13,%14,%15}, {%0,%1,%2,%3};\n"
+      : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3])
+      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]),
+        "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]));
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_est_shl_mma(const double* __restrict__ lat, const double* __restrict__ lon, const double* __restrict__ alt,
+              int64_t npts, const __grid_constant__ vi_shl_params P, const double* __restrict__ C, int Rsel,
+              const double* __restrict__ eq, int F, double* __restrict__ out, int KP, int LD) {
+  extern __shared__ __align__(16) double smem[];
+  double* sA = smem;                              // kThreads x LD   basis rows (slot order)
+  double* sC = smem + (size_t)kThreads * LD;      // 2 x kMmaRC x LD coefficient chunks (slot order)
+  __shared__ unsigned char s_in[kThreads];
+  const int N = P.maxk * P.maxl * P.maxl;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int64_t p0 = (int64_t)blockIdx.x * kThreads;
+  const int64_t p = p0 + tid;
+  // ---- phase 1: one thread per point evaluates its basis row into shared memory ----------------------
+  {
+    double* row = sA + (size_t)tid * LD;
+    for (int k = N; k < KP; ++k) row[k_slot(k)] = 0.0;      // K padding
+    bool in = false;
+    if (p < npts) {
+      const double la = lat[p], lo = lon[p], al = alt[p];
+      in = true;
+      if (F > 0) {
+        double x, y, z;
+        vi_geodetic2ecef(la, lo, al, &x, &y, &z);
+        in = inside_hull(eq, F, x, y, z);
+      }
+      if (in) vi_shl_row(P, la, lo, al, [&](int n, double v) { row[k_slot(n)] = v; });
+    }
+    if (!in) for (int k = 0; k < N; ++k) row[k_slot(k)] = 0.0;
+    s_in[tid] = in ? 1 : 0;
+  }
+  auto load_chunk = [&](int chunk, int buf) {
+    double* dst = sC + (size_t)buf * kMmaRC * LD;
+    const int r0 = chunk * kMmaRC;
+    for (int e = tid; e < kMmaRC * KP; e += kThreads) {
+      const int rr = e / KP, k = e - rr * KP;
+      double v = 0.0;
+      if (r0 + rr < Rsel && k < N) v = C[(int64_t)(r0 + rr) * N + k];
+      dst[rr * LD + k_slot(k)] = v;
+    }
+  };
+  const int nchunk = (Rsel + kMmaRC - 1) / kMmaRC;
+  load_chunk(0, 0);
+  __syncthreads();
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  // warp w owns points 32 w .. 32 w + 31 = two m16 tiles; four n8 tiles cover the 32 records of a chunk
+  for (int ch = 0; ch < nchunk; ++ch) {
+    if (ch + 1 < nchunk) load_chunk(ch + 1, (ch + 1) & 1);
+    const double* Cb = sC + (size_t)(ch & 1) * kMmaRC * LD;
+    double acc[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.0;
+    for (int ks = 0; ks < KP / 16; ++ks) {
+      const int kb = 16 * ks + 4 * t;
+      double a[2][8];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const double* q0 = sA + (size_t)(32 * warp + 16 * mt + g) * LD + kb;
+        const double* q1 = q0 + 8 * LD;
+        const double2 x01 = *reinterpret_cast<const double2*>(q0), x23 = *reinterpret_cast<const double2*>(q0 + 2);
+        const double2 z01 = *reinterpret_cast<const double2*>(q1), z23 = *reinterpret_cast<const double2*>(q1 + 2);
+        a[mt][0] = x01.x; a[mt][2] = x01.y; a[mt][4] = x23.x; a[mt][6] = x23.y;
+        a[mt][1] = z01.x; a[mt][3] = z01.y; a[mt][5] = z23.x; a[mt][7] = z23.y;
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const double* pb = Cb + (size_t)(8 * nt + g) * LD + kb;
+        const double2 b01 = *reinterpret_cast<const double2*>(pb), b23 = *reinterpret_cast<const double2*>(pb + 2);
+        const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+        est_dmma(acc[0][nt], a[0], b);
+        est_dmma(acc[1][nt], a[1], b);
+      }
+    }
+    // c0 (point g, record 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int pl = 32 * warp + 16 * mt + g + ((v & 2) ? 8 : 0);
+          const int r = ch * kMmaRC + 8 * nt + 2 * t + (v & 1);
+          if (p0 + pl < npts && r < Rsel) out[(int64_t)r * npts + p0 + pl] = s_in[pl] ? acc[mt][nt][v] : nan;
+        }
+    __syncthreads();
+  }
+}
+
 template <int RT>
 __global__ void __launch_bounds__(kThreads)
 k_est_rbf(const double* __restrict__ lat, const double* __restrict__ lon, const double* __restrict__ alt,
@@ -209,8 +317,17 @@ extern "C" int vi_estimate_sphharmlag(const double* lat, const double* lon, cons
   } else if (Rsel <= 8 || smem > 220 * 1024) {
     VI_KERNEL(VI_K_ESTIMATE, s, k_est_shl_reg<8><<<grid, kThreads, 0, s>>>(lat, lon, alt, npts, *params, C, Rsel, hull_eq, F, out));
   } else {
-    VI_CUDA(cudaFuncSetAttribute(k_est_shl_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VI_KERNEL(VI_K_ESTIMATE, s, k_est_shl_tile<<<grid, kThreads, smem, s>>>(lat, lon, alt, npts, *params, C, Rsel, hull_eq, F, out));
+    const int KP = (N + 15) / 16 * 16;
+    int LD = KP + 2;
+    while (LD % 16 != 2) ++LD;
+    const size_t smem_mma = ((size_t)kThreads * LD + 2 * (size_t)kMmaRC * LD) * sizeof(double);
+    if (Rsel >= 16 && smem_mma <= 227 * 1024 - 256) {
+      VI_CUDA(cudaFuncSetAttribute(k_est_shl_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma));
+      VI_KERNEL(VI_K_ESTIMATE, s, k_est_shl_mma<<<grid, kThreads, smem_mma, s>>>(lat, lon, alt, npts, *params, C, Rsel, hull_eq, F, out, KP, LD));
+    } else {
+      VI_CUDA(cudaFuncSetAttribute(k_est_shl_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VI_KERNEL(VI_K_ESTIMATE, s, k_est_shl_tile<<<grid, kThreads, smem, s>>>(lat, lon, alt, npts, *params, C, Rsel, hull_eq, F, out));
+    }
   }
   VI_LAUNCH_CHECK();
   return VI_OK;
