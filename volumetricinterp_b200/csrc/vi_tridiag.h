@@ -93,7 +93,7 @@ VI_HD int vi_tri_npair(int n) { return (n + 1) / 2; }
 VI_HD int vi_tri_groups(int n, int nt) { int ng = nt / vi_tri_npair(n); return ng < 1 ? 1 : ng; }
 // doubles of CTA-shared storage needed besides X
 VI_HD int vi_tri_aux_doubles(int n, int nt) {
-  return 4 * (n + 2) + (n + 2) + 6 * n + (nt > n ? nt : n) + vi_tri_groups(n, nt) * 2 * vi_tri_npair(n) + 8;
+  return 4 * (n + 2) + (n + 2) + 6 * n + (nt > n ? nt : n) + vi_tri_groups(n, nt) * 2 * vi_tri_npair(n) + 10;
 }
 // carve the auxiliary arrays out of one block of vi_tri_aux_doubles(n, nt) doubles (16-byte aligned)
 VI_HD void vi_tri_carve(vi_tri_ws& S, double* aux, int n, int nt) {
@@ -107,7 +107,7 @@ VI_HD void vi_tri_carve(vi_tri_ws& S, double* aux, int n, int nt) {
   S.tau = aux; aux += n;
   S.sc = aux; aux += 8;
   S.red1 = aux; aux += (nt > n ? nt : n);
-  S.psum = aux;
+  S.psum = aux + ((reinterpret_cast<uintptr_t>(aux) >> 3) & 1);     // 16-byte aligned (pair stores)
 }
 
 // X <- scl * (0.5 (G + G^T) + sum_r lam[r] Reg_r),  scl = 2^-exponent(max|X|);  yv <- y;  col <- X[:,0];
@@ -181,54 +181,72 @@ VI_HD void vi_tri_load(const vi_tri_ws& S, int n, const double* G, const double*
   )
 }
 
+// Reflector k from the pivot column S.col (which already carries every earlier update): d[k], e[k],
+// tau[k], vnext (S.vw[4 i + 2]) and row k of V.  Called by whole warps (warp-sum inside); the threads
+// tid in [k+1, n) store their element.
+VI_HD void vi_tri_reflector(const vi_tri_ws& S, int n, int k, double* V, int tid) {
+  const int lo1 = k + 1;
+  double tau = 0.0; double beta = 0.0; double scale = 0.0;
+  const bool last = (k == n - 2);
+  if (!last) {
+    const double xn2 = vi_warp_sum(k + 2, n, tid & 31, [&](int i) { double x = S.col[i]; return x * x; });
+    const double alpha = S.col[k + 1];
+    beta = alpha;
+    if (xn2 != 0.0) {
+      const double r2 = alpha * alpha + xn2;
+#if defined(__CUDA_ARCH__)
+      const double ri = rsqrt(r2);
+#else
+      const double ri = 1.0 / sqrt(r2);
+#endif
+      const double nrm = r2 * ri;
+      beta = -copysign(nrm, alpha);
+      tau = 1.0 + fabs(alpha) * ri;                        // (beta - alpha) / beta
+      scale = copysign(1.0, alpha) / (fabs(alpha) + nrm);  // 1 / (alpha - beta)
+    }
+  } else {
+    beta = S.col[n - 1];
+  }
+  if (tid >= lo1 && tid < n) {
+    double vv = 0.0;
+    if (tau != 0.0) vv = (tid == lo1) ? 1.0 : S.col[tid] * scale;
+    S.vw[4 * tid + 2] = vv;
+    if (!last) V[(int64_t)k * n + tid] = (tau == 0.0 && tid == lo1) ? 1.0 : vv;
+  }
+  if (tid == 0) { S.d[k] = S.col[k]; S.e[k] = beta; S.tau[k] = tau; }
+}
+
+// Sub-phase of the first `nsub` threads only (whole warps), closed by a NAMED barrier among them: the
+// other warps of the CTA are parked at the next CTA barrier and are not disturbed.
+#if defined(__CUDA_ARCH__)
+#define VI_SUBPHASE(nsub, ...) if (tid < (nsub)) { { __VA_ARGS__; } asm volatile("bar.sync 1, %0;" ::"r"(nsub) : "memory"); }
+#else
+#define VI_SUBPHASE(nsub, ...) for (int tid = 0; tid < (nsub) && tid < nt; ++tid) { __VA_ARGS__; }
+#endif
+
 // Reduction proper, FUSED form: the rank-2 update of reflector k-1 is deferred and applied in the same
 // pass over the trailing matrix that forms the mat-vec for reflector k (one read + one write of X per
 // Householder step instead of two reads + one write).  Iteration k = 0 .. n-2:
-//   A  every warp: norm of the pivot column (warp-sum) -> reflector k (vnext), d[k], e[k], tau[k]
-//   B  all threads, two columns each: x = X[i][c] - v[i] w[c] - w[i] v[c]; store; acc_c += x vnext[i]
-//   C1 column owners: p = tau * sum of partials; products for the two dot products
-//   C2 their warps: dot products (warp-sum), w for reflector k, rhs update, and the NEXT pivot column
-//      (column k+1 with the update of reflector k already applied), then (v, w) <- (vnext, wnext)
-// 4 CTA barriers per step.  V (global or host): row k holds reflector k in columns k+1..n-1
-// (v[k+1] = 1 stored explicitly).  After the call S.d, S.e, S.tau, S.yv (= Q^T y) are final.
+//   B   all threads, two columns each: x = X[i][c] - v[i] w[c] - w[i] v[c]; store; acc_c += x vnext[i]
+//       -> CTA barrier
+//   C   the ceil(n/32) warps that own a vector element, with named barriers between the sub-steps:
+//       C1 p = tau * sum of partials, products | C2 dot products (warp-sum), w for reflector k, rhs update,
+//       NEXT pivot column (column k+1 with reflector k applied), (v, w) <- (vnext, wnext) | C3 reflector k+1
+//       -> CTA barrier
+// i.e. 2 CTA barriers per step; the small O(n) section never stalls on the full CTA.  V (global or host):
+// row k holds reflector k in columns k+1..n-1 (v[k+1] = 1 stored explicitly).  After the call S.d, S.e,
+// S.tau, S.yv (= Q^T y) are final.
 VI_HD void vi_tri_reduce(const vi_tri_ws& S, int n, double* V, int tid, int nt) {
   (void)tid;
   const int ld = S.ld;
   const int npair = vi_tri_npair(n), npad = 2 * npair;
   const int ng = vi_tri_groups(n, nt);
+  const int nsub = (n + 31) & ~31;
+  if (n >= 2) {
+    VI_PHASE( if (tid < nsub) vi_tri_reflector(S, n, 0, V, tid); )
+  }
   for (int k = 0; k + 1 < n; ++k) {
     const int lo1 = k + 1;
-    // ---- A: reflector k from the pivot column --------------------------------------------------
-    VI_PHASE(
-      double tau = 0.0; double beta = 0.0; double scale = 0.0;
-      const bool last = (k == n - 2);
-      if (!last) {
-        const double xn2 = vi_warp_sum(k + 2, n, tid & 31, [&](int i) { double x = S.col[i]; return x * x; });
-        const double alpha = S.col[k + 1];
-        beta = alpha;
-        if (xn2 != 0.0) {
-          const double r2 = alpha * alpha + xn2;
-#if defined(__CUDA_ARCH__)
-          const double ri = rsqrt(r2);
-#else
-          const double ri = 1.0 / sqrt(r2);
-#endif
-          const double nrm = r2 * ri;
-          beta = -copysign(nrm, alpha);
-          tau = 1.0 + fabs(alpha) * ri;                      // (beta - alpha) / beta
-          scale = copysign(1.0, alpha) / (fabs(alpha) + nrm);  // 1 / (alpha - beta)
-        }
-      } else {
-        beta = S.col[n - 1];
-      }
-      if (tid >= lo1 && tid < n) {
-        double vv = 0.0;
-        if (tau != 0.0) vv = (tid == lo1) ? 1.0 : S.col[tid] * scale;
-        S.vw[4 * tid + 2] = vv;
-        if (!last) V[(int64_t)k * n + tid] = (tau == 0.0 && tid == lo1) ? 1.0 : vv;
-      }
-      if (tid == 0) { S.d[k] = S.col[k]; S.e[k] = beta; S.tau[k] = tau; }
-    )
     const double tau = S.tau[k];
     // ---- B: deferred update of reflector k-1 fused with the mat-vec for reflector k -------------
     VI_PHASE(
@@ -253,13 +271,13 @@ VI_HD void vi_tri_reduce(const vi_tri_ws& S, int n, double* V, int tid, int nt) 
             a0 += x.x * vni; a1 += x.y * vni;
             xp += step; q += 4 * ng;
           }
-          S.psum[g * npad + c0] = a0;
-          S.psum[g * npad + c0 + 1] = a1;
+          vi_d2 ps; ps.x = a0; ps.y = a1;
+          *reinterpret_cast<vi_d2*>(S.psum + g * npad + c0) = ps;
         }
       }
     )
     // ---- C1: p = tau * (X v), products ---------------------------------------------------------
-    VI_PHASE(
+    VI_SUBPHASE(nsub,
       if (tid >= lo1 && tid < n) {
         double p = 0.0;
         for (int g = 0; g < ng; ++g) p += S.psum[g * npad + tid];
@@ -271,8 +289,8 @@ VI_HD void vi_tri_reduce(const vi_tri_ws& S, int n, double* V, int tid, int nt) 
       }
     )
     // ---- C2: dot products, w, rhs, next pivot column, rotate (v, w) <- (vnext, wnext) ------------
-    VI_PHASE(
-      if (tid < ((n + 31) & ~31)) {
+    VI_SUBPHASE(nsub,
+      {
         const double dot = vi_warp_sum(lo1, n, tid & 31, [&](int i) { return S.red1[i]; });
         const double dot2 = vi_warp_sum(lo1, n, tid & 31, [&](int i) { return S.red2[i]; });
         if (tid >= lo1 && tid < n) {
@@ -288,6 +306,11 @@ VI_HD void vi_tri_reduce(const vi_tri_ws& S, int n, double* V, int tid, int nt) 
           S.vw[4 * tid + 1] = wn;
         }
       }
+    )
+    // ---- C3: reflector k + 1 (its vnext must not overwrite vw[.][2] before every C2 thread read it:
+    // the named barrier above orders that) ---------------------------------------------------------
+    VI_PHASE(
+      if (tid < nsub && k + 2 < n) vi_tri_reflector(S, n, k + 1, V, tid);
     )
   }
   VI_PHASE(
