@@ -141,6 +141,28 @@ void h_chi2_bracket(const double* table, int npts, int* status, int* k_lo, doubl
   *status = br.status; *k_lo = br.k_lo; *nu = br.nu;
 }
 
+// Lazy table phase of vi_fit_batched (k_table_plan / k_table_advance in csrc/fit.cu): entries are revealed `step`
+// at a time, entries past `lim` replicate entry lim-1; returns how many distinct entries had to be evaluated
+// and the bracket found on the partially filled table (unevaluated entries are poisoned with NaN).
+int h_chi2_bracket_lazy(const double* full, int npts, int step, int lim, int* status, int* k_lo, double* nu) {
+  double tab[VI_NALPHA];
+  for (int k = 0; k < VI_NALPHA; ++k) tab[k] = NAN;
+  int kdone = 0;
+  bool walking = true;
+  while (walking) {
+    int c = lim - kdone; if (c > step) c = step;
+    if (c <= 0) break;
+    for (int k = kdone; k < kdone + c; ++k) tab[k] = full[k];
+    kdone += c;
+    int avail = kdone;
+    if (kdone >= lim) { for (int k = lim; k < VI_NALPHA; ++k) tab[k] = tab[lim - 1]; avail = VI_NALPHA; }
+    walking = vi_chi2_walk_needs_more(tab, 1, npts, avail);
+  }
+  vi_bracket br = vi_chi2_bracket(tab, 1, npts);
+  *status = br.status; *k_lo = br.k_lo; *nu = br.nu;
+  return kdone;
+}
+
 // The complete per-system pipeline of kernels k_tridiag + k_tql (csrc/fit.cu) executed on the CPU
 // with the phase bodies of vi_tridiag.h run for tid = 0..nt-1 in turn:
 //   X = 2^-ex (sym(G) + sum lam_r Reg_r) -> T = Q^T X Q -> QL with tape -> truncated solve -> C = Q c~.

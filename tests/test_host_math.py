@@ -209,6 +209,43 @@ def test_bracket_walk(harness):
             assert nu.value == enu
 
 
+def test_lazy_table_gives_the_same_bracket(harness):
+    """The table chi2(10^-k) is extended a few decades at a time and only as far as the walk reads
+    (csrc/fit.cu k_table_plan / k_table_advance): same bracket as with all 102 entries, fewer systems."""
+    rng = np.random.default_rng(11)
+    saved = 0
+    for trial in range(400):
+        npts = int(rng.integers(50, 800))
+        kind = trial % 5
+        k0 = rng.integers(1, 100)
+        lim = int(rng.integers(1, 103)) if trial % 3 else 102
+        if kind == 0:
+            table = npts * (1.5 - 1.0 / (1 + np.exp(-(np.arange(102) - k0))))
+        elif kind == 1:
+            table = npts * (1.2 + rng.uniform(0, 1, 102))
+        elif kind == 2:
+            table = npts * rng.uniform(0.1, 0.5, 102)
+        elif kind == 3:
+            table = npts * rng.uniform(0.5, 1.6, 102)
+            table[0] = npts * 1.7
+        else:              # a failed system (NaN) somewhere
+            table = npts * (1.5 - 1.0 / (1 + np.exp(-(np.arange(102) - k0))))
+            table[int(rng.integers(0, 102))] = np.nan
+        table = np.ascontiguousarray(table)
+        table[lim:] = table[lim - 1]        # systems with k >= kstar are bit-identical
+        for step in (1, 4, 7, 16):
+            st, k, nu = C.c_int(0), C.c_int(0), C.c_double(0)
+            done = harness.h_chi2_bracket_lazy(dptr(table), npts, step, lim, C.byref(st), C.byref(k), C.byref(nu))
+            est, ek, enu = _walk_python(table, npts)
+            assert (st.value, k.value) == (est, ek)
+            if est != 2:
+                assert nu.value == enu
+            if est == 0 and enu == npts * 0.6:      # bracket at the first scale factor: nothing past it is touched
+                assert done <= min(lim, (ek // step + 1) * step)
+            saved += lim - done
+    assert saved > 0
+
+
 def test_nelder_mead_state_machine_replays_scipy(harness):
     """Same abscissae, same minimiser, same nit / nfev / success as scipy's Nelder-Mead (interpolate.py:291)."""
     FN = C.CFUNCTYPE(C.c_double, C.c_double)

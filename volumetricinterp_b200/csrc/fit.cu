@@ -22,6 +22,9 @@
 // all records in lock step (vi_brent.h state machine), one batch of systems per iteration.
 #include "common.cuh"
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
 #include <vector>
 #include "vi_brent.h"
 #include "vi_nm.h"
@@ -113,7 +116,9 @@ struct UnitBuf {      // one search unit = (record, regulariser)
   int32_t* active;    // U
   int32_t* tabbad;    // U
   int32_t* kstar;     // U
-  int64_t* off;       // U + 1: exclusive prefix sum of the number of distinct table systems per unit
+  int32_t* kdone;     // U   table entries chi2(10^-k), k < kdone, evaluated so far
+  int32_t* walking;   // U   the decade walk of this unit still needs entries beyond kdone
+  int64_t* off;       // U + 1: exclusive prefix sum of the number of table systems per unit in this pass
   vi_nm* nm;          // U   Nelder-Mead state (GCV)
   double* fsum;       // U   GCV objective being accumulated
   double* alpha;      // U   abscissa under evaluation
@@ -128,6 +133,8 @@ void unit_carve(Bump& b, UnitBuf& Ub, int64_t U) {
   Ub.active = b.take<int32_t>(U);
   Ub.tabbad = b.take<int32_t>(U);
   Ub.kstar = b.take<int32_t>(U);
+  Ub.kdone = b.take<int32_t>(U);
+  Ub.walking = b.take<int32_t>(U);
   Ub.off = b.take<int64_t>(U + 1);
   Ub.nm = b.take<vi_nm>(U);
   Ub.fsum = b.take<double>(U);
@@ -581,41 +588,55 @@ __global__ void k_chi2_sum(int64_t nsys, const int32_t* __restrict__ st, const d
 }
 
 // ---- system set-up for the three phases ---------------------------------------------------
-// table phase: global system index t = u*VI_NALPHA + k, chunk covers [t0, t0 + cnt)
-// Exclusive prefix sum of the distinct table systems per unit (min(kstar, NALPHA-1) + 1, or 0 for a unit
-// without valid gates): one block, each thread scans a contiguous slice.
-__global__ void __launch_bounds__(1024)
-k_table_offsets(int64_t U, int nreg, const int32_t* __restrict__ npts, const int32_t* __restrict__ kstar,
-                int64_t* __restrict__ off) {
-  __shared__ int64_t part[1024];
-  const int t = threadIdx.x;
-  const int64_t per = (U + 1023) / 1024;
-  const int64_t a = t * per, b = (a + per < U) ? a + per : U;
-  int64_t sum = 0;
-  for (int64_t u = a; u < b; ++u) {
-    int ks = kstar[u];
-    sum += (npts[u / nreg] > 0) ? ((ks < VI_NALPHA - 1 ? ks : VI_NALPHA - 1) + 1) : 0;
+// Table phase, LAZY: the decade walk (interpolate.py:180-207) reads chi2(10^-k) for k = 0, 1, ... and stops at
+// the first sign change of chi2 - nu, so only the entries up to there are ever needed.  The table is extended in
+// passes of `step` decades per unit; after each pass the walk (first scale factor) is replayed on what exists
+// and the unit leaves the table phase as soon as it would not read further.  A unit whose walk runs off the
+// end gets its full table (the later scale factors re-read it).  Decisions are identical to evaluating all
+// 102 entries up front; only entries the reference never looks at are skipped.
+__device__ __forceinline__ int table_limit(int ks) { return (ks < VI_NALPHA - 1 ? ks : VI_NALPHA - 1) + 1; }
+
+__global__ void k_table_init(int64_t U, int nreg, const int32_t* __restrict__ npts, UnitBuf Ub) {
+  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  Ub.kdone[u] = 0;
+  Ub.walking[u] = npts[u / nreg] > 0 ? 1 : 0;
+}
+
+__global__ void k_table_plan(int64_t U, int step, UnitBuf Ub, int64_t* __restrict__ cnt) {
+  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  int c = 0;
+  if (Ub.walking[u]) {
+    c = table_limit(Ub.kstar[u]) - Ub.kdone[u];
+    if (c > step) c = step;
   }
-  part[t] = sum;
-  __syncthreads();
-  if (t == 0) {
-    int64_t run = 0;
-    for (int i = 0; i < 1024; ++i) { int64_t v = part[i]; part[i] = run; run += v; }
-    off[U] = run;
+  cnt[u] = c;
+}
+
+// after a pass: account for the new entries, replicate entries k > kstar (bit-identical systems) once the
+// distinct ones are complete, and replay the walk to see whether it needs more
+__global__ void k_table_advance(int64_t U, int nreg, const int32_t* __restrict__ npts, const int64_t* __restrict__ cnt,
+                                UnitBuf Ub) {
+  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= U || !Ub.walking[u]) return;
+  const int kd = Ub.kdone[u] + (int)cnt[u];
+  Ub.kdone[u] = kd;
+  const int lim = table_limit(Ub.kstar[u]);
+  double* tab = Ub.table + u * VI_NALPHA;
+  int avail = kd;
+  if (kd >= lim) {
+    const double v = tab[lim - 1];
+    for (int k = lim; k < VI_NALPHA; ++k) tab[k] = v;
+    avail = VI_NALPHA;
   }
-  __syncthreads();
-  int64_t run = part[t];
-  for (int64_t u = a; u < b; ++u) {
-    off[u] = run;
-    int ks = kstar[u];
-    run += (npts[u / nreg] > 0) ? ((ks < VI_NALPHA - 1 ? ks : VI_NALPHA - 1) + 1) : 0;
-  }
+  Ub.walking[u] = vi_chi2_walk_needs_more(tab, 1, npts[u / nreg], avail) ? 1 : 0;
 }
 
 // table phase, compact numbering: system t in [0, off[U]) belongs to unit u = last unit with off[u] <= t,
-// k = t - off[u]; the chunk covers [t0, t0 + cnt)
+// k = kdone[u] + t - off[u]; the chunk covers [t0, t0 + cnt)
 __global__ void k_setup_table(int64_t t0, int64_t cnt, int64_t U, int nreg, const double* __restrict__ pow10tab,
-                              const int64_t* __restrict__ off, SysBuf B) {
+                              const int64_t* __restrict__ off, const int32_t* __restrict__ kdone, SysBuf B) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= B.cap) return;
   if (s >= cnt) { B.rec[s] = kSkip; return; }
@@ -626,7 +647,7 @@ __global__ void k_setup_table(int64_t t0, int64_t cnt, int64_t U, int nreg, cons
     if (off[mid] <= t) lo = mid; else hi = mid;
   }
   const int64_t u = lo;
-  const int k = (int)(t - off[u]);
+  const int k = kdone[u] + (int)(t - off[u]);
   const int r = (int)(u / nreg), q = (int)(u - (int64_t)r * nreg);
   B.rec[s] = r;
   B.unit[s] = (int32_t)u;
@@ -668,15 +689,6 @@ k_kstar(int nreg, int n, const double* __restrict__ G, const double* __restrict_
   if (threadIdx.x == 0) kstar[u] = hi;
 }
 
-__global__ void k_fill_table(int64_t U, const int32_t* __restrict__ kstar, UnitBuf Ub) {
-  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= U) return;
-  const int ks = kstar[u];
-  if (ks >= VI_NALPHA) return;
-  const double v = Ub.table[u * VI_NALPHA + ks];
-  for (int k = ks + 1; k < VI_NALPHA; ++k) Ub.table[u * VI_NALPHA + k] = v;
-}
-
 __global__ void k_scatter_table(int64_t cnt, SysBuf B, UnitBuf Ub) {
   int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= cnt) return;
@@ -695,9 +707,14 @@ __global__ void k_bracket(int64_t U, int nreg, const int32_t* __restrict__ npts,
   Ub.active[u] = 0;
   Ub.nu[u] = 0.0;
   if (npts[r] <= 0) { Ub.status[u] = VI_ST_EMPTY; return; }
-  if (Ub.tabbad[u] != 0) { Ub.status[u] = Ub.tabbad[u]; return; }
   const double* tab = Ub.table + u * VI_NALPHA;
   vi_bracket br = vi_chi2_bracket(tab, 1, npts[r]);
+  if (Ub.tabbad[u] != 0) {
+    // a table system failed: it only matters if the walk actually read that entry (stored as NaN)
+    const int last = (br.status == VI_ST_OK) ? br.k_lo : (br.status == VI_ST_TOO_SMOOTH ? 0 : VI_NALPHA - 1);
+    for (int k = 0; k <= last; ++k)
+      if (isnan(tab[k])) { Ub.status[u] = Ub.tabbad[u]; return; }
+  }
   Ub.status[u] = br.status;
   Ub.nu[u] = br.nu;
   if (br.status != VI_ST_OK) return;
@@ -1134,24 +1151,38 @@ extern "C" int vi_fit_batched(const double* At, const double* A, const double* W
     VI_CUDA(cudaMemsetAsync(Ub.count, 0, 8 * sizeof(int32_t), st));
     // ---- phase 1: chi2(10^-k) table for every unit -------------------------------------
     VI_KERNEL(VI_K_MISC, st, k_kstar<<<(unsigned)U, 256, 0, st>>>(nreg, N, G, regmats, pow10tab, Ub.kstar));
-    VI_KERNEL(VI_K_MISC, st, k_table_offsets<<<1, 1024, 0, st>>>(U, nreg, npts, Ub.kstar, Ub.off));
-    int64_t T = 0;
-    VI_CUDA(cudaMemcpyAsync(&T, Ub.off + U, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    VI_CUDA(cudaStreamSynchronize(st));
+    VI_KERNEL(VI_K_MISC, st, k_table_init<<<blocks(U, 128), 128, 0, st>>>(U, nreg, npts, Ub));
+    // decades per pass: small when there are many units (little overshoot past the sign change, the
+    // batches stay large), larger for few units (fewer latency-bound passes)
+    int step = (int)(cap / (U > 0 ? U : 1));
+    if (step < 4) step = 4;
+    if (step > 16) step = 16;
+    if (const char* e = getenv("VI_TABLE_STEP")) { int v = atoi(e); if (v >= 1) step = v; }
     // (A two-stream variant that overlapped apply/chi2 of one chunk with the tridiagonalisation of the next
     // was measured on B200 and gave no gain: 3.72 s vs 3.69 s per 10 k records; kept simple instead.)
-    for (int64_t t0 = 0; t0 < T; t0 += cap) {
-      int64_t cnt = (T - t0 < cap) ? T - t0 : cap;
-      VI_KERNEL(VI_K_MISC, st, k_setup_table<<<blocks(cap, 256), 256, 0, st>>>(t0, cnt, U, nreg, pow10tab, Ub.off, B));
-      if (int rc = run_systems(cnt, G, y, regmats, B, rcond, B.Csys, B.rank, st)) return rc;
-      if (int rc = run_chi2(cnt, At, Wm, bm, P, B, B.Csys, B.chi2, st)) return rc;
-      VI_KERNEL(VI_K_MISC, st, k_scatter_table<<<blocks(cnt, 256), 256, 0, st>>>(cnt, B, Ub));
+    for (int pass = 0; pass < VI_NALPHA + 1; ++pass) {
+      VI_KERNEL(VI_K_MISC, st, k_table_plan<<<blocks(U, 128), 128, 0, st>>>(U, step, Ub, ucount));
+      VI_KERNEL(VI_K_MISC, st, k_scan_counts<<<1, 1024, 0, st>>>(U, ucount, Ub.off));
+      int64_t T = 0;
+      VI_CUDA(cudaMemcpyAsync(&T, Ub.off + U, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      VI_CUDA(cudaStreamSynchronize(st));
+      if (T == 0) break;
+      for (int64_t t0 = 0; t0 < T; t0 += cap) {
+        int64_t cnt = (T - t0 < cap) ? T - t0 : cap;
+        VI_KERNEL(VI_K_MISC, st, k_setup_table<<<blocks(cap, 256), 256, 0, st>>>(t0, cnt, U, nreg, pow10tab, Ub.off, Ub.kdone, B));
+        if (int rc = run_systems(cnt, G, y, regmats, B, rcond, B.Csys, B.rank, st)) return rc;
+        if (int rc = run_chi2(cnt, At, Wm, bm, P, B, B.Csys, B.chi2, st)) return rc;
+        VI_KERNEL(VI_K_MISC, st, k_scatter_table<<<blocks(cnt, 256), 256, 0, st>>>(cnt, B, Ub));
+      }
+      solved += T;
+      VI_KERNEL(VI_K_MISC, st, k_table_advance<<<blocks(U, 128), 128, 0, st>>>(U, nreg, npts, ucount, Ub));
     }
-    solved += T;
-    VI_KERNEL(VI_K_MISC, st, k_fill_table<<<blocks(U, 128), 128, 0, st>>>(U, Ub.kstar, Ub));
     // ---- phase 2: bracket + Brent in lock step ------------------------------------------
     VI_KERNEL(VI_K_MISC, st, k_bracket<<<blocks(U, 128), 128, 0, st>>>(U, nreg, npts, Ub));
     VI_LAUNCH_CHECK();
+    const bool dbg = getenv("VI_DEBUG_ROUNDS") != nullptr;
+    struct timespec ts0;
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
     for (int it = 0; it < VI_BRENT_MAXITER + 2; ++it) {
       int64_t round_total = 0;
       for (int64_t u0 = 0; u0 < U; u0 += cap) {
@@ -1166,6 +1197,13 @@ extern "C" int vi_fit_batched(const double* At, const double* A, const double* W
         if (int rc = run_systems(h_count, G, y, regmats, B, rcond, B.Csys, B.rank, st)) return rc;
         if (int rc = run_chi2(h_count, At, Wm, bm, P, B, B.Csys, B.chi2, st)) return rc;
         VI_KERNEL(VI_K_MISC, st, k_brent_feed<<<blocks(h_count, 128), 128, 0, st>>>(h_count, B, Ub));
+      }
+      if (dbg) {
+        struct timespec ts1;
+        clock_gettime(CLOCK_MONOTONIC, &ts1);
+        fprintf(stderr, "[vi] brent round %d: %lld systems, %.2f ms since the previous round's count\n", it,
+                (long long)round_total, (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6);
+        ts0 = ts1;
       }
       if (round_total == 0) break;
       solved += round_total;

@@ -67,6 +67,27 @@ VI_HD vi_bracket vi_chi2_bracket(const double* chi2, int64_t stride, int npts) {
   return out;
 }
 
+// Lazy table: with only chi2[0 .. avail) evaluated, would the walk above read an entry >= avail?  Only the
+// first scale factor can be cut short: if its walk runs to k = 101 without a sign change the table is
+// complete anyway and the later scale factors re-read it.  Same comparisons as vi_chi2_bracket.
+VI_HD bool vi_chi2_walk_needs_more(const double* chi2, int64_t stride, int npts, int avail) {
+  if (avail >= VI_NALPHA) return false;
+  if (avail < 1) return true;
+  const double nu = npts * 0.6;
+  double val0 = 1.0;
+  int k = 0;
+  double val = chi2[0] - nu;
+  if (val < 0.0) return false;
+  while (val0 * val > 0.0) {
+    val0 = val;
+    k = k + 1;
+    if (k >= avail) return true;
+    val = chi2[(int64_t)k * stride] - nu;
+    if (k > 100) break;
+  }
+  return false;
+}
+
 struct vi_brent {
   double xpre, xcur, xblk, fpre, fcur, fblk, spre, scur;
   double root;
