@@ -255,25 +255,33 @@ __device__ __forceinline__ void tape_replay(vi_svec w, const double2* __restrict
 
 // u = Z L^+ Z^T g, one thread per system: forward replay, spectral cut-off (|l| > rcond max|l|: gelsd's
 // rule), backward replay.  Result (scaled back by 2^-ex) returns to B.g; rank to B.rank.
-constexpr int kReplayThreads = 64;
-__global__ void __launch_bounds__(kReplayThreads)
-k_replay(int64_t nsys, SysBuf B, double rcond) {
+// Both thread-per-system kernels are latency-bound dependent chains whose residency is capped by shared
+// memory (n doubles per system here, 2n in k_tql_smem), not by threads.  They therefore run with only L of the
+// 32 lanes of a warp carrying a system ("sparse lanes"): the same number of systems per SM is spread over
+// 32/L times as many warps, which gives the schedulers that many more independent chains to interleave and
+// cuts the divergence between the systems of a warp.  L adapts to the batch (small Brent rounds: L = 1).
+constexpr int kReplayWarps = 8;
+__global__ void __launch_bounds__(kReplayWarps * 32)
+k_replay(int64_t nsys, SysBuf B, double rcond, int L) {
   extern __shared__ __align__(16) double sm[];
-  const int tid = threadIdx.x, n = B.n;
-  const int64_t s = (int64_t)blockIdx.x * kReplayThreads + tid;
-  const bool act = (s < nsys) && (B.st[s] == VI_ST_OK);
-  vi_svec w{sm + tid, kReplayThreads};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = B.n;
+  const int T = kReplayWarps * L;                       // systems per CTA
+  const int slot = warp * L + (lane < L ? lane : 0);
+  const int64_t s = (int64_t)blockIdx.x * T + slot;
+  const bool act = (lane < L) && (s < nsys) && (B.st[s] == VI_ST_OK);
+  vi_svec w{sm + slot, T};
   const int64_t sc = act ? s : 0;
   const int64_t base = ileave(sc, n);
   const int32_t nrot = act ? B.nrot[sc] : 0;
   int32_t nmax = nrot;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
-  if (nmax == 0 && !act) { /* whole warp may still need the divide for systems without rotations */ }
-  for (int i = 0; i < n; ++i) w[i] = act ? B.g[base + (int64_t)i * 32] : 0.0;
+  if (nmax == 0 && !__any_sync(0xffffffffu, act)) return;
+  if (act)
+    for (int i = 0; i < n; ++i) w[i] = B.g[base + (int64_t)i * 32];
   const double2* tcs = reinterpret_cast<const double2*>(B.tcs + sc * (int64_t)B.tapecap * 2);
   const int32_t* tix = B.tix + sc * (int64_t)B.tapecap;
-  tape_replay<+1>(w, tcs, tix, nrot, nmax);
+  if (lane < L) tape_replay<+1>(w, tcs, tix, nrot, nmax);
   if (act) {
     double lmax = 0.0;
     for (int i = 0; i < n; ++i) lmax = fmax(lmax, fabs(B.d[base + (int64_t)i * 32]));
@@ -286,7 +294,7 @@ k_replay(int64_t nsys, SysBuf B, double rcond) {
     }
     B.rank[s] = rank;
   }
-  tape_replay<-1>(w, tcs, tix, nrot, nmax);
+  if (lane < L) tape_replay<-1>(w, tcs, tix, nrot, nmax);
   if (act) {
     const double scl = B.scl[s];
     for (int i = 0; i < n; ++i) B.g[base + (int64_t)i * 32] = w[i] * scl;
@@ -297,13 +305,15 @@ k_replay(int64_t nsys, SysBuf B, double rcond) {
 // sit on the dependency chain of every rotation, so they live in shared memory laid out [i][thread]
 // (a lane always hits its own bank pair whatever i it is at).  Leaves the eigenvalues in B.d, the
 // tape in B.tcs / B.tix; the right-hand side is handled by k_apply.
-__global__ void k_tql_smem(int64_t nsys, SysBuf B) {
+__global__ void k_tql_smem(int64_t nsys, SysBuf B, int L) {
   extern __shared__ __align__(16) double sm[];
-  const int T = blockDim.x, tid = threadIdx.x, n = B.n;
-  const int64_t s = (int64_t)blockIdx.x * T + tid;
-  const bool act = (s < nsys) && (B.st[s] == VI_ST_OK);     // idle lanes still take part in the warp votes
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = B.n;
+  const int T = (blockDim.x >> 5) * L;                  // systems per CTA (sparse lanes, see k_replay)
+  const int slot = warp * L + (lane < L ? lane : 0);
+  const int64_t s = (int64_t)blockIdx.x * T + slot;
+  const bool act = (lane < L) && (s < nsys) && (B.st[s] == VI_ST_OK);     // idle lanes still take part in the warp votes
   const int64_t sc = act ? s : 0;
-  vi_svec d{sm + tid, T}, e{sm + (size_t)n * T + tid, T};
+  vi_svec d{sm + slot, T}, e{sm + (size_t)n * T + slot, T};
   const int64_t base = ileave(sc, n);
   if (act)
     for (int i = 0; i < n; ++i) {
@@ -311,7 +321,7 @@ __global__ void k_tql_smem(int64_t nsys, SysBuf B) {
       e[i] = B.e[base + (int64_t)i * 32];
     }
   int32_t nrot = 0;
-  const int q = vi_tql_values_flat(n, d, e, tape_of(B, sc), &nrot, act);
+  const int q = vi_tql_values_flat(n, d, e, tape_of(B, sc), &nrot, act, L >= 32 ? 8 : (L + 3) / 4);
   if (!act) return;
   if (q != 0) { B.st[s] = VI_ST_NOCONV; return; }
   B.nrot[s] = nrot;
@@ -995,24 +1005,70 @@ int run_tridiag(int64_t cnt, const double* G, const double* y, const double* reg
 // the whole shared memory of an SM, so it serialises with k_tridiag; k_apply and k_chi2 are small and can
 // run next to the tridiagonalisation of the following chunk (pipelined table phase: s_apply != s_ql, the
 // caller orders the two streams with events).
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  if (!e) return dflt;
+  int v = atoi(e);
+  return v >= 1 ? v : dflt;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// lanes per warp that carry a system: as few as keep every system of the batch resident at once, at most Lmax
+int sparse_lanes(int64_t cnt, int sys_per_sm_max, int warps_per_sm, int Lmax) {
+  int64_t per_sm = (cnt + sm_count() - 1) / sm_count();
+  if (per_sm > sys_per_sm_max) per_sm = sys_per_sm_max;
+  int L = (int)((per_sm + warps_per_sm - 1) / warps_per_sm);
+  if (L < 1) L = 1;
+  if (L > Lmax) L = Lmax;
+  return L;
+}
+
 int run_ql(int64_t cnt, const SysBuf& B, cudaStream_t s, bool* split) {
-  const size_t per_thread = (size_t)2 * B.n * sizeof(double);
-  int T = (int)((227 * 1024) / per_thread) / 32 * 32;     // as many as 2n doubles per thread allow (<= 96)
-  if (T > 96) T = 96;
-  *split = T >= 32;
+  const size_t per_sys = (size_t)2 * B.n * sizeof(double);
+  const int fit = (int)((227 * 1024) / per_sys);          // systems whose d, e fit one SM
+  *split = fit >= 32;
   if (cnt <= 0 || !*split) return VI_OK;
-  size_t smem = (size_t)T * per_thread;
+  // one CTA per SM of W warps x L lanes; W*L <= fit
+  static const int Lmax = env_int("VI_TQL_LANES", 16);
+  int W = fit / Lmax;
+  if (W > 24) W = 24;
+  if (W < 1) W = 1;
+  int L = sparse_lanes(cnt, fit, W, Lmax);
+  if (W * L > fit) L = fit / W;
+  if (L < 1) { L = 1; W = fit; }
+  const int T = W * L;
+  size_t smem = (size_t)T * per_sys;
   VI_CUDA(cudaFuncSetAttribute(k_tql_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  VI_KERNEL(VI_K_TQL, s, k_tql_smem<<<blocks(cnt, T), T, smem, s>>>(cnt, B));
+  VI_KERNEL(VI_K_TQL, s, k_tql_smem<<<blocks(cnt, T), W * 32, smem, s>>>(cnt, B, L));
   return VI_OK;
 }
 
 int run_apply(int64_t cnt, const SysBuf& B, double rcond, double* Cout, int32_t* rank_out, cudaStream_t s, bool split) {
   if (cnt <= 0) return VI_OK;
   if (split) {
-    size_t smem1 = (size_t)kReplayThreads * B.n * sizeof(double);
+    const size_t per_sys = (size_t)B.n * sizeof(double);
+    const int fit = (int)((227 * 1024) / per_sys);
+    static const int Lenv = env_int("VI_REPLAY_LANES", 16);
+    int Lmax = Lenv > 32 ? 32 : Lenv;
+    while (Lmax > 1 && (size_t)kReplayWarps * Lmax * per_sys > 227 * 1024) --Lmax;
+    int nb = 1;      // resident CTAs per SM at the full lane count (registers and shared memory both count)
+    VI_CUDA(cudaFuncSetAttribute(k_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)kReplayWarps * Lmax * per_sys)));
+    VI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_replay, kReplayWarps * 32, (size_t)kReplayWarps * Lmax * per_sys));
+    if (nb < 1) nb = 1;
+    const int L = sparse_lanes(cnt, nb * kReplayWarps * Lmax, nb * kReplayWarps, Lmax);
+    (void)fit;
+    size_t smem1 = (size_t)kReplayWarps * L * per_sys;
     VI_CUDA(cudaFuncSetAttribute(k_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-    VI_KERNEL(VI_K_APPLY, s, k_replay<<<blocks(cnt, kReplayThreads), kReplayThreads, smem1, s>>>(cnt, B, rcond));
+    VI_KERNEL(VI_K_APPLY, s, k_replay<<<blocks(cnt, kReplayWarps * L), kReplayWarps * 32, smem1, s>>>(cnt, B, rcond, L));
     size_t smem2 = (size_t)kApplyWarps * B.n * sizeof(double);
     VI_KERNEL(VI_K_APPLY, s, k_apply<<<blocks(cnt, kApplyWarps), kApplyWarps * 32, smem2, s>>>(cnt, B, Cout, rank_out));
   } else {

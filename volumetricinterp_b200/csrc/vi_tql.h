@@ -333,7 +333,8 @@ VI_HD bool vi_ql_negl(double ev, double da, double db) {
   return ev * ev <= (VI_EPS_HALF * VI_EPS_HALF * fabs(da)) * fabs(db) + VI_SAFMIN;
 }
 
-VI_HD int vi_tql_values_flat(int n, vi_svec d, vi_svec e, vi_tape tape, int32_t* nrot_out, bool active) {
+VI_HD int vi_tql_values_flat(int n, vi_svec d, vi_svec e, vi_tape tape, int32_t* nrot_out, bool active,
+                              int iter_batch = 8) {
   int32_t nrot = 0;
   int status = 0;
   int budget = 30 * n;
@@ -354,11 +355,11 @@ VI_HD int vi_tql_values_flat(int n, vi_svec d, vi_svec e, vi_tape tape, int32_t*
   double s = 1.0, c = 1.0, p = 0.0, gg = 0.0, dnext = 0.0;
   for (;;) {
     // The sweep set-up (shift: two divisions and a square root) is batched: lanes that reach it idle until
-    // eight of them are waiting or no lane is rotating, so its ~120 instructions are not paid on every trip.
+    // `iter_batch` of them are waiting or no lane is rotating, so its ~120 instructions are not paid on every trip.
 #if defined(__CUDA_ARCH__)
     const unsigned m_iter = __ballot_sync(0xffffffffu, phase == VI_QL_ITER);
     const unsigned m_rot = __ballot_sync(0xffffffffu, phase == VI_QL_ROT);
-    const bool do_iter = (__popc(m_iter) >= 8) || (m_rot == 0u);
+    const bool do_iter = (__popc(m_iter) >= iter_batch) || (m_rot == 0u);
 #else
     const bool do_iter = true;
 #endif
