@@ -10,6 +10,7 @@
 #include "../volumetricinterp_b200/csrc/vi_tql.h"
 #include "../volumetricinterp_b200/csrc/vi_brent.h"
 #include "../volumetricinterp_b200/csrc/vi_tridiag.h"
+#include "../volumetricinterp_b200/csrc/vi_tridiag_packed.h"
 #include "../volumetricinterp_b200/csrc/vi_nm.h"
 
 extern "C" {
@@ -192,6 +193,38 @@ int h_system_solve(int n, const double* G, const double* y, const double* regs, 
   *rank = vi_spectral_divide(n, {d.data(), 1}, {g.data(), 1}, rcond);
   vi_tape_apply_z({g.data(), 1}, tape, nr);
   for (int i = 0; i < n; ++i) g[i] *= S.sc[0];
+  vi_tri_backtransform(n, V.data(), tau.data(), 1, g.data(), 1);
+  std::memcpy(C, g.data(), n * sizeof(double));
+  return 0;
+}
+
+// Same pipeline with the packed-triangle tridiagonalisation (vi_tridiag_packed.h, kernel k_tridiag_packed):
+// phases run thread by thread, warp reductions restated in the device's order.
+int h_system_solve_packed(int n, const double* G, const double* y, const double* regs, const double* lam, int nreg,
+                          double rcond, double* C, int* rank, double* dd, double* ee, int* bad) {
+  const int nt = vi_trp_threads(n);
+  std::vector<double> mem(vi_trp_doubles(n) + 16), V((size_t)n * n, 0.0);
+  vi_trp_ws W;
+  double* base = mem.data();
+  if (reinterpret_cast<uintptr_t>(base) & 15) base += 1;
+  vi_trp_carve(W, base, n);
+  vi_trp_load(W, G, y, regs, lam, nreg, 0, nt);
+  *bad = W.sc[1] != 0.0;
+  if (*bad) return 0;
+  vi_trp_reduce(W, V.data(), 0, nt);
+  for (int i = 0; i < n; ++i) { dd[i] = W.d[i]; ee[i] = W.e[i]; }
+  std::vector<double> d(W.d, W.d + n), e(W.e, W.e + n), g(W.yv, W.yv + n), tau(W.tau, W.tau + n);
+  int cap = n * n + 64;
+  std::vector<double> tcs(2 * (size_t)cap);
+  std::vector<int32_t> ti(cap);
+  vi_tape tape{{tcs.data(), 2}, {tcs.data() + 1, 2}, {ti.data(), 1}, cap};
+  int32_t nr = 0;
+  int st = vi_tql_values(n, {d.data(), 1}, {e.data(), 1}, tape, &nr);
+  if (st != 0) return st;
+  vi_tape_apply_zt({g.data(), 1}, tape, nr);
+  *rank = vi_spectral_divide(n, {d.data(), 1}, {g.data(), 1}, rcond);
+  vi_tape_apply_z({g.data(), 1}, tape, nr);
+  for (int i = 0; i < n; ++i) g[i] *= W.sc[0];
   vi_tri_backtransform(n, V.data(), tau.data(), 1, g.data(), 1);
   std::memcpy(C, g.data(), n * sizeof(double));
   return 0;

@@ -46,6 +46,9 @@ def test_radbasfun_rows_match_reference_basis(harness):
     assert np.allclose(A, g["A"], rtol=1e-12, atol=1e-300)
 
 
+PACKED = -1
+
+
 def _system(harness, G, y, regs, lam, nt):
     n = G.shape[0]
     Cq = np.zeros(n)
@@ -53,12 +56,17 @@ def _system(harness, G, y, regs, lam, nt):
     dd, ee = np.zeros(n), np.zeros(n)
     regs = np.ascontiguousarray(regs)
     lam = np.ascontiguousarray(lam, dtype=float)
-    st = harness.h_system_solve(n, dptr(G), dptr(y), dptr(regs), dptr(lam), len(lam), nt, C.c_double(EPS),
-                                dptr(Cq), C.byref(rank), dptr(dd), dptr(ee), C.byref(bad))
+    if nt == PACKED:      # the packed-triangle kernel's phases (vi_tridiag_packed.h), thread count fixed by n
+        st = harness.h_system_solve_packed(n, dptr(G), dptr(y), dptr(regs), dptr(lam), len(lam), C.c_double(EPS),
+                                           dptr(Cq), C.byref(rank), dptr(dd), dptr(ee), C.byref(bad))
+    else:
+        st = harness.h_system_solve(n, dptr(G), dptr(y), dptr(regs), dptr(lam), len(lam), nt, C.c_double(EPS),
+                                    dptr(Cq), C.byref(rank), dptr(dd), dptr(ee), C.byref(bad))
     return st, bad.value, rank.value, Cq, dd, ee
 
 
-@pytest.mark.parametrize("name,nt", [("lo8", 8), ("lo8", 32), ("lo12", 48), ("lo12_two", 12)])
+@pytest.mark.parametrize("name,nt", [("lo8", 8), ("lo8", 32), ("lo12", 48), ("lo12_two", 12),
+                                     ("lo8", PACKED), ("lo12", PACKED), ("lo12_two", PACKED)])
 def test_system_pipeline_matches_lstsq_low_order(harness, name, nt):
     """tridiagonalise (CTA phases run thread by thread) + tape QL + truncated solve + back-transform
     == scipy.linalg.lstsq (interpolate.py:462) on full-rank systems."""
@@ -84,7 +92,8 @@ def test_system_pipeline_matches_lstsq_low_order(harness, name, nt):
             assert np.max(np.abs(Cq - ref)) <= 50 * EPS * cond * np.abs(ref).max()
 
 
-def test_system_pipeline_rank_deficient(harness):
+@pytest.mark.parametrize("nt", [576, PACKED])
+def test_system_pipeline_rank_deficient(harness, nt):
     """N = 144: numerical rank and fitted densities agree with lstsq where the solve is well posed."""
     g = load_golden("c1_144")
     ok = np.isfinite(g["value"][0])
@@ -95,11 +104,37 @@ def test_system_pipeline_rank_deficient(harness):
         ref = scipy.linalg.lstsq(X, y)[0]
         s = np.linalg.svd(X, compute_uv=False)
         st, bad, rank, Cq, _, _ = _system(harness, np.ascontiguousarray(G), np.ascontiguousarray(y),
-                                          np.stack(g["regs"]), [10.0 ** alpha], 576)
+                                          np.stack(g["regs"]), [10.0 ** alpha], nt)
         assert st == 0 and bad == 0
         assert abs(rank - int((s > EPS * s[0]).sum())) <= 1
         dens, dref = A @ Cq, A @ ref
         assert np.max(np.abs(dens - dref)) <= 1e-5 * np.abs(dref).max()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 9, 16, 27, 40, 65, 100, 144, 150])
+def test_packed_tridiagonalisation_random(harness, n):
+    """Packed-triangle Householder reduction: T has the spectrum of X, the solve matches numpy, for orders
+    around every octet / warp-assignment boundary."""
+    rng = np.random.default_rng(100 + n)
+    M = rng.standard_normal((n, n))
+    X = M @ M.T + n * np.eye(n)
+    y = rng.standard_normal(n)
+    st, bad, rank, Cq, dd, ee = _system(harness, np.ascontiguousarray(X), y, np.zeros((1, n, n)), [0.0], PACKED)
+    assert bad == 0
+    T = np.diag(dd) + np.diag(ee[:-1], 1) + np.diag(ee[:-1], -1)
+    ev = np.linalg.eigvalsh(X)
+    evT = np.linalg.eigvalsh(T)
+    scl = np.abs(ev).max() / np.abs(evT).max()
+    assert np.allclose(evT * scl, ev, rtol=0, atol=1e-13 * np.abs(ev).max())
+    if st == 0:      # (st == 2: the QL rotation tape of n^2 + 64 entries overflowed; not the reduction's business)
+        assert rank == n
+        ref = np.linalg.solve(X, y)
+        assert np.max(np.abs(Cq - ref)) <= 1e-12 * np.abs(ref).max()
+    # same system through the full-square phases: same tridiagonal form up to rounding
+    st2, bad2, rank2, Cq2, dd2, ee2 = _system(harness, np.ascontiguousarray(X), y, np.zeros((1, n, n)), [0.0],
+                                              max(32, (n + 31) // 32 * 32))
+    assert np.allclose(dd, dd2, rtol=0, atol=1e-12 * np.abs(dd2).max())
+    assert np.allclose(np.abs(ee), np.abs(ee2), rtol=0, atol=1e-12 * np.abs(dd2).max())
 
 
 def test_nonfinite_system_is_flagged(harness):

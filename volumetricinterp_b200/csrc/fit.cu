@@ -30,6 +30,7 @@
 #include "vi_nm.h"
 #include "vi_tql.h"
 #include "vi_tridiag.h"
+#include "vi_tridiag_packed.h"
 
 namespace {
 
@@ -206,6 +207,40 @@ k_tridiag(const double* __restrict__ G, const double* __restrict__ y, const doub
       B.tau[base + (int64_t)i * 32] = S.tau[i];
     }
   if (tid == 0) { B.scl[s] = S.sc[0]; B.st[s] = bad ? VI_ST_NONFINITE : VI_ST_OK; }
+}
+
+// Packed-triangle variant (vi_tridiag_packed.h): 87.5 KB of shared memory at n = 144 -> two CTAs per SM.
+__global__ void __launch_bounds__(352, 2)
+k_tridiag_packed(const double* __restrict__ G, const double* __restrict__ y, const double* __restrict__ regs, SysBuf B,
+                 Downdate dd) {
+  extern __shared__ __align__(16) double sm[];
+  const int64_t s = blockIdx.x;
+  const int r = B.rec[s];
+  if (r < 0) { if (threadIdx.x == 0) B.st[s] = kSkip; return; }
+  const int n = B.n, nt = blockDim.x, tid = threadIdx.x;
+  vi_trp_ws W;
+  vi_trp_carve(W, sm, n);
+  const double* arow = nullptr;
+  double wj = 0.0, bj = 0.0;
+  if (dd.A != nullptr) {
+    const int j = B.gate[s];
+    arow = dd.A + (int64_t)j * n;
+    wj = dd.Wm[(int64_t)r * dd.P + j];
+    bj = dd.bm[(int64_t)r * dd.P + j];
+  }
+  vi_trp_load(W, G + (int64_t)r * n * n, y + (int64_t)r * n, regs, B.lam + s * (B.nreg > 0 ? B.nreg : 1), B.nreg, tid, nt,
+              arow, wj, bj);
+  const bool bad = W.sc[1] != 0.0;
+  if (!bad) vi_trp_reduce(W, B.V + s * (int64_t)n * n, tid, nt);
+  const int64_t base = ileave(s, n);
+  if (!bad)
+    for (int i = tid; i < n; i += nt) {
+      B.d[base + (int64_t)i * 32] = W.d[i];
+      B.e[base + (int64_t)i * 32] = W.e[i];
+      B.g[base + (int64_t)i * 32] = W.yv[i];
+      B.tau[base + (int64_t)i * 32] = W.tau[i];
+    }
+  if (tid == 0) { B.scl[s] = W.sc[0]; B.st[s] = bad ? VI_ST_NONFINITE : VI_ST_OK; }
 }
 
 __device__ __forceinline__ vi_tape tape_of(const SysBuf& B, int64_t s) {
@@ -991,6 +1026,17 @@ inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / p
 int run_tridiag(int64_t cnt, const double* G, const double* y, const double* regs, const SysBuf& B, cudaStream_t s,
                 Downdate dd = Downdate{nullptr, nullptr, nullptr, 0}) {
   if (cnt <= 0) return VI_OK;
+  {
+    // packed form whenever its working set fits one CTA (two CTAs per SM up to n = 144)
+    static const bool force_full = getenv("VI_TRIDIAG_FULL") != nullptr;
+    const size_t smem = (size_t)vi_trp_doubles(B.n) * sizeof(double);
+    const int nt = vi_trp_threads(B.n);
+    if (!force_full && smem <= 227 * 1024 && nt <= 352) {
+      VI_CUDA(cudaFuncSetAttribute(k_tridiag_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VI_KERNEL(VI_K_TRIDIAG, s, k_tridiag_packed<<<(unsigned)cnt, nt, smem, s>>>(G, y, regs, B, dd));
+      return VI_OK;
+    }
+  }
   if (B.use_gx) {
     VI_CUDA(cudaFuncSetAttribute(k_tridiag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B.smem));
     VI_KERNEL(VI_K_TRIDIAG, s, k_tridiag<true><<<(unsigned)cnt, B.nt, B.smem, s>>>(G, y, regs, B, dd));

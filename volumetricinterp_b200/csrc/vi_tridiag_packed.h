@@ -1,0 +1,424 @@
+// Householder tridiagonalisation of one symmetric system by one CTA, PACKED form (kernel K3a).
+//
+// Same role and same algorithm as vi_tridiag.h (LAPACK dsytd2 convention, the rank-2 update of reflector
+// k-1 deferred into the pass that forms the mat-vec for reflector k; reference call being replaced:
+// scipy.linalg.lstsq at interpolate.py:462).  What changes is the storage and the work split:
+//
+//   * only the lower triangle is kept, column-major by OCTETS of columns: column c stores the rows
+//     8*floor(c/8) .. npad-1 contiguously (npad = n rounded up to 8).  At n = 144 that is 87.5 KB instead
+//     of 166 KB, so TWO systems are resident per SM and one CTA's latency-bound vector section overlaps the
+//     other's matrix pass;
+//   * every stored element is touched once per Householder step by one thread, which applies the deferred
+//     update and feeds BOTH the column sum (X v)_c and the row sum (X v)_i it belongs to (half the
+//     shared-memory traffic and half the FMAs of the full-square form);
+//   * a thread works on tiles of 2 rows x 8 columns (the 2 rows are one 128-bit access per column), a warp
+//     owns one or two octets and walks their row pairs 32 at a time; the 8 column sums of an octet are
+//     reduced across the warp once per step (recursive halving, fixed order), the 2 row sums of a tile go
+//     to a per-tile slot that the vector section adds up.
+//
+// As in vi_tridiag.h the algorithm is a sequence of phases separated by barriers, and the test-only CPU
+// harness (tests/cpu_harness.cpp) executes the same phase bodies thread by thread, warp reductions
+// included in the same order.
+#pragma once
+#include "vi_tridiag.h"
+
+struct vi_trp_ws {
+  double* X;      // packed lower triangle, vi_trp_xdoubles(n) doubles
+  double* Pr;     // 2 x ntiles: row sums of every tile (rows 2 ip, 2 ip + 1)
+  double* v;      // npad  deferred reflector k-1
+  double* w;      // npad  its companion vector
+  double* vn;     // npad  reflector k
+  double* pcol;   // npad  column sums
+  double* p;      // n
+  double* yv;     // n  right-hand side being transformed (ends as g = Q^T y)
+  double* col;    // n  pivot column, carrying every earlier update
+  double* red1;   // max(n, nt)
+  double* red2;   // n
+  double* d;      // n
+  double* e;      // n
+  double* tau;    // n
+  double* sc;     // 8 scalars: [0] scale 2^-ex, [1] non-finite flag
+  int n, npad, noct, nwarp;
+};
+
+VI_HD int vi_trp_npad(int n) { return (n + 7) & ~7; }
+VI_HD int vi_trp_noct(int n) { return vi_trp_npad(n) >> 3; }
+// warps of the CTA: the two longest octets get a warp of their own, the others are paired (long, short)
+VI_HD int vi_trp_nwarp(int n) { const int o = vi_trp_noct(n); const int w = (o + 2) / 2; return w > o ? o : w; }
+// doubles stored before octet q: sum_{t<q} 8 (npad - 8 t)
+VI_HD int vi_trp_octoff(int npad, int q) { return 8 * q * npad - 32 * q * (q - 1); }
+VI_HD int vi_trp_xdoubles(int n) { const int np = vi_trp_npad(n); return vi_trp_octoff(np, np >> 3); }
+// element (i, c) with i >= 8 floor(c/8)
+VI_HD int vi_trp_idx(int npad, int i, int c) {
+  const int q = c >> 3;
+  return vi_trp_octoff(npad, q) + (c - 8 * q) * (npad - 8 * q) + (i - 8 * q);
+}
+// tiles (row pair ip >= 4 q, octet q): slot = tileoff(q) + ip - 4 q
+VI_HD int vi_trp_tileoff(int npad, int q) { return q * (npad >> 1) - 2 * q * (q - 1); }
+VI_HD int vi_trp_ntiles(int n) { const int np = vi_trp_npad(n); return vi_trp_tileoff(np, np >> 3); }
+VI_HD int vi_trp_threads(int n) { return 32 * vi_trp_nwarp(n); }
+// doubles of CTA-shared storage, X included
+VI_HD int vi_trp_doubles(int n) {
+  const int np = vi_trp_npad(n), nt = vi_trp_threads(n);
+  return vi_trp_xdoubles(n) + 2 * vi_trp_ntiles(n) + 4 * np + 7 * n + (nt > n ? nt : n) + 8 + 8;
+}
+
+VI_HD void vi_trp_carve(vi_trp_ws& W, double* mem, int n) {
+  const int np = vi_trp_npad(n), nt = vi_trp_threads(n);
+  W.n = n; W.npad = np; W.noct = np >> 3; W.nwarp = vi_trp_nwarp(n);
+  W.X = mem; mem += vi_trp_xdoubles(n);          // even number of doubles: everything below stays 16-byte aligned
+  W.Pr = mem; mem += 2 * vi_trp_ntiles(n);
+  W.v = mem; mem += np;
+  W.w = mem; mem += np;
+  W.vn = mem; mem += np;
+  W.pcol = mem; mem += np;
+  W.p = mem; mem += n;
+  W.yv = mem; mem += n;
+  W.col = mem; mem += n;
+  W.red2 = mem; mem += n;
+  W.d = mem; mem += n;
+  W.e = mem; mem += n;
+  W.tau = mem; mem += n;
+  W.sc = mem; mem += 8;
+  W.red1 = mem; mem += (nt > n ? nt : n);
+}
+
+// X <- scl * (0.5 (G + G^T) + sum_r lam[r] Reg_r) (lower triangle, packed), scl = 2^-exponent(max|X|);
+// yv <- y; col <- X[:,0]; v, w, vn <- 0.  Same arithmetic per element as vi_tri_load, including the optional
+// rank-one downdate of the GCV objective (interpolate.py:332-349).
+VI_HD void vi_trp_load(const vi_trp_ws& W, const double* G, const double* y, const double* regs, const double* lam,
+                       int nreg, int tid, int nt, const double* arow = nullptr, double wj = 0.0, double bj = 0.0) {
+  (void)tid;
+  const int n = W.n, npad = W.npad;
+  VI_PHASE(
+    double mx = 0.0; double bad = 0.0;
+    const int warp = tid >> 5; const int lane = tid & 31; const int nwarp = nt >> 5;
+    // a warp takes 4 columns of one octet per trip, lanes walk the rows: shared-memory stores are
+    // conflict-free (consecutive rows), G[c][i] is read coalesced, G[i][c] strided (both through L2)
+    for (int cb = 4 * warp; cb < npad; cb += 4 * nwarp) {
+      const int r0 = cb & ~7;
+      for (int i = r0 + lane; i < npad; i += 32) {
+        double x[4];
+        VI_UNROLL4
+        for (int u = 0; u < 4; ++u) {
+          const int c = cb + u;
+          const bool in = (i < n) && (c < n);
+          x[u] = in ? 0.5 * (G[(int64_t)i * n + c] + G[(int64_t)c * n + i]) : 0.0;
+        }
+        for (int r = 0; r < nreg; ++r) {
+          const double l = lam[r];
+          if (l != 0.0) {
+            VI_UNROLL4
+            for (int u = 0; u < 4; ++u) {
+              const int c = cb + u;
+              if ((i < n) && (c < n)) x[u] = fma(l, regs[((int64_t)r * n + i) * n + c], x[u]);
+            }
+          }
+        }
+        VI_UNROLL4
+        for (int u = 0; u < 4; ++u) {
+          const int c = cb + u;
+          double xv = x[u];
+          if (arow && (i < n) && (c < n)) xv = xv - wj * (arow[i] * arow[c]);
+          if (!(fabs(xv) <= 1.79769313486231570e308)) bad = 1.0;
+          mx = fmax(mx, fabs(xv));
+          W.X[vi_trp_idx(npad, i, c)] = xv;
+        }
+      }
+    }
+    for (int i = tid; i < n; i += nt) {
+      double t = y[i];
+      if (arow) t = t - (wj * bj) * arow[i];
+      if (!(fabs(t) <= 1.79769313486231570e308)) bad = 1.0;
+      W.yv[i] = t;
+      W.p[i] = 0.0;
+    }
+    for (int i = tid; i < npad; i += nt) { W.v[i] = 0.0; W.w[i] = 0.0; W.vn[i] = 0.0; W.pcol[i] = 0.0; }
+    W.red1[tid] = (bad != 0.0) ? -1.0 : mx;
+  )
+  VI_PHASE(
+    if (tid == 0) {
+      double mx = 0.0; double bad = 0.0;
+      for (int t = 0; t < nt; ++t) { double r = W.red1[t]; if (r < 0.0) bad = 1.0; else mx = fmax(mx, r); }
+      int ex = 0;
+      double scl = 1.0;
+      if (bad == 0.0 && mx > 0.0) { frexp(mx, &ex); scl = ldexp(1.0, -ex); }
+      W.sc[0] = scl; W.sc[1] = bad;
+    }
+  )
+  VI_PHASE(
+    const double scl = W.sc[0];
+    const int tot = vi_trp_xdoubles(n);
+    if (scl != 1.0)
+      for (int idx = tid; idx < tot; idx += nt) W.X[idx] *= scl;
+  )
+  VI_PHASE(
+    for (int i = tid; i < n; i += nt) W.col[i] = W.X[i];       // column 0 starts the packed array
+  )
+}
+
+// Reflector k from the pivot column W.col: d[k], e[k], tau[k], vn and row k of V (vi_tri_reflector with the
+// vectors in separate arrays).  vn[k] is cleared: the tile pass reads vn for the odd row k when k + 1 is odd.
+VI_HD void vi_trp_reflector(const vi_trp_ws& W, int k, double* V, int tid) {
+  const int n = W.n, lo1 = k + 1;
+  double tau = 0.0; double beta = 0.0; double scale = 0.0;
+  const bool last = (k == n - 2);
+  if (!last) {
+    const double xn2 = vi_warp_sum(k + 2, n, tid & 31, [&](int i) { double x = W.col[i]; return x * x; });
+    const double alpha = W.col[k + 1];
+    beta = alpha;
+    if (xn2 != 0.0) {
+      const double r2 = alpha * alpha + xn2;
+#if defined(__CUDA_ARCH__)
+      const double ri = rsqrt(r2);
+#else
+      const double ri = 1.0 / sqrt(r2);
+#endif
+      const double nrm = r2 * ri;
+      beta = -copysign(nrm, alpha);
+      tau = 1.0 + fabs(alpha) * ri;
+      scale = copysign(1.0, alpha) / (fabs(alpha) + nrm);
+    }
+  } else {
+    beta = W.col[n - 1];
+  }
+  if (tid >= lo1 && tid < n) {
+    double vv = 0.0;
+    if (tau != 0.0) vv = (tid == lo1) ? 1.0 : W.col[tid] * scale;
+    W.vn[tid] = vv;
+    if (!last) V[(int64_t)k * n + tid] = (tau == 0.0 && tid == lo1) ? 1.0 : vv;
+  }
+  if (tid == k) W.vn[k] = 0.0;
+  if (tid == 0) { W.d[k] = W.col[k]; W.e[k] = beta; W.tau[k] = tau; }
+}
+
+// One tile: rows (2 ip, 2 ip + 1) x the 8 columns of octet q.  xb points at element (row 0, column 8 q) of a
+// virtual column-major block of leading dimension len = npad - 8 q, so element (i, 8 q + j) is xb[j len + i].
+// Applies x <- x - v_i w_c - w_i v_c, accumulates acc[j] += x vn_i (column sums) and returns the two row
+// sums sum_c x vn_c.  In the tiles that straddle the diagonal an element counts once for its column if
+// i >= c and once for its row if i > c; stored positions above the diagonal are dead.
+VI_HD void vi_trp_tile(double* xb, int len, const vi_trp_ws& W, int q, int ip, int lo1, double* acc, double* pr) {
+  const int i0 = 2 * ip;
+  const vi_d2 v01 = *reinterpret_cast<const vi_d2*>(W.v + i0);
+  const vi_d2 w01 = *reinterpret_cast<const vi_d2*>(W.w + i0);
+  const vi_d2 n01 = *reinterpret_cast<const vi_d2*>(W.vn + i0);
+  double pr0 = 0.0, pr1 = 0.0;
+  const bool diag = ip < 4 * q + 4;
+  const double* vq = W.v + 8 * q;
+  const double* wq = W.w + 8 * q;
+  const double* nq = W.vn + 8 * q;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < 8; ++j) {
+    const int c = 8 * q + j;
+    if (c < lo1) continue;                       // finished column (uniform over the warp)
+    const double vc = vq[j], wc = wq[j], nc = nq[j];
+    vi_d2* xp = reinterpret_cast<vi_d2*>(xb + j * len + i0);
+    vi_d2 x = *xp;
+    x.x = x.x - v01.x * wc; x.x = x.x - w01.x * vc;
+    x.y = x.y - v01.y * wc; x.y = x.y - w01.y * vc;
+    *xp = x;
+    if (!diag) {
+      acc[j] += x.x * n01.x; acc[j] += x.y * n01.y;
+      pr0 += x.x * nc; pr1 += x.y * nc;
+    } else {
+      if (i0 >= c) acc[j] += x.x * n01.x;
+      if (i0 + 1 >= c) acc[j] += x.y * n01.y;
+      if (i0 > c) pr0 += x.x * nc;
+      if (i0 + 1 > c) pr1 += x.y * nc;
+    }
+  }
+  pr[0] = pr0; pr[1] = pr1;
+}
+
+// The octets of warp `warp`: slot 0 is octet `warp`; slot 1 (warps >= nsingle only) is octet warp + noct - nwarp.
+VI_HD int vi_trp_octet_of(const vi_trp_ws& W, int warp, int slot) {
+  if (slot == 0) return warp < W.noct ? warp : -1;
+  const int nsingle = 2 * W.nwarp - W.noct;
+  return (warp >= nsingle) ? warp + W.noct - W.nwarp : -1;
+}
+
+// lane -> which of the 8 column sums it ends up holding after vi_trp_reduce8 (lanes with lane % 4 == 0 store)
+VI_HD int vi_trp_reduce_slot(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
+
+#if defined(__CUDA_ARCH__)
+// sum over the 32 lanes of each of 8 values by recursive halving: 4 + 2 + 1 exchanges, then two butterfly
+// steps on the single value left (fixed order -> reproducible)
+__device__ __forceinline__ double vi_trp_reduce8(const double* acc, int lane) {
+  double a4[4], a2[2], a1;
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const double send = hi ? acc[t] : acc[t + 4];
+      const double keep = hi ? acc[t + 4] : acc[t];
+      a4[t] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const double send = hi ? a4[t] : a4[t + 2];
+      const double keep = hi ? a4[t + 2] : a4[t];
+      a2[t] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool hi = lane & 4;
+    const double send = hi ? a2[0] : a2[1];
+    const double keep = hi ? a2[1] : a2[0];
+    a1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  a1 = a1 + __shfl_xor_sync(0xffffffffu, a1, 2);
+  a1 = a1 + __shfl_xor_sync(0xffffffffu, a1, 1);
+  return a1;
+}
+#else
+// host restatement: acc[lane][8] -> out[lane], same exchanges in the same order
+inline void vi_trp_reduce8_host(const double (*acc)[8], double* out) {
+  double a4[32][4], a2[32][2], a1[32], t1[32];
+  for (int l = 0; l < 32; ++l) {
+    const bool hi = l & 16;
+    for (int t = 0; t < 4; ++t) {
+      const double keep = hi ? acc[l][t + 4] : acc[l][t];
+      const double recv = (l ^ 16) & 16 ? acc[l ^ 16][t] : acc[l ^ 16][t + 4];
+      a4[l][t] = keep + recv;
+    }
+  }
+  for (int l = 0; l < 32; ++l) {
+    const bool hi = l & 8;
+    for (int t = 0; t < 2; ++t) {
+      const double keep = hi ? a4[l][t + 2] : a4[l][t];
+      const double recv = (l ^ 8) & 8 ? a4[l ^ 8][t] : a4[l ^ 8][t + 2];
+      a2[l][t] = keep + recv;
+    }
+  }
+  for (int l = 0; l < 32; ++l) {
+    const bool hi = l & 4;
+    const double keep = hi ? a2[l][1] : a2[l][0];
+    const double recv = (l ^ 4) & 4 ? a2[l ^ 4][0] : a2[l ^ 4][1];
+    a1[l] = keep + recv;
+  }
+  for (int l = 0; l < 32; ++l) t1[l] = a1[l] + a1[l ^ 2];
+  for (int l = 0; l < 32; ++l) out[l] = t1[l] + t1[l ^ 1];
+}
+#endif
+
+// Matrix pass of step k (lo1 = k + 1) for one warp: its octets, 32 row pairs per trip.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void vi_trp_pass(const vi_trp_ws& W, int lo1, int warp, int lane) {
+  const int npad = W.npad, nrp = npad >> 1;
+#pragma unroll 1
+  for (int slot = 0; slot < 2; ++slot) {
+    const int q = vi_trp_octet_of(W, warp, slot);
+    if (q < 0 || 8 * q + 7 < lo1) continue;
+    const int len = npad - 8 * q;
+    double* xb = W.X + vi_trp_octoff(npad, q) - 8 * q;
+    double* prq = W.Pr + 2 * (vi_trp_tileoff(npad, q) - 4 * q);
+    const int ip0 = (4 * q > (lo1 >> 1)) ? 4 * q : (lo1 >> 1);
+    double acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+#pragma unroll 1
+    for (int ip = ip0 + lane; ip < nrp; ip += 32) {
+      double pr[2];
+      vi_trp_tile(xb, len, W, q, ip, lo1, acc, pr);
+      vi_d2 o; o.x = pr[0]; o.y = pr[1];
+      *reinterpret_cast<vi_d2*>(prq + 2 * ip) = o;
+    }
+    const double tot = vi_trp_reduce8(acc, lane);
+    if ((lane & 3) == 0) W.pcol[8 * q + vi_trp_reduce_slot(lane)] = tot;
+  }
+}
+#else
+inline void vi_trp_pass_host(const vi_trp_ws& W, int lo1, int warp) {
+  const int npad = W.npad, nrp = npad >> 1;
+  for (int slot = 0; slot < 2; ++slot) {
+    const int q = vi_trp_octet_of(W, warp, slot);
+    if (q < 0 || 8 * q + 7 < lo1) continue;
+    const int len = npad - 8 * q;
+    double* xb = W.X + vi_trp_octoff(npad, q) - 8 * q;
+    double* prq = W.Pr + 2 * (vi_trp_tileoff(npad, q) - 4 * q);
+    const int ip0 = (4 * q > (lo1 >> 1)) ? 4 * q : (lo1 >> 1);
+    double acc[32][8], tot[32];
+    for (int lane = 0; lane < 32; ++lane) {
+      for (int j = 0; j < 8; ++j) acc[lane][j] = 0.0;
+      for (int ip = ip0 + lane; ip < nrp; ip += 32) {
+        double pr[2];
+        vi_trp_tile(xb, len, W, q, ip, lo1, acc[lane], pr);
+        prq[2 * ip] = pr[0]; prq[2 * ip + 1] = pr[1];
+      }
+    }
+    vi_trp_reduce8_host(acc, tot);
+    for (int lane = 0; lane < 32; lane += 4) W.pcol[8 * q + vi_trp_reduce_slot(lane)] = tot[lane];
+  }
+}
+#endif
+
+// Reduction proper.  Per Householder step: matrix pass (all warps) -> CTA barrier -> vector section on the
+// ceil(n/32) warps that own a vector element (named barriers between its three sub-steps) -> CTA barrier.
+// After the call W.d, W.e, W.tau, W.yv (= Q^T y) are final; V row k holds reflector k in columns k+1..n-1.
+VI_HD void vi_trp_reduce(const vi_trp_ws& W, double* V, int tid, int nt) {
+  (void)tid;
+  const int n = W.n, npad = W.npad;
+  const int nsub = (n + 31) & ~31;
+  if (n >= 2) {
+    VI_PHASE( if (tid < nsub) vi_trp_reflector(W, 0, V, tid); )
+  }
+  for (int k = 0; k + 1 < n; ++k) {
+    const int lo1 = k + 1;
+    const double tau = W.tau[k];
+    // ---- B: deferred update of reflector k-1 fused with both halves of the symmetric mat-vec -------
+#if defined(__CUDA_ARCH__)
+    vi_trp_pass(W, lo1, tid >> 5, tid & 31);
+    __syncthreads();
+#else
+    for (int warp = 0; warp < (nt >> 5); ++warp) vi_trp_pass_host(W, lo1, warp);
+#endif
+    // ---- C1: p = tau * (column sum + row sums of the tiles left of the diagonal), products ----------
+    VI_SUBPHASE(nsub,
+      if (tid >= lo1 && tid < n) {
+        double p = W.pcol[tid];
+        const int ip = tid >> 1;
+        const int qhi = tid >> 3;
+        for (int q = lo1 >> 3; q <= qhi; ++q) p += W.Pr[2 * (vi_trp_tileoff(npad, q) + ip - 4 * q) + (tid & 1)];
+        p = tau * p;
+        const double vn = W.vn[tid];
+        W.p[tid] = p;
+        W.red1[tid] = p * vn;
+        W.red2[tid] = vn * W.yv[tid];
+      }
+    )
+    // ---- C2: dot products, w, rhs, next pivot column, rotate (v, w) <- (vn, wn) ----------------------
+    VI_SUBPHASE(nsub,
+      {
+        const double dot = vi_warp_sum(lo1, n, tid & 31, [&](int i) { return W.red1[i]; });
+        const double dot2 = vi_warp_sum(lo1, n, tid & 31, [&](int i) { return W.red2[i]; });
+        if (tid >= lo1 && tid < n) {
+          const double a2 = -0.5 * tau * dot;
+          const double vn = W.vn[tid];
+          const double wn = W.p[tid] + a2 * vn;
+          W.yv[tid] = W.yv[tid] - (tau * dot2) * vn;
+          const double vlo = W.vn[lo1];
+          const double wlo = W.p[lo1] + a2 * vlo;
+          W.col[tid] = (W.X[vi_trp_idx(npad, tid, lo1)] - vn * wlo) - wn * vlo;
+          W.v[tid] = vn;
+          W.w[tid] = wn;
+        }
+      }
+    )
+    // ---- C3: reflector k + 1 ---------------------------------------------------------------------------
+    VI_PHASE(
+      if (tid < nsub && k + 2 < n) vi_trp_reflector(W, k + 1, V, tid);
+    )
+  }
+  VI_PHASE(
+    if (tid == 0) {
+      if (n == 1) W.d[0] = W.X[0];
+      else W.d[n - 1] = W.col[n - 1];
+      W.e[n - 1] = 0.0; W.tau[n - 1] = 0.0;
+    }
+  )
+}
