@@ -67,7 +67,7 @@ int h_tql_values_solve(int n, const double* d0, const double* e0, const double* 
                        double* w, double* lam, int* rank, int* nrot) {
   std::vector<double> d(d0, d0 + n), e(n, 0.0), g(g0, g0 + n);
   for (int i = 0; i + 1 < n; ++i) e[i] = e0[i];
-  int cap = n * n + 64;
+  int cap = 2 * n * n + 64;
   std::vector<double> tcs(2 * (size_t)cap);
   std::vector<int32_t> ti(cap);
   vi_tape tape{{tcs.data(), 2}, {tcs.data() + 1, 2}, {ti.data(), 1}, cap};
@@ -87,7 +87,7 @@ int h_tql_values_solve(int n, const double* d0, const double* e0, const double* 
 int h_tql_flat_identical(int n, const double* d0, const double* e0, int* nrot_out) {
   std::vector<double> d1(d0, d0 + n), e1(n, 0.0), d2(d0, d0 + n), e2(n, 0.0);
   for (int i = 0; i + 1 < n; ++i) { e1[i] = e0[i]; e2[i] = e0[i]; }
-  int cap = n * n + 64;
+  int cap = 2 * n * n + 64;
   std::vector<double> t1(2 * (size_t)cap, 0.0), t2(2 * (size_t)cap, 0.0);
   std::vector<int32_t> i1(cap, 0), i2(cap, 0);
   vi_tape ta{{t1.data(), 2}, {t1.data() + 1, 2}, {i1.data(), 1}, cap};
@@ -182,7 +182,7 @@ int h_system_solve(int n, const double* G, const double* y, const double* regs, 
   vi_tri_reduce(S, n, V.data(), 0, nt);
   for (int i = 0; i < n; ++i) { dd[i] = S.d[i]; ee[i] = S.e[i]; }
   std::vector<double> d(S.d, S.d + n), e(S.e, S.e + n), g(S.yv, S.yv + n), tau(S.tau, S.tau + n);
-  int cap = n * n + 64;
+  int cap = 2 * n * n + 64;
   std::vector<double> tcs(2 * (size_t)cap);
   std::vector<int32_t> ti(cap);
   vi_tape tape{{tcs.data(), 2}, {tcs.data() + 1, 2}, {ti.data(), 1}, cap};
@@ -214,7 +214,7 @@ int h_system_solve_packed(int n, const double* G, const double* y, const double*
   vi_trp_reduce(W, V.data(), 0, nt);
   for (int i = 0; i < n; ++i) { dd[i] = W.d[i]; ee[i] = W.e[i]; }
   std::vector<double> d(W.d, W.d + n), e(W.e, W.e + n), g(W.yv, W.yv + n), tau(W.tau, W.tau + n);
-  int cap = n * n + 64;
+  int cap = 2 * n * n + 64;
   std::vector<double> tcs(2 * (size_t)cap);
   std::vector<int32_t> ti(cap);
   vi_tape tape{{tcs.data(), 2}, {tcs.data() + 1, 2}, {ti.data(), 1}, cap};

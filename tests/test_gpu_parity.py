@@ -121,6 +121,27 @@ def test_solver_matches_lstsq_given_identical_system(cuda, name):
         assert np.max(np.abs(Cf[i] - ref)) <= 50 * EPS * (s[0] / s[-1]) * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("n", [1, 2, 5, 8, 9, 16, 27, 40, 64, 100, 144, 150])
+def test_solver_generic_full_rank_systems(cuda, n):
+    """Well-conditioned dense systems of every order around the octet / warp boundaries of the packed
+    tridiagonalisation: QL needs ~1.4 n^2 rotations there (the fits' graded spectra need far fewer), the
+    answer must be numpy's to rounding."""
+    rng = np.random.default_rng(300 + n)
+    S = 5
+    Gs, ys = [], []
+    for _ in range(S):
+        M = rng.standard_normal((n, n))
+        Gs.append(M @ M.T + n * np.eye(n)); ys.append(rng.standard_normal(n))
+    regs = np.zeros((1, n, n)); regs[0] = np.eye(n)
+    lam = np.full((S, 1), 0.5)
+    Cf, rank, status = _solve(cuda, np.array(Gs), np.array(ys), regs, lam)
+    assert (status == 0).all() and (rank == n).all()
+    for i in range(S):
+        X = Gs[i] + 0.5 * np.eye(n)
+        ref = np.linalg.solve(X, ys[i])
+        assert np.max(np.abs(Cf[i] - ref)) <= 1e-12 * np.linalg.cond(X) * np.abs(ref).max()
+
+
 def test_solver_rank_deficient_and_bad_systems(cuda):
     g = load_golden("c1_144")
     ok = np.isfinite(g["value"][0])

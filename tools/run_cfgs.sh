@@ -1,7 +1,6 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_packed.log 2>&1; echo pytest rc=$?; tail -4 gpurun_out/pytest_packed.log
-for cfg in packed full; do
-if [ $cfg = full ]; then export VI_TRIDIAG_FULL=1; fi
-python bench.py --steps 1 --warmup 1 --e2e-steps 1 --no-cpu-baseline > gpurun_out/bench_$cfg.log 2>gpurun_out/bench_$cfg.err
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_packed2.log 2>&1; echo pytest rc=$?; tail -3 gpurun_out/pytest_packed2.log
+for cfg in packed; do
+python bench.py --steps 2 --warmup 1 --e2e-steps 1 --no-cpu-baseline > gpurun_out/bench_$cfg.log 2>gpurun_out/bench_$cfg.err
 python - <<PY
 import json
 for l in open("gpurun_out/bench_$cfg.log"):

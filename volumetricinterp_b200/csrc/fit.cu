@@ -77,7 +77,7 @@ int tri_threads(int n) {
 
 void sysbuf_carve(Bump& b, SysBuf& S, int64_t cap, int n, int nreg, int P) {
   S.cap = cap; S.n = n; S.nreg = nreg;
-  S.tapecap = n * n + 64;
+  S.tapecap = 2 * n * n + 64;   // generic spectra need ~1.4 n^2 rotations (measured), graded ones far fewer
   S.nt = tri_threads(n);
   S.ld = vi_tri_ld(n);
   S.nchunk = (P + kChiGates - 1) / kChiGates;
@@ -157,10 +157,43 @@ int64_t per_system_bytes(int n, int nreg, int P) {
   return (b.off + 32 * 256) / 32;
 }
 
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  if (!e) return dflt;
+  int v = atoi(e);
+  return v >= 1 ? v : dflt;
+}
+
+// QL kernel geometry (k_tql_smem): one CTA per SM of W warps, at most Lmax lanes of each carry a system
+// (2n doubles of shared memory per system).  Returns 0 warps when not even 32 systems fit.
+int ql_lanes_max() { static const int L = env_int("VI_TQL_LANES", 16); return L > 32 ? 32 : L; }
+int ql_warps(int n) {
+  const int fit = (int)((227 * 1024) / ((size_t)2 * n * sizeof(double)));
+  if (fit < 32) return 0;
+  int W = fit / ql_lanes_max();
+  if (W > 24) W = 24;
+  return W < 1 ? 1 : W;
+}
+int64_t ql_wave(int n) { return (int64_t)sm_count() * ql_warps(n) * ql_lanes_max(); }
+
 int64_t default_system_cap(int64_t wanted, int n, int nreg, int P) {
   int64_t per = per_system_bytes(n, nreg, P);
-  int64_t budget = (int64_t)16 << 30;   // 16 GiB of scratch by default
+  int64_t budget = (int64_t)32 << 30;   // 32 GiB of scratch by default (of 180 GB)
   int64_t cap = budget / per;
+  // whole waves of the QL kernel (thread per system, residency bounded by 2n doubles of shared memory per
+  // system): a chunk of 1.1 waves would cost two
+  const int64_t wave = ql_wave(n);
+  if (wave >= 32 && cap > wave) cap = cap / wave * wave;
   if (cap > wanted) cap = wanted;
   if (cap < 32) cap = 32;
   return vi_align_up(cap, 32);
@@ -1051,23 +1084,6 @@ int run_tridiag(int64_t cnt, const double* G, const double* y, const double* reg
 // the whole shared memory of an SM, so it serialises with k_tridiag; k_apply and k_chi2 are small and can
 // run next to the tridiagonalisation of the following chunk (pipelined table phase: s_apply != s_ql, the
 // caller orders the two streams with events).
-int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  if (!e) return dflt;
-  int v = atoi(e);
-  return v >= 1 ? v : dflt;
-}
-
-int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
-}
-
 // lanes per warp that carry a system: as few as keep every system of the batch resident at once, at most Lmax
 int sparse_lanes(int64_t cnt, int sys_per_sm_max, int warps_per_sm, int Lmax) {
   int64_t per_sm = (cnt + sm_count() - 1) / sm_count();
@@ -1080,17 +1096,10 @@ int sparse_lanes(int64_t cnt, int sys_per_sm_max, int warps_per_sm, int Lmax) {
 
 int run_ql(int64_t cnt, const SysBuf& B, cudaStream_t s, bool* split) {
   const size_t per_sys = (size_t)2 * B.n * sizeof(double);
-  const int fit = (int)((227 * 1024) / per_sys);          // systems whose d, e fit one SM
-  *split = fit >= 32;
+  const int W = ql_warps(B.n), Lmax = ql_lanes_max();
+  *split = W > 0;
   if (cnt <= 0 || !*split) return VI_OK;
-  // one CTA per SM of W warps x L lanes; W*L <= fit
-  static const int Lmax = env_int("VI_TQL_LANES", 16);
-  int W = fit / Lmax;
-  if (W > 24) W = 24;
-  if (W < 1) W = 1;
-  int L = sparse_lanes(cnt, fit, W, Lmax);
-  if (W * L > fit) L = fit / W;
-  if (L < 1) { L = 1; W = fit; }
+  const int L = sparse_lanes(cnt, W * Lmax, W, Lmax);
   const int T = W * L;
   size_t smem = (size_t)T * per_sys;
   VI_CUDA(cudaFuncSetAttribute(k_tql_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1173,6 +1182,8 @@ static int64_t cap_for_workspace(int64_t ws_bytes, int64_t U, int n, int nreg, i
   int64_t per = per_system_bytes(n, nreg, P);
   int64_t cap = left / per;
   cap = cap / 32 * 32;
+  const int64_t wave = ql_wave(n);
+  if (wave >= 32 && cap > wave) cap = cap / wave * wave;     // whole QL waves, as in default_system_cap
   return cap;
 }
 

@@ -43,7 +43,7 @@ struct vi_trp_ws {
 
 VI_HD int vi_trp_npad(int n) { return (n + 7) & ~7; }
 VI_HD int vi_trp_noct(int n) { return vi_trp_npad(n) >> 3; }
-// warps of the CTA: the two longest octets get a warp of their own, the others are paired (long, short)
+// warps of the CTA: a little over half the octets, see vi_trp_octet_of
 VI_HD int vi_trp_nwarp(int n) { const int o = vi_trp_noct(n); const int w = (o + 2) / 2; return w > o ? o : w; }
 // doubles stored before octet q: sum_{t<q} 8 (npad - 8 t)
 VI_HD int vi_trp_octoff(int npad, int q) { return 8 * q * npad - 32 * q * (q - 1); }
@@ -192,18 +192,16 @@ VI_HD void vi_trp_reflector(const vi_trp_ws& W, int k, double* V, int tid) {
   if (tid == 0) { W.d[k] = W.col[k]; W.e[k] = beta; W.tau[k] = tau; }
 }
 
-// One tile: rows (2 ip, 2 ip + 1) x the 8 columns of octet q.  xb points at element (row 0, column 8 q) of a
-// virtual column-major block of leading dimension len = npad - 8 q, so element (i, 8 q + j) is xb[j len + i].
-// Applies x <- x - v_i w_c - w_i v_c, accumulates acc[j] += x vn_i (column sums) and returns the two row
-// sums sum_c x vn_c.  In the tiles that straddle the diagonal an element counts once for its column if
-// i >= c and once for its row if i > c; stored positions above the diagonal are dead.
+// One tile BELOW the diagonal block of its octet: rows (2 ip, 2 ip + 1), ip >= 4 q + 4, x the 8 columns of octet
+// q.  xb points at element (row 0, column 8 q) of a virtual column-major block of leading dimension
+// len = npad - 8 q, so element (i, 8 q + j) is xb[j len + i].  Applies x <- x - v_i w_c - w_i v_c, accumulates
+// acc[j] += x vn_i (column sums) and returns the two row sums sum_c x vn_c.
 VI_HD void vi_trp_tile(double* xb, int len, const vi_trp_ws& W, int q, int ip, int lo1, double* acc, double* pr) {
   const int i0 = 2 * ip;
   const vi_d2 v01 = *reinterpret_cast<const vi_d2*>(W.v + i0);
   const vi_d2 w01 = *reinterpret_cast<const vi_d2*>(W.w + i0);
   const vi_d2 n01 = *reinterpret_cast<const vi_d2*>(W.vn + i0);
   double pr0 = 0.0, pr1 = 0.0;
-  const bool diag = ip < 4 * q + 4;
   const double* vq = W.v + 8 * q;
   const double* wq = W.w + 8 * q;
   const double* nq = W.vn + 8 * q;
@@ -219,24 +217,43 @@ VI_HD void vi_trp_tile(double* xb, int len, const vi_trp_ws& W, int q, int ip, i
     x.x = x.x - v01.x * wc; x.x = x.x - w01.x * vc;
     x.y = x.y - v01.y * wc; x.y = x.y - w01.y * vc;
     *xp = x;
-    if (!diag) {
-      acc[j] += x.x * n01.x; acc[j] += x.y * n01.y;
-      pr0 += x.x * nc; pr1 += x.y * nc;
-    } else {
-      if (i0 >= c) acc[j] += x.x * n01.x;
-      if (i0 + 1 >= c) acc[j] += x.y * n01.y;
-      if (i0 > c) pr0 += x.x * nc;
-      if (i0 + 1 > c) pr1 += x.y * nc;
-    }
+    acc[j] += x.x * n01.x; acc[j] += x.y * n01.y;
+    pr0 += x.x * nc; pr1 += x.y * nc;
   }
   pr[0] = pr0; pr[1] = pr1;
 }
 
-// The octets of warp `warp`: slot 0 is octet `warp`; slot 1 (warps >= nsingle only) is octet warp + noct - nwarp.
-VI_HD int vi_trp_octet_of(const vi_trp_ws& W, int warp, int slot) {
-  if (slot == 0) return warp < W.noct ? warp : -1;
-  const int nsingle = 2 * W.nwarp - W.noct;
-  return (warp >= nsingle) ? warp + W.noct - W.nwarp : -1;
+// The 8 x 8 diagonal block of octet q, one lane per (row pair rp = lane / 8, column j = lane % 8): an element
+// counts once for its column if i >= c and once for its row if i > c; stored positions above the diagonal are
+// dead.  Returns this lane's contribution to column sum j (cj) and to the two row sums of its row pair.
+VI_HD void vi_trp_diag_lane(double* xb, int len, const vi_trp_ws& W, int q, int lo1, int lane,
+                            double* cj, double* r0, double* r1) {
+  const int rp = lane >> 3, j = lane & 7;
+  const int ip = 4 * q + rp, i0 = 2 * ip, c = 8 * q + j;
+  *cj = 0.0; *r0 = 0.0; *r1 = 0.0;
+  if (ip < (lo1 >> 1) || c < lo1 || c > i0 + 1) return;
+  const vi_d2 v01 = *reinterpret_cast<const vi_d2*>(W.v + i0);
+  const vi_d2 w01 = *reinterpret_cast<const vi_d2*>(W.w + i0);
+  const vi_d2 n01 = *reinterpret_cast<const vi_d2*>(W.vn + i0);
+  const double vc = W.v[c], wc = W.w[c], nc = W.vn[c];
+  vi_d2* xp = reinterpret_cast<vi_d2*>(xb + j * len + i0);
+  vi_d2 x = *xp;
+  x.x = x.x - v01.x * wc; x.x = x.x - w01.x * vc;
+  x.y = x.y - v01.y * wc; x.y = x.y - w01.y * vc;
+  *xp = x;
+  double s = x.y * n01.y;                        // i0 + 1 >= c here
+  if (i0 >= c) s += x.x * n01.x;
+  *cj = s;
+  if (i0 > c) *r0 = x.x * nc;
+  if (i0 + 1 > c) *r1 = x.y * nc;
+}
+
+// The octets of warp `warp` at a step whose first active octet is a: slot 0 is octet a + warp, slot 1 the octet
+// folded back from the end, a + 2 nwarp - 1 - warp (long octets come first, so the warps that got the longest
+// ones get the shortest of the rest, or none).  Every active octet belongs to exactly one warp.
+VI_HD int vi_trp_octet_of(const vi_trp_ws& W, int warp, int slot, int a) {
+  const int q = (slot == 0) ? a + warp : a + 2 * W.nwarp - 1 - warp;
+  return q < W.noct ? q : -1;
 }
 
 // lane -> which of the 8 column sums it ends up holding after vi_trp_reduce8 (lanes with lane % 4 == 0 store)
@@ -306,21 +323,36 @@ inline void vi_trp_reduce8_host(const double (*acc)[8], double* out) {
 }
 #endif
 
-// Matrix pass of step k (lo1 = k + 1) for one warp: its octets, 32 row pairs per trip.
+// Matrix pass of step k (lo1 = k + 1) for one warp: its octets; per octet the diagonal block (one lane per row
+// pair and column), then the tiles below it, 32 row pairs per trip.
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ void vi_trp_pass(const vi_trp_ws& W, int lo1, int warp, int lane) {
-  const int npad = W.npad, nrp = npad >> 1;
+  const int npad = W.npad, nrp = npad >> 1, a = lo1 >> 3;
 #pragma unroll 1
   for (int slot = 0; slot < 2; ++slot) {
-    const int q = vi_trp_octet_of(W, warp, slot);
-    if (q < 0 || 8 * q + 7 < lo1) continue;
+    const int q = vi_trp_octet_of(W, warp, slot, a);
+    if (q < 0) continue;
     const int len = npad - 8 * q;
     double* xb = W.X + vi_trp_octoff(npad, q) - 8 * q;
     double* prq = W.Pr + 2 * (vi_trp_tileoff(npad, q) - 4 * q);
-    const int ip0 = (4 * q > (lo1 >> 1)) ? 4 * q : (lo1 >> 1);
     double acc[8];
+    {
+      double cj, r0, r1;
+      vi_trp_diag_lane(xb, len, W, q, lo1, lane, &cj, &r0, &r1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+      for (int j = 0; j < 8; ++j) acc[j] = ((lane & 7) == j) ? cj : 0.0;
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+      }
+      const int ipd = 4 * q + (lane >> 3);
+      if ((lane & 7) == 0 && ipd >= (lo1 >> 1)) {
+        vi_d2 o2; o2.x = r0; o2.y = r1;
+        *reinterpret_cast<vi_d2*>(prq + 2 * ipd) = o2;
+      }
+    }
+    const int ip0 = (4 * q + 4 > (lo1 >> 1)) ? 4 * q + 4 : (lo1 >> 1);
 #pragma unroll 1
     for (int ip = ip0 + lane; ip < nrp; ip += 32) {
       double pr[2];
@@ -334,17 +366,29 @@ __device__ __forceinline__ void vi_trp_pass(const vi_trp_ws& W, int lo1, int war
 }
 #else
 inline void vi_trp_pass_host(const vi_trp_ws& W, int lo1, int warp) {
-  const int npad = W.npad, nrp = npad >> 1;
+  const int npad = W.npad, nrp = npad >> 1, a = lo1 >> 3;
   for (int slot = 0; slot < 2; ++slot) {
-    const int q = vi_trp_octet_of(W, warp, slot);
-    if (q < 0 || 8 * q + 7 < lo1) continue;
+    const int q = vi_trp_octet_of(W, warp, slot, a);
+    if (q < 0) continue;
     const int len = npad - 8 * q;
     double* xb = W.X + vi_trp_octoff(npad, q) - 8 * q;
     double* prq = W.Pr + 2 * (vi_trp_tileoff(npad, q) - 4 * q);
-    const int ip0 = (4 * q > (lo1 >> 1)) ? 4 * q : (lo1 >> 1);
-    double acc[32][8], tot[32];
+    double acc[32][8], tot[32], r0[32], r1[32], t0[32], t1[32];
     for (int lane = 0; lane < 32; ++lane) {
-      for (int j = 0; j < 8; ++j) acc[lane][j] = 0.0;
+      double cj;
+      vi_trp_diag_lane(xb, len, W, q, lo1, lane, &cj, &r0[lane], &r1[lane]);
+      for (int j = 0; j < 8; ++j) acc[lane][j] = ((lane & 7) == j) ? cj : 0.0;
+    }
+    for (int o = 1; o < 8; o <<= 1) {
+      for (int l = 0; l < 32; ++l) { t0[l] = r0[l] + r0[l ^ o]; t1[l] = r1[l] + r1[l ^ o]; }
+      for (int l = 0; l < 32; ++l) { r0[l] = t0[l]; r1[l] = t1[l]; }
+    }
+    for (int lane = 0; lane < 32; lane += 8) {
+      const int ipd = 4 * q + (lane >> 3);
+      if (ipd >= (lo1 >> 1)) { prq[2 * ipd] = r0[lane]; prq[2 * ipd + 1] = r1[lane]; }
+    }
+    const int ip0 = (4 * q + 4 > (lo1 >> 1)) ? 4 * q + 4 : (lo1 >> 1);
+    for (int lane = 0; lane < 32; ++lane) {
       for (int ip = ip0 + lane; ip < nrp; ip += 32) {
         double pr[2];
         vi_trp_tile(xb, len, W, q, ip, lo1, acc[lane], pr);
