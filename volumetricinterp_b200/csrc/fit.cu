@@ -243,7 +243,8 @@ k_tridiag(const double* __restrict__ G, const double* __restrict__ y, const doub
 }
 
 // Packed-triangle variant (vi_tridiag_packed.h): 87.5 KB of shared memory at n = 144 -> two CTAs per SM.
-__global__ void __launch_bounds__(352, 2)
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 k_tridiag_packed(const double* __restrict__ G, const double* __restrict__ y, const double* __restrict__ regs, SysBuf B,
                  Downdate dd) {
   extern __shared__ __align__(16) double sm[];
@@ -1064,9 +1065,14 @@ int run_tridiag(int64_t cnt, const double* G, const double* y, const double* reg
     static const bool force_full = getenv("VI_TRIDIAG_FULL") != nullptr;
     const size_t smem = (size_t)vi_trp_doubles(B.n) * sizeof(double);
     const int nt = vi_trp_threads(B.n);
-    if (!force_full && smem <= 227 * 1024 && nt <= 352) {
-      VI_CUDA(cudaFuncSetAttribute(k_tridiag_packed, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      VI_KERNEL(VI_K_TRIDIAG, s, k_tridiag_packed<<<(unsigned)cnt, nt, smem, s>>>(G, y, regs, B, dd));
+    if (!force_full && smem <= 227 * 1024 && nt <= 448) {
+      if (nt <= 320) {       // n <= 144: two CTAs per SM (registers capped accordingly)
+        VI_CUDA(cudaFuncSetAttribute(k_tridiag_packed<320, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VI_KERNEL(VI_K_TRIDIAG, s, (k_tridiag_packed<320, 2><<<(unsigned)cnt, nt, smem, s>>>(G, y, regs, B, dd)));
+      } else {
+        VI_CUDA(cudaFuncSetAttribute(k_tridiag_packed<448, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VI_KERNEL(VI_K_TRIDIAG, s, (k_tridiag_packed<448, 1><<<(unsigned)cnt, nt, smem, s>>>(G, y, regs, B, dd)));
+      }
       return VI_OK;
     }
   }

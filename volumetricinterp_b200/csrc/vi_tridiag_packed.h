@@ -196,7 +196,7 @@ VI_HD void vi_trp_reflector(const vi_trp_ws& W, int k, double* V, int tid) {
 // q.  xb points at element (row 0, column 8 q) of a virtual column-major block of leading dimension
 // len = npad - 8 q, so element (i, 8 q + j) is xb[j len + i].  Applies x <- x - v_i w_c - w_i v_c, accumulates
 // acc[j] += x vn_i (column sums) and returns the two row sums sum_c x vn_c.
-VI_HD void vi_trp_tile(double* xb, int len, const vi_trp_ws& W, int q, int ip, int lo1, double* acc, double* pr) {
+VI_HD void vi_trp_tile(double* xb, int len, const vi_trp_ws& W, int q, int ip, double* acc, double* pr) {
   const int i0 = 2 * ip;
   const vi_d2 v01 = *reinterpret_cast<const vi_d2*>(W.v + i0);
   const vi_d2 w01 = *reinterpret_cast<const vi_d2*>(W.w + i0);
@@ -205,12 +205,12 @@ VI_HD void vi_trp_tile(double* xb, int len, const vi_trp_ws& W, int q, int ip, i
   const double* vq = W.v + 8 * q;
   const double* wq = W.w + 8 * q;
   const double* nq = W.vn + 8 * q;
+  // (a finished column c < lo1 of the first active octet is processed like the others: its stored values are
+  // never read again, its column sum is not used and vn[c] = 0 keeps it out of the row sums)
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int j = 0; j < 8; ++j) {
-    const int c = 8 * q + j;
-    if (c < lo1) continue;                       // finished column (uniform over the warp)
     const double vc = vq[j], wc = wq[j], nc = nq[j];
     vi_d2* xp = reinterpret_cast<vi_d2*>(xb + j * len + i0);
     vi_d2 x = *xp;
@@ -356,7 +356,7 @@ __device__ __forceinline__ void vi_trp_pass(const vi_trp_ws& W, int lo1, int war
 #pragma unroll 1
     for (int ip = ip0 + lane; ip < nrp; ip += 32) {
       double pr[2];
-      vi_trp_tile(xb, len, W, q, ip, lo1, acc, pr);
+      vi_trp_tile(xb, len, W, q, ip, acc, pr);
       vi_d2 o; o.x = pr[0]; o.y = pr[1];
       *reinterpret_cast<vi_d2*>(prq + 2 * ip) = o;
     }
@@ -391,7 +391,7 @@ inline void vi_trp_pass_host(const vi_trp_ws& W, int lo1, int warp) {
     for (int lane = 0; lane < 32; ++lane) {
       for (int ip = ip0 + lane; ip < nrp; ip += 32) {
         double pr[2];
-        vi_trp_tile(xb, len, W, q, ip, lo1, acc[lane], pr);
+        vi_trp_tile(xb, len, W, q, ip, acc[lane], pr);
         prq[2 * ip] = pr[0]; prq[2 * ip + 1] = pr[1];
       }
     }
