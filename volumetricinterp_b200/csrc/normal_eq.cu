@@ -17,6 +17,7 @@
 //                staged through shared memory by cp.async double buffering; the weights are
 //                applied to the A-fragment in registers.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -437,6 +438,226 @@ k_ne_dmma2(const double* __restrict__ A, const double* __restrict__ Wm, const do
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// fast, version 3: version 2 without the work that is not part of the lower triangle.
+//   * the right-hand side y = A^T W b no longer occupies a 16x8 tile per row block (one useful column
+//     of eight): it is accumulated with plain DFMAs from the A fragments the diagonal unit holds anyway;
+//   * the tile right of the diagonal block's first half, (mi, 2 mi + 1), only has its lower 8 rows
+//     below the diagonal: it is issued as four m8n8k4 (half the tensor work of an m16n8k16);
+//   * units are dealt to the 12 warps by weight (full tile 4, diagonal unit 3), contiguously in
+//     (mi, ni) order so a warp still reloads its A fragment only when mi changes.
+// Issued tensor work per record: 81 full + 9 half tiles = 10 944 pairs for 10 440 needed (95 %),
+// against 99 x 128 = 12 672 (82 %) in version 2.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+constexpr int kUnitDiag = 1 << 16;      // unit flag: diagonal unit (half tile + rhs)
+constexpr int kUnitHalf = 1 << 17;      // ... whose half tile exists (8 (2 mi + 1) < N)
+constexpr int kMaxUnits = 96;
+constexpr int kW3 = 16;          // warps per CTA in version 3: four per tensor sub-partition, so that the ~4-deep
+                                 // dependent DMMA chain of one accumulator is covered by the other warps' work
+struct NeSplit {
+  int nunits;
+  int wbeg[kW3], wend[kW3];
+  int uinfo[kMaxUnits];
+};
+
+// units in (mi, ni) order and their contiguous split over the warps by weight (full tile 4, diagonal unit 3):
+// warp w ends where the running weight is closest to (w + 1) / kW3 of the total.  false if it does not fit.
+inline bool ne3_split(int N, int mt, int DT, NeSplit& sp) {
+  int c = 0, total = 0;
+  for (int mi = 0; mi < mt; ++mi) {
+    for (int ni = 0; ni <= 2 * mi; ++ni) {
+      if (c >= kMaxUnits) return false;
+      sp.uinfo[c++] = mi | (ni << 8); total += 4;
+    }
+    if (c >= kMaxUnits) return false;
+    const bool half = 8 * (2 * mi + 1) < N;
+    sp.uinfo[c++] = mi | ((2 * mi + 1) << 8) | kUnitDiag | (half ? kUnitHalf : 0);
+    total += 3;
+  }
+  sp.nunits = c;
+  // contiguous chunks of nearly equal weight ...
+  int cbeg[kW3 + 1], cw[kW3];
+  int u = 0, run = 0;
+  for (int w = 0; w < kW3; ++w) {
+    cbeg[w] = u;
+    const int before = run;
+    const int goal = (total * (w + 1) + kW3 / 2) / kW3;
+    while (u < c && (u - cbeg[w]) < DT) {
+      const int wt = (sp.uinfo[u] & kUnitDiag) ? 3 : 4;
+      if (w < kW3 - 1 && run + wt > goal && run + wt - goal > goal - run) break;
+      run += wt; ++u;
+    }
+    cw[w] = run - before;
+  }
+  cbeg[kW3] = u;
+  if (u != c) return false;
+  // ... dealt to the warps so that the four tensor sub-partitions (warp % 4) carry equal sums: heaviest chunk
+  // first, each to the lightest sub-partition that still has a free warp
+  bool used[kW3];
+  int spsum[4] = {0, 0, 0, 0}, spcnt[4] = {0, 0, 0, 0};
+  for (int w = 0; w < kW3; ++w) used[w] = false;
+  for (int n = 0; n < kW3; ++n) {
+    int best = -1;
+    for (int w = 0; w < kW3; ++w)
+      if (!used[w] && (best < 0 || cw[w] > cw[best])) best = w;
+    used[best] = true;
+    int q = -1;
+    for (int p = 0; p < 4; ++p)
+      if (spcnt[p] < kW3 / 4 && (q < 0 || spsum[p] < spsum[q])) q = p;
+    const int warp = q + 4 * spcnt[q];
+    spsum[q] += cw[best]; ++spcnt[q];
+    sp.wbeg[warp] = cbeg[best];
+    sp.wend[warp] = cbeg[best + 1];
+  }
+  return true;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kW3 * 32)
+k_ne_dmma3(const double* __restrict__ A, const double* __restrict__ Wm, const double* __restrict__ bm,
+           int P, int N, int mt, int cols, const __grid_constant__ NeSplit sp, double* __restrict__ G,
+           double* __restrict__ y) {
+  extern __shared__ __align__(16) double sm[];
+  double* S = sm;                                              // kEStages x cols x kELD
+  double* sw = sm + (size_t)kEStages * cols * kELD;            // kEStages x kEJ (slot order)
+  double* sb = sw + kEStages * kEJ;                            // kEStages x kEJ (slot order)
+  const int r = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  for (int e = tid; e < kEStages * cols * kELD + 2 * kEStages * kEJ; e += blockDim.x) sm[e] = 0.0;
+  __syncthreads();
+  const int t0 = sp.wbeg[warp];
+  const int t1 = sp.wend[warp];
+  int tinfo[DT];
+  double acc[DT][4];
+#pragma unroll
+  for (int q = 0; q < DT; ++q) {
+    const int tt = t0 + q;
+    tinfo[q] = (tt < t1) ? sp.uinfo[tt] : -1;
+    acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0;
+  }
+  const int nchunk = (P + kEJ - 1) / kEJ;
+  const int rj = warp, cc = lane;                  // a warp copies one gate (one row of A) per trip
+  const double* Wr = Wm + (int64_t)r * P;
+  const double* br = bm + (int64_t)r * P;
+
+  auto stage_load = [&](int chunk) {
+    const int st = chunk % kEStages;
+    double* dst = S + (size_t)st * cols * kELD;
+    const int j0 = chunk * kEJ;
+#pragma unroll
+    for (int q = 0; q < kEJ / kW3; ++q) {
+      const int jj = rj + kW3 * q;
+      const int j = j0 + jj;
+      const int sl = gate_slot(jj);
+      if (j < P) {
+        const double* src = A + (int64_t)j * N;
+        for (int c = cc; c < N; c += 32) cp_async8(dst + c * kELD + sl, src + c);
+      } else {
+        for (int c = cc; c < N; c += 32) dst[c * kELD + sl] = 0.0;
+      }
+    }
+    if (tid < kEJ) {
+      const int j = j0 + tid, sl = gate_slot(tid);
+      if (j < P) { cp_async8(sw + st * kEJ + sl, Wr + j); cp_async8(sb + st * kEJ + sl, br + j); }
+      else { sw[st * kEJ + sl] = 0.0; sb[st * kEJ + sl] = 0.0; }
+    }
+    cp_async_commit();
+  };
+
+  for (int c = 0; c < kEStages - 1 && c < nchunk; ++c) stage_load(c);
+  for (int ch = 0; ch < nchunk; ++ch) {
+    if (kEStages >= 3 && ch + 1 < nchunk) cp_async_wait<kEStages - 2>(); else cp_async_wait<0>();
+    __syncthreads();
+    if (ch + kEStages - 1 < nchunk) stage_load(ch + kEStages - 1);
+    const int st = ch % kEStages;
+    const double* Sst = S + (size_t)st * cols * kELD;
+    const double* Wst = sw + st * kEJ;
+    const double* Bst = sb + st * kEJ;
+#pragma unroll
+    for (int ks = 0; ks < kEJ / 16; ++ks) {
+      const int kb = 16 * ks + 4 * t;
+      const double2 w01 = *reinterpret_cast<const double2*>(Wst + kb);
+      const double2 w23 = *reinterpret_cast<const double2*>(Wst + kb + 2);
+      int cur_mi = -1;
+      double a[8];
+#pragma unroll
+      for (int q = 0; q < DT; ++q) {
+        if (tinfo[q] >= 0) {
+          const int mi = tinfo[q] & 255, ni = (tinfo[q] >> 8) & 255;
+          if (mi != cur_mi) {
+            cur_mi = mi;
+            const double* p0 = Sst + (16 * mi + g) * kELD + kb;
+            const double* p1 = p0 + 8 * kELD;
+            const double2 x01 = *reinterpret_cast<const double2*>(p0), x23 = *reinterpret_cast<const double2*>(p0 + 2);
+            const double2 z01 = *reinterpret_cast<const double2*>(p1), z23 = *reinterpret_cast<const double2*>(p1 + 2);
+            a[0] = x01.x * w01.x; a[2] = x01.y * w01.y; a[4] = x23.x * w23.x; a[6] = x23.y * w23.y;
+            a[1] = z01.x * w01.x; a[3] = z01.y * w01.y; a[5] = z23.x * w23.x; a[7] = z23.y * w23.y;
+          }
+          if (!(tinfo[q] & kUnitDiag)) {
+            const double* pb = Sst + (8 * ni + g) * kELD + kb;
+            const double2 b01 = *reinterpret_cast<const double2*>(pb), b23 = *reinterpret_cast<const double2*>(pb + 2);
+            const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+            dmma_16x8x16(acc[q], a, b);
+          } else {
+            if (tinfo[q] & kUnitHalf) {
+              const double* pb = Sst + (8 * ni + g) * kELD + kb;
+              const double2 b01 = *reinterpret_cast<const double2*>(pb), b23 = *reinterpret_cast<const double2*>(pb + 2);
+              dmma_8x8x4(acc[q][2], acc[q][3], a[1], b01.x);
+              dmma_8x8x4(acc[q][2], acc[q][3], a[3], b01.y);
+              dmma_8x8x4(acc[q][2], acc[q][3], a[5], b23.x);
+              dmma_8x8x4(acc[q][2], acc[q][3], a[7], b23.y);
+            }
+            // rhs: y_i += sum_k (A_ki w_k) b_k over this lane's four gates (rows g and g + 8 of the block)
+            const double2 v01 = *reinterpret_cast<const double2*>(Bst + kb);
+            const double2 v23 = *reinterpret_cast<const double2*>(Bst + kb + 2);
+            acc[q][0] = fma(a[0], v01.x, acc[q][0]); acc[q][0] = fma(a[2], v01.y, acc[q][0]);
+            acc[q][0] = fma(a[4], v23.x, acc[q][0]); acc[q][0] = fma(a[6], v23.y, acc[q][0]);
+            acc[q][1] = fma(a[1], v01.x, acc[q][1]); acc[q][1] = fma(a[3], v01.y, acc[q][1]);
+            acc[q][1] = fma(a[5], v23.x, acc[q][1]); acc[q][1] = fma(a[7], v23.y, acc[q][1]);
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < DT; ++q) {
+    if (tinfo[q] < 0) continue;
+    const int mi = tinfo[q] & 255, ni = (tinfo[q] >> 8) & 255;
+    const bool diag = tinfo[q] & kUnitDiag;
+    if (diag) {
+      // rhs: the four lanes of a group hold the partial sums of different gates
+      double y0 = acc[q][0], y1 = acc[q][1];
+      y0 += __shfl_xor_sync(0xffffffffu, y0, 1); y1 += __shfl_xor_sync(0xffffffffu, y1, 1);
+      y0 += __shfl_xor_sync(0xffffffffu, y0, 2); y1 += __shfl_xor_sync(0xffffffffu, y1, 2);
+      if (t == 0) {
+        const int i = 16 * mi + g;
+        if (i < N) y[(int64_t)r * N + i] = y0;
+        if (i + 8 < N) y[(int64_t)r * N + i + 8] = y1;
+      }
+      if (!(tinfo[q] & kUnitHalf)) continue;
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      if (diag && v < 2) continue;
+      const int i = 16 * mi + g + ((v & 2) ? 8 : 0);
+      const int k = 8 * ni + 2 * t + (v & 1);
+      if (i >= N) continue;
+      const double val = acc[q][v];
+      if (k <= i) {
+        G[((int64_t)r * N + i) * N + k] = val;
+        if (k != i) G[((int64_t)r * N + k) * N + i] = val;
+      }
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int vi_normal_eq_batched(const double* A, const double* value, const double* error, const double* weight,
@@ -473,6 +694,18 @@ extern "C" int vi_normal_eq_batched(const double* A, const double* value, const 
   }
   const int cols = (16 * mt > 8 * nt) ? 16 * mt : 8 * nt;
   const int tpw = (ntiles + kDW - 1) / kDW;
+  if (Wm && bm && !getenv("VI_NE_V2")) {
+    // version 3: lower-triangle work only (half tiles on the diagonal, rhs on the FP64 ALUs)
+    const int cols3 = 16 * mt;
+    size_t smem3 = ((size_t)kEStages * cols3 * kELD + 2 * kEStages * kEJ) * sizeof(double) + 64;
+    NeSplit sp;
+    if (smem3 <= 227 * 1024 && ne3_split(N, mt, 7, sp)) {
+      VI_CUDA(cudaFuncSetAttribute(k_ne_dmma3<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+      VI_KERNEL(VI_K_NORMAL_EQ, s, k_ne_dmma3<7><<<(unsigned)R, kW3 * 32, smem3, s>>>(A, Wm, bm, P, N, mt, cols3, sp, G, y));
+      VI_LAUNCH_CHECK();
+      return VI_OK;
+    }
+  }
   if (Wm && bm) {
     // masked weights / data already materialised by k_prep: streaming variant
     size_t smem2 = ((size_t)kEStages * cols * kELD + kEStages * kEJ) * sizeof(double) + 512;
