@@ -19,6 +19,7 @@ OBJ = os.path.join(HERE, "build")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INC, "-I", CSRC, "--expt-relaxed-constexpr"]
+COMMON += os.environ.get("VI_EXTRA_NVCC", "").split()      # e.g. -DVI_TRP_PROFILE (phase timers of k_tridiag_packed)
 UNITS = {          # file -> extra flags
     "abi.cu": [],
     "basis.cu": ["-fmad=false"],

@@ -44,8 +44,19 @@
 template <class F>
 VI_HD double vi_warp_sum(int a, int b, int lane, F f) {
 #if defined(__CUDA_ARCH__)
+  // four terms per trip, loaded before they are added (same order of additions as the plain loop; the loads
+  // of a trip overlap instead of each waiting behind the previous addition)
   double s = 0.0;
-  for (int k = a + lane; k < b; k += 32) s += f(k);
+  for (int k = a + lane; k < b; k += 128) {
+    const double t0 = f(k);
+    const double t1 = (k + 32 < b) ? f(k + 32) : 0.0;
+    const double t2 = (k + 64 < b) ? f(k + 64) : 0.0;
+    const double t3 = (k + 96 < b) ? f(k + 96) : 0.0;
+    s += t0;
+    if (k + 32 < b) s += t1;
+    if (k + 64 < b) s += t2;
+    if (k + 96 < b) s += t3;
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   return s;

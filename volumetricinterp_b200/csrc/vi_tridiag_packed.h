@@ -21,6 +21,7 @@
 // included in the same order.
 #pragma once
 #include "vi_tridiag.h"
+#include <vector>      // host restatement of the vector section only
 
 struct vi_trp_ws {
   double* X;      // packed lower triangle, vi_trp_xdoubles(n) doubles
@@ -38,6 +39,8 @@ struct vi_trp_ws {
   double* e;      // n
   double* tau;    // n
   double* sc;     // 8 scalars: [0] scale 2^-ex, [1] non-finite flag
+  double* part;   // 2 per vector-section warp: partial sums of p.vn and vn.y
+  double* part2;  // 1 per vector-section warp: partial sums of |pivot column|^2
   int n, npad, noct, nwarp;
 };
 
@@ -60,7 +63,7 @@ VI_HD int vi_trp_threads(int n) { return 32 * vi_trp_nwarp(n); }
 // doubles of CTA-shared storage, X included
 VI_HD int vi_trp_doubles(int n) {
   const int np = vi_trp_npad(n), nt = vi_trp_threads(n);
-  return vi_trp_xdoubles(n) + 2 * vi_trp_ntiles(n) + 4 * np + 7 * n + (nt > n ? nt : n) + 8 + 8;
+  return vi_trp_xdoubles(n) + 2 * vi_trp_ntiles(n) + 4 * np + 7 * n + (nt > n ? nt : n) + 8 + 8 + 4 * ((n + 31) / 32);
 }
 
 VI_HD void vi_trp_carve(vi_trp_ws& W, double* mem, int n) {
@@ -81,6 +84,8 @@ VI_HD void vi_trp_carve(vi_trp_ws& W, double* mem, int n) {
   W.tau = mem; mem += n;
   W.sc = mem; mem += 8;
   W.red1 = mem; mem += (nt > n ? nt : n);
+  W.part = mem; mem += 2 * ((n + 31) / 32);
+  W.part2 = mem; mem += 2 * ((n + 31) / 32);
 }
 
 // X <- scl * (0.5 (G + G^T) + sum_r lam[r] Reg_r) (lower triangle, packed), scl = 2^-exponent(max|X|);
@@ -207,16 +212,19 @@ VI_HD void vi_trp_tile(double* xb, int len, const vi_trp_ws& W, int q, int ip, d
   const vi_d2* nq = reinterpret_cast<const vi_d2*>(W.vn + 8 * q);
   // (a finished column c < lo1 of the first active octet is processed like the others: its stored values are
   // never read again, its column sum is not used and vn[c] = 0 keeps it out of the row sums)
-  // One column after the other (load, update, store): issuing the loads of several columns together was
-  // measured slower on B200 (1434 vs 1395 ms per 10k records).
+  // One column after the other, the next column's load issued before the current one's store (the compiler
+  // cannot hoist it on its own: it does not know that the columns do not overlap).  Issuing four or eight
+  // loads together was measured slower on B200 (1434 vs 1395 ms per 10k records).
   double* xp = xb + i0;
+  vi_d2 xn = *reinterpret_cast<vi_d2*>(xp);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int j2 = 0; j2 < 4; ++j2) {
     const vi_d2 vc = vq[j2], wc = wq[j2], nc = nq[j2];
     {
-      vi_d2 x = *reinterpret_cast<vi_d2*>(xp);
+      vi_d2 x = xn;
+      xn = *reinterpret_cast<vi_d2*>(xp + len);
       x.x = x.x - v01.x * wc.x; x.x = x.x - w01.x * vc.x;
       x.y = x.y - v01.y * wc.x; x.y = x.y - w01.y * vc.x;
       *reinterpret_cast<vi_d2*>(xp) = x;
@@ -225,7 +233,8 @@ VI_HD void vi_trp_tile(double* xb, int len, const vi_trp_ws& W, int q, int ip, d
       xp += len;
     }
     {
-      vi_d2 x = *reinterpret_cast<vi_d2*>(xp);
+      vi_d2 x = xn;
+      if (j2 < 3) xn = *reinterpret_cast<vi_d2*>(xp + len);
       x.x = x.x - v01.x * wc.y; x.x = x.x - w01.x * vc.y;
       x.y = x.y - v01.y * wc.y; x.y = x.y - w01.y * vc.y;
       *reinterpret_cast<vi_d2*>(xp) = x;
@@ -415,6 +424,100 @@ inline void vi_trp_pass_host(const vi_trp_ws& W, int lo1, int warp) {
 }
 #endif
 
+// ---- vector section of one Householder step (threads tid < nsub, i.e. the warps that own a vector element) -----
+// Every thread keeps its element of p, vn, y and of the next pivot column in registers; the three dot products
+// of a step (p.vn, vn.y, |column|^2) are block sums: a butterfly inside each warp, one partial per warp in
+// shared memory, a named barrier, and every thread adds the partials in warp order.  The pieces below are the
+// per-thread arithmetic, shared by the device code and its host restatement.
+
+// C1: p_i = tau (column sum + row sums of the tiles left of the diagonal); returns p_i, sets r1 = p_i vn_i, r2 = vn_i y_i
+VI_HD double vi_trp_c1(const vi_trp_ws& W, int lo1, double tau, int tid, double vn_i, double yv_i, double* r1, double* r2) {
+  const int npad = W.npad;
+  const int qlo = lo1 >> 3, qhi = tid >> 3;
+  const double* prt = W.Pr + 2 * (tid >> 1) + (tid & 1);
+  // four running sums (fixed assignment q % 4 relative to qlo), combined at the end: a short dependent chain
+  double s0 = W.pcol[tid], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for (int q = qlo; q <= qhi; q += 4) {
+    const double t0 = prt[2 * (vi_trp_tileoff(npad, q) - 4 * q)];
+    const double t1 = (q + 1 <= qhi) ? prt[2 * (vi_trp_tileoff(npad, q + 1) - 4 * (q + 1))] : 0.0;
+    const double t2 = (q + 2 <= qhi) ? prt[2 * (vi_trp_tileoff(npad, q + 2) - 4 * (q + 2))] : 0.0;
+    const double t3 = (q + 3 <= qhi) ? prt[2 * (vi_trp_tileoff(npad, q + 3) - 4 * (q + 3))] : 0.0;
+    s0 += t0; s1 += t1; s2 += t2; s3 += t3;
+  }
+  const double p = tau * ((s0 + s1) + (s2 + s3));
+  *r1 = p * vn_i;
+  *r2 = vn_i * yv_i;
+  return p;
+}
+
+// C2: w_i, rhs update, element i of the next pivot column (column k+1 with reflector k applied); returns col_i
+VI_HD double vi_trp_c2(const vi_trp_ws& W, int lo1, double tau, double dot, double dot2, int tid, double p_i,
+                       double vn_i, double yv_i, double xcol) {
+  const double a2 = -0.5 * tau * dot;
+  const double wn = p_i + a2 * vn_i;
+  W.yv[tid] = yv_i - (tau * dot2) * vn_i;
+  const double vlo = W.vn[lo1];
+  const double wlo = W.p[lo1] + a2 * vlo;
+  const double col = (xcol - vn_i * wlo) - wn * vlo;
+  W.col[tid] = col;
+  W.v[tid] = vn_i;
+  W.w[tid] = wn;
+  return col;
+}
+
+// C3: reflector kk from the pivot column (col_i in a register, |col[kk+2:]|^2 = xn2 given); same arithmetic as
+// vi_trp_reflector
+VI_HD void vi_trp_c3(const vi_trp_ws& W, int kk, double xn2, double* V, int tid, double col_i) {
+  const int n = W.n, lo = kk + 1;
+  double tau = 0.0; double beta = 0.0; double scale = 0.0;
+  const bool last = (kk == n - 2);
+  if (!last) {
+    const double alpha = W.col[kk + 1];
+    beta = alpha;
+    if (xn2 != 0.0) {
+      const double r2 = alpha * alpha + xn2;
+#if defined(__CUDA_ARCH__)
+      const double ri = rsqrt(r2);
+#else
+      const double ri = 1.0 / sqrt(r2);
+#endif
+      const double nrm = r2 * ri;
+      beta = -copysign(nrm, alpha);
+      tau = 1.0 + fabs(alpha) * ri;
+      scale = copysign(1.0, alpha) / (fabs(alpha) + nrm);
+    }
+  } else {
+    beta = W.col[n - 1];
+  }
+  if (tid >= lo && tid < n) {
+    double vv = 0.0;
+    if (tau != 0.0) vv = (tid == lo) ? 1.0 : col_i * scale;
+    W.vn[tid] = vv;
+    if (!last) V[(int64_t)kk * n + tid] = (tau == 0.0 && tid == lo) ? 1.0 : vv;
+  }
+  if (tid == kk) W.vn[kk] = 0.0;
+  if (tid == 0) { W.d[kk] = W.col[kk]; W.e[kk] = beta; W.tau[kk] = tau; }
+}
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ double vi_bfly(double x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+#define VI_NAMED_BAR(nsub) asm volatile("bar.sync 1, %0;" ::"r"(nsub) : "memory")
+#else
+inline void vi_bfly_host(const double* x, double* out) {      // 32 lanes -> the value every lane ends with
+  double a[32], b[32];
+  for (int l = 0; l < 32; ++l) a[l] = x[l];
+  for (int o = 16; o > 0; o >>= 1) {
+    for (int l = 0; l < 32; ++l) b[l] = a[l] + a[l ^ o];
+    for (int l = 0; l < 32; ++l) a[l] = b[l];
+  }
+  *out = a[0];
+}
+#endif
+
 // Reduction proper.  Per Householder step: matrix pass (all warps) -> CTA barrier -> vector section on the
 // ceil(n/32) warps that own a vector element (named barriers between its three sub-steps) -> CTA barrier.
 // After the call W.d, W.e, W.tau, W.yv (= Q^T y) are final; V row k holds reflector k in columns k+1..n-1.
@@ -425,53 +528,93 @@ VI_HD void vi_trp_reduce(const vi_trp_ws& W, double* V, int tid, int nt) {
   if (n >= 2) {
     VI_PHASE( if (tid < nsub) vi_trp_reflector(W, 0, V, tid); )
   }
+#if defined(__CUDA_ARCH__) && defined(VI_TRP_PROFILE)
+  long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define VI_TRP_TICK(i) { const long long now_ = clock64(); pt[i] += now_ - t_; t_ = now_; }
+  long long t_ = clock64();
+#else
+#define VI_TRP_TICK(i)
+#endif
   for (int k = 0; k + 1 < n; ++k) {
     const int lo1 = k + 1;
     const double tau = W.tau[k];
     // ---- B: deferred update of reflector k-1 fused with both halves of the symmetric mat-vec -------
 #if defined(__CUDA_ARCH__)
     vi_trp_pass(W, lo1, tid >> 5, tid & 31);
+    VI_TRP_TICK(0)
     __syncthreads();
+    VI_TRP_TICK(1)
 #else
     for (int warp = 0; warp < (nt >> 5); ++warp) vi_trp_pass_host(W, lo1, warp);
 #endif
-    // ---- C1: p = tau * (column sum + row sums of the tiles left of the diagonal), products ----------
-    VI_SUBPHASE(nsub,
-      if (tid >= lo1 && tid < n) {
-        double p = W.pcol[tid];
-        const int ip = tid >> 1;
-        const int qhi = tid >> 3;
-        for (int q = lo1 >> 3; q <= qhi; ++q) p += W.Pr[2 * (vi_trp_tileoff(npad, q) + ip - 4 * q) + (tid & 1)];
-        p = tau * p;
-        const double vn = W.vn[tid];
-        W.p[tid] = p;
-        W.red1[tid] = p * vn;
-        W.red2[tid] = vn * W.yv[tid];
+    // ---- C: vector section (see vi_trp_c1 .. c3) ------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+    if (tid < nsub) {
+      const bool in = (tid >= lo1) && (tid < n);
+      const int warp = tid >> 5, lane = tid & 31, nw = nsub >> 5;
+      double vn_i = 0.0, yv_i = 0.0, p_i = 0.0, r1 = 0.0, r2 = 0.0, xcol = 0.0;
+      if (in) {
+        vn_i = W.vn[tid]; yv_i = W.yv[tid];
+        xcol = W.X[vi_trp_idx(npad, tid, lo1)];
+        p_i = vi_trp_c1(W, lo1, tau, tid, vn_i, yv_i, &r1, &r2);
+        W.p[tid] = p_i;
       }
-    )
-    // ---- C2: dot products, w, rhs, next pivot column, rotate (v, w) <- (vn, wn) ----------------------
-    VI_SUBPHASE(nsub,
-      {
-        const double dot = vi_warp_sum(lo1, n, tid & 31, [&](int i) { return W.red1[i]; });
-        const double dot2 = vi_warp_sum(lo1, n, tid & 31, [&](int i) { return W.red2[i]; });
-        if (tid >= lo1 && tid < n) {
-          const double a2 = -0.5 * tau * dot;
-          const double vn = W.vn[tid];
-          const double wn = W.p[tid] + a2 * vn;
-          W.yv[tid] = W.yv[tid] - (tau * dot2) * vn;
-          const double vlo = W.vn[lo1];
-          const double wlo = W.p[lo1] + a2 * vlo;
-          W.col[tid] = (W.X[vi_trp_idx(npad, tid, lo1)] - vn * wlo) - wn * vlo;
-          W.v[tid] = vn;
-          W.w[tid] = wn;
+      r1 = vi_bfly(r1); r2 = vi_bfly(r2);
+      if (lane == 0) { W.part[2 * warp] = r1; W.part[2 * warp + 1] = r2; }
+      VI_NAMED_BAR(nsub);
+      VI_TRP_TICK(2)
+      double dot = 0.0, dot2 = 0.0;
+      for (int w = 0; w < nw; ++w) { dot += W.part[2 * w]; dot2 += W.part[2 * w + 1]; }
+      double col_i = 0.0;
+      if (in) col_i = vi_trp_c2(W, lo1, tau, dot, dot2, tid, p_i, vn_i, yv_i, xcol);
+      if (k + 2 < n) {
+        double sq = (tid >= k + 3 && tid < n) ? col_i * col_i : 0.0;
+        sq = vi_bfly(sq);
+        if (lane == 0) W.part2[warp] = sq;
+        VI_NAMED_BAR(nsub);
+        VI_TRP_TICK(3)
+        double xn2 = 0.0;
+        for (int w = 0; w < nw; ++w) xn2 += W.part2[w];
+        vi_trp_c3(W, k + 1, xn2, V, tid, col_i);
+      }
+    }
+    VI_TRP_TICK(4)
+    __syncthreads();
+    VI_TRP_TICK(5)
+#else
+    {
+      const int nw = nsub >> 5;
+      std::vector<double> vn_(nsub, 0.0), yv_(nsub, 0.0), p_(nsub, 0.0), r1_(nsub, 0.0), r2_(nsub, 0.0), xc_(nsub, 0.0),
+          col_(nsub, 0.0), sq_(nsub, 0.0);
+      for (int t = 0; t < nsub; ++t) {
+        if (t >= lo1 && t < n) {
+          vn_[t] = W.vn[t]; yv_[t] = W.yv[t];
+          xc_[t] = W.X[vi_trp_idx(npad, t, lo1)];
+          p_[t] = vi_trp_c1(W, lo1, tau, t, vn_[t], yv_[t], &r1_[t], &r2_[t]);
+          W.p[t] = p_[t];
         }
       }
-    )
-    // ---- C3: reflector k + 1 ---------------------------------------------------------------------------
-    VI_PHASE(
-      if (tid < nsub && k + 2 < n) vi_trp_reflector(W, k + 1, V, tid);
-    )
+      for (int w = 0; w < nw; ++w) { vi_bfly_host(&r1_[32 * w], &W.part[2 * w]); vi_bfly_host(&r2_[32 * w], &W.part[2 * w + 1]); }
+      double dot = 0.0, dot2 = 0.0;
+      for (int w = 0; w < nw; ++w) { dot += W.part[2 * w]; dot2 += W.part[2 * w + 1]; }
+      // (W.p[lo1] and W.vn[lo1] are read by every thread of C2 and written by none of them)
+      for (int t = 0; t < nsub; ++t)
+        if (t >= lo1 && t < n) col_[t] = vi_trp_c2(W, lo1, tau, dot, dot2, t, p_[t], vn_[t], yv_[t], xc_[t]);
+      if (k + 2 < n) {
+        for (int t = 0; t < nsub; ++t) sq_[t] = (t >= k + 3 && t < n) ? col_[t] * col_[t] : 0.0;
+        for (int w = 0; w < nw; ++w) vi_bfly_host(&sq_[32 * w], &W.part2[w]);
+        double xn2 = 0.0;
+        for (int w = 0; w < nw; ++w) xn2 += W.part2[w];
+        for (int t = 0; t < nsub; ++t) vi_trp_c3(W, k + 1, xn2, V, t, col_[t]);
+      }
+    }
+#endif
   }
+#if defined(__CUDA_ARCH__) && defined(VI_TRP_PROFILE)
+  if ((tid == 0 || tid == 32 * 7) && (blockIdx.x % 2000) == 7)
+    printf("[trp] block %d tid %d: pass %lld  bar1 %lld  C1 %lld  C2 %lld  C3 %lld  bar2 %lld  (cycles per system)\n",
+           (int)blockIdx.x, tid, pt[0], pt[1], pt[2], pt[3], pt[4], pt[5]);
+#endif
   VI_PHASE(
     if (tid == 0) {
       if (n == 1) W.d[0] = W.X[0];
