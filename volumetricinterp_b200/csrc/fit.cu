@@ -442,18 +442,131 @@ k_apply(int64_t nsys, SysBuf B, double* __restrict__ Cout, int32_t* __restrict__
 // thread i owns column i of Z in shared memory and replays the rotation tape on it (all threads run
 // the same rotation sequence: uniform control flow, tape entries are broadcast loads), then applies the
 // reflectors.  H = E diag(scl/lambda) E^T, T = H G and dC = T H are three batched N x N products.
+// The rotation tape and the reflectors are the same for all n columns, so they are STAGED through shared memory
+// (cp.async, double-buffered: 256 rotations / 8 reflector rows at a time) instead of every thread fetching every
+// entry from global memory behind its own dependent chain (that version spent 2.2 ms per record, 95 % of the
+// covariance phase).
+constexpr int kEvTape = 256;     // rotations per staged chunk
+constexpr int kEvRows = 8;       // reflector rows per staged batch
+
+__device__ __forceinline__ void cpa16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cpa8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cpa4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N_>
+__device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N_)); }
+
+// doubles of staging space behind the n x ld eigenvector block
+__host__ __device__ inline int eigvec_stage_doubles(int n) {
+  const int tape = 2 * kEvTape * 2 + (2 * kEvTape + 1) / 2;                  // (c, s) pairs + int32 codes, two buffers
+  const int rows = 2 * kEvRows * ((n + 1) & ~1) + 2 * kEvRows;               // rows + their tau, two buffers
+  return (tape > rows ? tape : rows) + 2;
+}
+
 __global__ void k_eigvec(int64_t s0, SysBuf B, double pinv_rtol, double* __restrict__ E, double* __restrict__ dinv) {
   extern __shared__ __align__(16) double sm[];
-  const int n = B.n, i = threadIdx.x, ld = B.ld;
+  const int n = B.n, i = threadIdx.x, ld = B.ld, nt = blockDim.x;
   const int64_t s = s0 + blockIdx.x;
   if (B.st[s] != VI_ST_OK || B.rec[s] < 0) return;
   const int64_t base = ileave(s, n);
+  double* stage = sm + (size_t)n * ld;
+  double* col = sm + i;                          // this thread's column of Z (stride ld)
+  if (i < n)
+    for (int r = 0; r < n; ++r) col[r * ld] = (r == i) ? 1.0 : 0.0;
+  // ---- Z: replay the tape backwards (vi_tape_apply_z order) ------------------------------------------------
+  {
+    const int32_t nrot = B.nrot[s];
+    const double2* gcs = reinterpret_cast<const double2*>(B.tcs + s * (int64_t)B.tapecap * 2);
+    const int32_t* gix = B.tix + s * (int64_t)B.tapecap;
+    double2* scs = reinterpret_cast<double2*>(stage);                  // [2][kEvTape]
+    int32_t* six = reinterpret_cast<int32_t*>(scs + 2 * kEvTape);      // [2][kEvTape]
+    const int nchunk = (nrot + kEvTape - 1) / kEvTape;
+    auto load = [&](int c) {
+      const int buf = c & 1;
+      for (int t = i; t < kEvTape; t += nt) {
+        const int32_t idx = nrot - 1 - (c * kEvTape + t);              // t-th rotation of this chunk, going backwards
+        if (idx >= 0) { cpa16(scs + buf * kEvTape + t, gcs + idx); cpa4(six + buf * kEvTape + t, gix + idx); }
+      }
+      cpa_commit();
+    };
+    if (nchunk > 0) load(0);
+    for (int c = 0; c < nchunk; ++c) {
+      if (c + 1 < nchunk) { load(c + 1); cpa_wait<1>(); } else cpa_wait<0>();
+      __syncthreads();
+      if (i < n) {
+        const int cnt = min(kEvTape, nrot - c * kEvTape);
+        const double2* pcs = scs + (c & 1) * kEvTape;
+        const int32_t* pix = six + (c & 1) * kEvTape;
+#pragma unroll 4
+        for (int t = 0; t < cnt; ++t) {
+          const int32_t code = pix[t];
+          const double2 cs = pcs[t];
+          const int pi = code >> 1;
+          const int pj = (code & 1) ? pi - 1 : pi + 1;
+          const double a = col[pi * ld], b = col[pj * ld];
+          col[pi * ld] = cs.x * a + cs.y * b;
+          col[pj * ld] = cs.x * b - cs.y * a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- E = Q Z: reflectors n-3 .. 0 (vi_tri_backtransform order), rows staged kEvRows at a time ----------------
+  {
+    const int nld = (n + 1) & ~1;
+    double* srow = stage;                                   // [2][kEvRows][nld]
+    double* stau = stage + 2 * kEvRows * nld;               // [2][kEvRows]
+    const double* V = B.V + s * (int64_t)n * n;
+    const int nref = n - 2;                                 // reflectors j = 0 .. n-3
+    const int nbatch = nref > 0 ? (nref + kEvRows - 1) / kEvRows : 0;
+    auto load = [&](int bidx) {
+      const int buf = bidx & 1;
+      const int jhi = nref - 1 - bidx * kEvRows;            // first (highest) reflector of the batch
+      for (int e = i; e < kEvRows * n; e += nt) {
+        const int q = e / n, c = e - q * n;
+        const int j = jhi - q;
+        if (j >= 0 && c > j) cpa8(srow + (buf * kEvRows + q) * nld + c, V + (int64_t)j * n + c);
+      }
+      if (i < kEvRows && jhi - i >= 0) cpa8(stau + buf * kEvRows + i, B.tau + base + (int64_t)(jhi - i) * 32);
+      cpa_commit();
+    };
+    if (nbatch > 0) load(0);
+    for (int bidx = 0; bidx < nbatch; ++bidx) {
+      if (bidx + 1 < nbatch) { load(bidx + 1); cpa_wait<1>(); } else cpa_wait<0>();
+      __syncthreads();
+      if (i < n) {
+        const int jhi = nref - 1 - bidx * kEvRows;
+        for (int q = 0; q < kEvRows; ++q) {
+          const int j = jhi - q;
+          if (j < 0) break;
+          const double t = stau[(bidx & 1) * kEvRows + q];
+          if (t == 0.0) continue;
+          const double* vj = srow + ((bidx & 1) * kEvRows + q) * nld;
+          double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+          int r = j + 1;
+          for (; r + 3 < n; r += 4) {
+            d0 += vj[r] * col[r * ld];
+            d1 += vj[r + 1] * col[(r + 1) * ld];
+            d2 += vj[r + 2] * col[(r + 2) * ld];
+            d3 += vj[r + 3] * col[(r + 3) * ld];
+          }
+          for (; r < n; ++r) d0 += vj[r] * col[r * ld];
+          const double dot = ((d0 + d1) + (d2 + d3)) * t;
+          for (r = j + 1; r < n; ++r) col[r * ld] -= dot * vj[r];
+        }
+      }
+      __syncthreads();
+    }
+  }
   if (i < n) {
-    for (int r = 0; r < n; ++r) sm[r * ld + i] = (r == i) ? 1.0 : 0.0;
-    vi_tape_apply_z(vi_svec{sm + i, ld}, tape_of(B, s), B.nrot[s]);
-    vi_tri_backtransform(n, B.V + s * (int64_t)n * n, B.tau + base, 32, sm + i, ld);
     double* Es = E + (int64_t)blockIdx.x * n * n;
-    for (int r = 0; r < n; ++r) Es[(int64_t)r * n + i] = sm[r * ld + i];
+    for (int r = 0; r < n; ++r) Es[(int64_t)r * n + i] = col[r * ld];
     double lmax = 0.0;
     for (int m = 0; m < n; ++m) lmax = fmax(lmax, fabs(B.d[base + (int64_t)m * 32]));
     const double l = B.d[base + (int64_t)i * 32];
@@ -1364,7 +1477,7 @@ extern "C" int vi_fit_batched(const double* At, const double* A, const double* W
     if (int rc = run_chi2(cnt, At, Wm, bm, P, B, C + r0 * N, B.chi2, st)) return rc;
     if (dC != nullptr) {
       const int64_t NN = (int64_t)N * N;
-      const size_t smem_e = (size_t)N * B.ld * sizeof(double);
+      const size_t smem_e = ((size_t)N * B.ld + eigvec_stage_doubles(N)) * sizeof(double);
       VI_CUDA(cudaFuncSetAttribute(k_eigvec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
       const unsigned tiles = (unsigned)((N + 63) / 64);
       for (int64_t c0 = 0; c0 < cnt; c0 += cc) {
