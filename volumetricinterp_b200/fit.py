@@ -160,4 +160,14 @@ def _to_host(tensors, dev):
         view.copy_(t, non_blocking=True)
         staged.append(view)
     torch.cuda.synchronize(dev)
-    return [v.numpy().copy() if v is not None else None for v in staged]
+    # pageable copies that own their memory; torch's CPU copy is multi-threaded (the covariance block is
+    # 1.7 GB for 10k records: a single-threaded numpy copy with its page faults costs more than the PCIe transfer)
+    out = []
+    for v in staged:
+        if v is None:
+            out.append(None)
+            continue
+        o = torch.empty(v.shape, dtype=v.dtype)
+        o.copy_(v)
+        out.append(o.numpy())
+    return out
