@@ -329,9 +329,10 @@ __device__ __forceinline__ void tape_replay(vi_svec w, const double2* __restrict
 // 32 lanes of a warp carrying a system ("sparse lanes"): the same number of systems per SM is spread over
 // 32/L times as many warps, which gives the schedulers that many more independent chains to interleave and
 // cuts the divergence between the systems of a warp.  L adapts to the batch (small Brent rounds: L = 1).
-constexpr int kReplayWarps = 8;
-__global__ void __launch_bounds__(kReplayWarps * 32)
+constexpr int kReplayWarpsMax = 12;
+__global__ void __launch_bounds__(kReplayWarpsMax * 32)
 k_replay(int64_t nsys, SysBuf B, double rcond, int L) {
+  const int kReplayWarps = blockDim.x >> 5;
   extern __shared__ __align__(16) double sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = B.n;
   const int T = kReplayWarps * L;                       // systems per CTA
@@ -1232,6 +1233,8 @@ int run_apply(int64_t cnt, const SysBuf& B, double rcond, double* Cout, int32_t*
     const size_t per_sys = (size_t)B.n * sizeof(double);
     const int fit = (int)((227 * 1024) / per_sys);
     static const int Lenv = env_int("VI_REPLAY_LANES", 16);
+    static const int Wenv = env_int("VI_REPLAY_WARPS", 8);
+    const int kReplayWarps = Wenv > kReplayWarpsMax ? kReplayWarpsMax : Wenv;
     int Lmax = Lenv > 32 ? 32 : Lenv;
     while (Lmax > 1 && (size_t)kReplayWarps * Lmax * per_sys > 227 * 1024) --Lmax;
     int nb = 1;      // resident CTAs per SM at the full lane count (registers and shared memory both count)
