@@ -121,7 +121,7 @@ def test_solver_matches_lstsq_given_identical_system(cuda, name):
         assert np.max(np.abs(Cf[i] - ref)) <= 50 * EPS * (s[0] / s[-1]) * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("n", [1, 2, 5, 8, 9, 16, 27, 40, 64, 100, 144, 150])
+@pytest.mark.parametrize("n", [1, 2, 5, 8, 9, 16, 27, 40, 64, 100, 144, 150, 176, 200, 230])
 def test_solver_generic_full_rank_systems(cuda, n):
     """Well-conditioned dense systems of every order around the octet / warp boundaries of the packed
     tridiagonalisation: QL needs ~1.4 n^2 rotations there (the fits' graded spectra need far fewer), the

@@ -111,7 +111,7 @@ def test_system_pipeline_rank_deficient(harness, nt):
         assert np.max(np.abs(dens - dref)) <= 1e-5 * np.abs(dref).max()
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 9, 16, 27, 40, 65, 100, 144, 150])
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 9, 16, 27, 40, 65, 100, 144, 150, 200])
 def test_packed_tridiagonalisation_random(harness, n):
     """Packed-triangle Householder reduction: T has the spectrum of X, the solve matches numpy, for orders
     around every octet / warp-assignment boundary."""
