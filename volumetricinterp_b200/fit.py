@@ -10,6 +10,7 @@ C ABI in _native.py).  One call fits all R records of a file:
 which replaces the reference's record loop, interpolate.py:511-574.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -168,6 +169,32 @@ def _to_host(tensors, dev):
             out.append(None)
             continue
         o = torch.empty(v.shape, dtype=v.dtype)
-        o.copy_(v)
+        _parallel_copy(o, v)
         out.append(o.numpy())
     return out
+
+
+_copy_pool = None
+
+
+def _parallel_copy(dst, src, min_bytes=64 << 20):
+    """dst.copy_(src) for host tensors, split over a few Python threads (torch's copy releases the GIL).  Does not
+    depend on OMP_NUM_THREADS, which torchrun sets to 1 for every rank."""
+    global _copy_pool
+    import torch
+    nbytes = src.numel() * src.element_size()
+    if nbytes < min_bytes or src.dim() == 0 or src.shape[0] < 2:
+        dst.copy_(src)
+        return
+    import concurrent.futures
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    nthr = max(1, min(8, (os.cpu_count() or 1) // max(1, local_world), src.shape[0]))
+    if nthr == 1:
+        dst.copy_(src)
+        return
+    if _copy_pool is None:
+        _copy_pool = concurrent.futures.ThreadPoolExecutor(max_workers=8)
+    step = (src.shape[0] + nthr - 1) // nthr
+    futs = [_copy_pool.submit(lambda a=a: dst[a:a + step].copy_(src[a:a + step])) for a in range(0, src.shape[0], step)]
+    for f in futs:
+        f.result()
