@@ -90,7 +90,9 @@ int vi_normal_eq_batched(const double* A, const double* value, const double* err
                          double* G, double* y, double* sWbb, int32_t* npts, double* Wm, double* bm, void* stream);
 
 /* Scratch size needed by vi_fit_batched / vi_solve_batched for the given shape. `systems` is the
- * number of simultaneous eigen-systems the caller is willing to hold (0 = library default). */
+ * number of simultaneous eigen-systems the caller is willing to hold (0 = library default: as many
+ * as 32 GiB hold, rounded down to whole waves of the QL kernel, at most what the batch needs;
+ * about 1 MB per system at N = 144). */
 int vi_fit_workspace_bytes(int32_t R, int32_t P, int32_t N, int32_t nreg, int64_t systems, int64_t* bytes);
 
 /* interpolate.py:462 for S independent systems: C_s = lstsq(sym(G[rec_s]) + sum_i lam[s][i] Reg_i, y[rec_s])
