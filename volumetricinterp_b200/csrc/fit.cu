@@ -176,7 +176,7 @@ int env_int(const char* name, int dflt) {
 
 // QL kernel geometry (k_tql_smem): one CTA per SM of W warps, at most Lmax lanes of each carry a system
 // (2n doubles of shared memory per system).  Returns 0 warps when not even 32 systems fit.
-int ql_lanes_max() { static const int L = env_int("VI_TQL_LANES", 16); return L > 32 ? 32 : L; }
+int ql_lanes_max() { static const int L = env_int("VI_TQL_LANES", 12); return L > 32 ? 32 : L; }
 int ql_warps(int n) {
   const int fit = (int)((227 * 1024) / ((size_t)2 * n * sizeof(double)));
   if (fit < 32) return 0;
