@@ -1454,10 +1454,8 @@ extern "C" int vi_fit_batched(const double* At, const double* A, const double* W
       VI_KERNEL(VI_K_MISC, st, k_nm_propose<<<blocks(U, 128), 128, 0, st>>>(U, nreg, nvalid, Ub, ucount));
       VI_KERNEL(VI_K_MISC, st, k_scan_counts<<<1, 1024, 0, st>>>(U, ucount, Ub.off));
       int64_t T = 0;
-      int32_t any_active = 0;
       VI_CUDA(cudaMemcpyAsync(&T, Ub.off + U, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
       VI_CUDA(cudaStreamSynchronize(st));
-      (void)any_active;
       if (T == 0) break;       // every unit has terminated (a unit with zero weighted gates never starts)
       for (int64_t t0 = 0; t0 < T; t0 += cap) {
         int64_t cnt = (T - t0 < cap) ? T - t0 : cap;

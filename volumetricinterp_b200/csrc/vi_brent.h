@@ -45,13 +45,12 @@ VI_HD vi_bracket vi_chi2_bracket(const double* chi2, int64_t stride, int npts) {
   for (int isf = 0; isf < 5; ++isf) {
     double nu = npts * sfs[isf];
     double val0 = 1.0;
-    int k = 0, k0 = 0;
+    int k = 0;
     double val = chi2[0] - nu;
     if (val < 0.0) { out.status = VI_ST_TOO_SMOOTH; out.nu = nu; return out; }
     while (val0 * val > 0.0) {
       bracket = true;
       val0 = val;
-      k0 = k;
       k = k + 1;                       // alpha = alpha - 1
       val = chi2[(int64_t)k * stride] - nu;
       if (k > 100) { bracket = false; break; }   // alpha < -100
@@ -60,7 +59,6 @@ VI_HD vi_bracket vi_chi2_bracket(const double* chi2, int64_t stride, int npts) {
       out.status = VI_ST_OK;
       out.k_lo = k;
       out.nu = nu;
-      (void)k0;
       return out;
     }
   }
