@@ -246,12 +246,12 @@ VI_HD void vi_trp_tile(double* xb, int len, const vi_trp_ws& W, int q, int ip, d
   pr[0] = pr0; pr[1] = pr1;
 }
 
-// The 8 x 8 diagonal block of octet q, one lane per (row pair rp = lane / 8, column j = lane % 8): an element
+// The 8 x 8 diagonal block of octet q, one lane per (row pair rp = lane % 4, column j = lane / 4): an element
 // counts once for its column if i >= c and once for its row if i > c; stored positions above the diagonal are
 // dead.  Returns this lane's contribution to column sum j (cj) and to the two row sums of its row pair.
 VI_HD void vi_trp_diag_lane(double* xb, int len, const vi_trp_ws& W, int q, int lo1, int lane,
                             double* cj, double* r0, double* r1) {
-  const int rp = lane >> 3, j = lane & 7;
+  const int rp = lane & 3, j = lane >> 2;      // row pair fastest: a quarter-warp reads 2 columns x 4 consecutive row pairs
   const int ip = 4 * q + rp, i0 = 2 * ip, c = 8 * q + j;
   *cj = 0.0; *r0 = 0.0; *r1 = 0.0;
   if (ip < (lo1 >> 1) || c < lo1 || c > i0 + 1) return;
@@ -363,14 +363,14 @@ __device__ __forceinline__ void vi_trp_pass(const vi_trp_ws& W, int lo1, int war
       double cj, r0, r1;
       vi_trp_diag_lane(xb, len, W, q, lo1, lane, &cj, &r0, &r1);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = ((lane & 7) == j) ? cj : 0.0;
+      for (int j = 0; j < 8; ++j) acc[j] = ((lane >> 2) == j) ? cj : 0.0;
 #pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {
+      for (int o = 4; o < 32; o <<= 1) {
         r0 += __shfl_xor_sync(0xffffffffu, r0, o);
         r1 += __shfl_xor_sync(0xffffffffu, r1, o);
       }
-      const int ipd = 4 * q + (lane >> 3);
-      if ((lane & 7) == 0 && ipd >= (lo1 >> 1)) {
+      const int ipd = 4 * q + (lane & 3);
+      if (lane < 4 && ipd >= (lo1 >> 1)) {
         vi_d2 o2; o2.x = r0; o2.y = r1;
         *reinterpret_cast<vi_d2*>(prq + 2 * ipd) = o2;
       }
@@ -400,14 +400,14 @@ inline void vi_trp_pass_host(const vi_trp_ws& W, int lo1, int warp) {
     for (int lane = 0; lane < 32; ++lane) {
       double cj;
       vi_trp_diag_lane(xb, len, W, q, lo1, lane, &cj, &r0[lane], &r1[lane]);
-      for (int j = 0; j < 8; ++j) acc[lane][j] = ((lane & 7) == j) ? cj : 0.0;
+      for (int j = 0; j < 8; ++j) acc[lane][j] = ((lane >> 2) == j) ? cj : 0.0;
     }
-    for (int o = 1; o < 8; o <<= 1) {
+    for (int o = 4; o < 32; o <<= 1) {
       for (int l = 0; l < 32; ++l) { t0[l] = r0[l] + r0[l ^ o]; t1[l] = r1[l] + r1[l ^ o]; }
       for (int l = 0; l < 32; ++l) { r0[l] = t0[l]; r1[l] = t1[l]; }
     }
-    for (int lane = 0; lane < 32; lane += 8) {
-      const int ipd = 4 * q + (lane >> 3);
+    for (int lane = 0; lane < 4; ++lane) {
+      const int ipd = 4 * q + (lane & 3);
       if (ipd >= (lo1 >> 1)) { prq[2 * ipd] = r0[lane]; prq[2 * ipd + 1] = r1[lane]; }
     }
     const int ip0 = (4 * q + 4 > (lo1 >> 1)) ? 4 * q + 4 : (lo1 >> 1);
