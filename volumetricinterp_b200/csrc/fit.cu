@@ -375,7 +375,7 @@ k_replay(int64_t nsys, SysBuf B, double rcond, int L) {
 // sit on the dependency chain of every rotation, so they live in shared memory laid out [i][thread]
 // (a lane always hits its own bank pair whatever i it is at).  Leaves the eigenvalues in B.d, the
 // tape in B.tcs / B.tix; the right-hand side is handled by k_apply.
-__global__ void k_tql_smem(int64_t nsys, SysBuf B, int L) {
+__global__ void k_tql_smem(int64_t nsys, SysBuf B, int L, int iter_batch) {
   extern __shared__ __align__(16) double sm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = B.n;
   const int T = (blockDim.x >> 5) * L;                  // systems per CTA (sparse lanes, see k_replay)
@@ -391,7 +391,7 @@ __global__ void k_tql_smem(int64_t nsys, SysBuf B, int L) {
       e[i] = B.e[base + (int64_t)i * 32];
     }
   int32_t nrot = 0;
-  const int q = vi_tql_values_flat(n, d, e, tape_of(B, sc), &nrot, act, L >= 32 ? 8 : (L + 3) / 4);
+  const int q = vi_tql_values_flat(n, d, e, tape_of(B, sc), &nrot, act, iter_batch);
   if (!act) return;
   if (q != 0) { B.st[s] = VI_ST_NOCONV; return; }
   B.nrot[s] = nrot;
@@ -1223,7 +1223,10 @@ int run_ql(int64_t cnt, const SysBuf& B, cudaStream_t s, bool* split) {
   const int T = W * L;
   size_t smem = (size_t)T * per_sys;
   VI_CUDA(cudaFuncSetAttribute(k_tql_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  VI_KERNEL(VI_K_TQL, s, k_tql_smem<<<blocks(cnt, T), W * 32, smem, s>>>(cnt, B, L));
+  // lanes that reach the (expensive) sweep set-up wait until this many of the warp are there, or nobody rotates
+  static const int batch_env = env_int("VI_TQL_BATCH", 0);
+  const int iter_batch = batch_env > 0 ? batch_env : (L >= 32 ? 8 : 1);     // sparse lanes: waiting does not pay (measured)
+  VI_KERNEL(VI_K_TQL, s, k_tql_smem<<<blocks(cnt, T), W * 32, smem, s>>>(cnt, B, L, iter_batch));
   return VI_OK;
 }
 
