@@ -91,7 +91,7 @@ void sysbuf_carve(Bump& b, SysBuf& S, int64_t cap, int n, int nreg, int P) {
   S.g = b.take<double>(cap * n);
   S.tau = b.take<double>(cap * n);
   S.scl = b.take<double>(cap);
-  S.tcs = b.take<double>(cap * S.tapecap * 2);     // (c, s) pairs, interleaved over groups of 32 systems (tape_base)
+  S.tcs = b.take<double>(cap * S.tapecap * 2);     // (c, s) pairs, contiguous per system
   S.tix = b.take<int32_t>(cap * S.tapecap);
   S.lam = b.take<double>(cap * (nreg > 0 ? nreg : 1));
   S.Csys = b.take<double>(cap * n);
@@ -277,13 +277,9 @@ k_tridiag_packed(const double* __restrict__ G, const double* __restrict__ y, con
   if (tid == 0) { B.scl[s] = W.sc[0]; B.st[s] = bad ? VI_ST_NONFINITE : VI_ST_OK; }
 }
 
-// Rotation tapes are interleaved over groups of 32 systems: entry t of system s sits at ((s / 32) cap + t) 32 + s % 32,
-// so the lanes of a warp that replay their tapes in lock step (k_replay) read consecutive 16-byte pairs.
-__device__ __forceinline__ int64_t tape_base(const SysBuf& B, int64_t s) { return (s >> 5) * (int64_t)B.tapecap * 32 + (s & 31); }
 __device__ __forceinline__ vi_tape tape_of(const SysBuf& B, int64_t s) {
-  const int64_t b = tape_base(B, s);
-  double* cs = B.tcs + 2 * b;
-  return vi_tape{{cs, 64}, {cs + 1, 64}, {B.tix + b, 32}, B.tapecap};
+  double* cs = B.tcs + s * (int64_t)B.tapecap * 2;
+  return vi_tape{{cs, 2}, {cs + 1, 2}, {B.tix + s * (int64_t)B.tapecap, 1}, B.tapecap};
 }
 
 // Tape replay, one THREAD per system (every lane does distinct work; a warp-per-system version spent
@@ -300,18 +296,14 @@ __device__ __forceinline__ void tape_replay(vi_svec w, const double2* __restrict
   constexpr int NB = VI_REPLAY_NB;
   double2 cur[NB], nxt[NB];
   int32_t icur[NB], inxt[NB];
-  // entry t of the lane's tape is at cs[32 t] / ix[32 t] (interleaved layout, see tape_base).  Both directions walk
-  // the ABSOLUTE index in lock step across the warp (backwards: nmax-1 .. 0, a lane whose tape is shorter applies
-  // identities first), so the loads of the lanes coalesce.
   auto fetch = [&](int32_t base, double2 (&c)[NB], int32_t (&id)[NB]) {
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
       const int32_t t = base + q;
-      const int32_t tt = (DIR > 0) ? t : nmax - 1 - t;
-      const bool ok = (tt >= 0) && (tt < nrot);
-      const int64_t off = ok ? (int64_t)tt * 32 : 0;
-      const double2 v = cs[off];
-      const int32_t code = ix[off];
+      const bool ok = t < nrot;
+      const int32_t tt = ok ? ((DIR > 0) ? t : nrot - 1 - t) : 0;
+      const double2 v = cs[tt];
+      const int32_t code = ix[tt];
       c[q] = ok ? v : make_double2(1.0, 0.0);
       id[q] = ok ? code : 0;
     }
@@ -324,7 +316,6 @@ __device__ __forceinline__ void tape_replay(vi_svec w, const double2* __restrict
   int upi = icur[0] >> 1;
   int upj = (icur[0] & 1) ? upi - 1 : upi + 1;
   double va = w[upi], vb = w[upj];
-  // (prefetch.global.L1 of the entries 32 rotations ahead was measured: slower, 8.94 vs 7.80 ms per 28416 systems)
   for (int32_t base = 0; base < nmax; base += NB) {
     fetch(base + NB, nxt, inxt);
 #pragma unroll
@@ -380,8 +371,8 @@ k_replay(int64_t nsys, SysBuf B, double rcond, int L) {
   if (nmax == 0 && !__any_sync(0xffffffffu, act)) return;
   if (act)
     for (int i = 0; i < n; ++i) w[i] = B.g[base + (int64_t)i * 32];
-  const double2* tcs = reinterpret_cast<const double2*>(B.tcs) + tape_base(B, sc);
-  const int32_t* tix = B.tix + tape_base(B, sc);
+  const double2* tcs = reinterpret_cast<const double2*>(B.tcs + sc * (int64_t)B.tapecap * 2);
+  const int32_t* tix = B.tix + sc * (int64_t)B.tapecap;
   if (lane < L) tape_replay<+1>(w, tcs, tix, nrot, nmax);
   if (act) {
     double lmax = 0.0;
@@ -514,8 +505,8 @@ __global__ void k_eigvec(int64_t s0, SysBuf B, double pinv_rtol, double* __restr
   // ---- Z: replay the tape backwards (vi_tape_apply_z order) ------------------------------------------------
   {
     const int32_t nrot = B.nrot[s];
-    const double2* gcs = reinterpret_cast<const double2*>(B.tcs) + tape_base(B, s);      // entry t at [32 t]
-    const int32_t* gix = B.tix + tape_base(B, s);
+    const double2* gcs = reinterpret_cast<const double2*>(B.tcs + s * (int64_t)B.tapecap * 2);
+    const int32_t* gix = B.tix + s * (int64_t)B.tapecap;
     double2* scs = reinterpret_cast<double2*>(stage);                  // [2][kEvTape]
     int32_t* six = reinterpret_cast<int32_t*>(scs + 2 * kEvTape);      // [2][kEvTape]
     const int nchunk = (nrot + kEvTape - 1) / kEvTape;
@@ -523,7 +514,7 @@ __global__ void k_eigvec(int64_t s0, SysBuf B, double pinv_rtol, double* __restr
       const int buf = c & 1;
       for (int t = i; t < kEvTape; t += nt) {
         const int32_t idx = nrot - 1 - (c * kEvTape + t);              // t-th rotation of this chunk, going backwards
-        if (idx >= 0) { cpa16(scs + buf * kEvTape + t, gcs + (int64_t)idx * 32); cpa4(six + buf * kEvTape + t, gix + (int64_t)idx * 32); }
+        if (idx >= 0) { cpa16(scs + buf * kEvTape + t, gcs + idx); cpa4(six + buf * kEvTape + t, gix + idx); }
       }
       cpa_commit();
     };

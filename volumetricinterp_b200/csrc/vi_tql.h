@@ -179,15 +179,14 @@ VI_HD int vi_tql(int n, vi_svec d, vi_svec e, vi_svec g, vi_tape tape, int32_t* 
 //     end), so the loops index d/e directly instead of through the PD/PE view;
 //   * running pointers instead of index arithmetic; (c, s) stored as one pair;
 //   * Z^T g is NOT accumulated here - the tape is replayed forwards by the apply kernel.
-// tape.c / tape.s must be the two halves of (c, s) pairs (c.p + 1 == s.p, equal strides >= 2).
+// tape.c / tape.s must be the two halves of interleaved (c, s) pairs (c.p + 1 == s.p, stride 2).
 VI_HD int vi_tql_values(int n, vi_svec d, vi_svec e, vi_tape tape, int32_t* nrot_out) {
   int32_t nrot = 0;
   int status = 0;
   int budget = 30 * n;
   const int64_t sd = d.stride, se = e.stride;
-  double* const cs = tape.c.p;        // pairs: cs[t * cstr] = c, cs[t * cstr + 1] = s
+  double* const cs = tape.c.p;        // pairs: cs[2t] = c, cs[2t+1] = s
   int32_t* const ix = tape.ix.p;
-  const int64_t cstr = tape.c.stride, istr = tape.ix.stride;
   const int32_t cap = tape.cap;
   int l1 = 0;
   while (l1 < n) {
@@ -286,9 +285,9 @@ VI_HD int vi_tql_values(int n, vi_svec d, vi_svec e, vi_tape tape, int32_t* nrot
           gg = c * r - b;
           dnext = di;
           if (nrot < cap) {
-            cs[cstr * nrot] = c;
-            cs[cstr * nrot + 1] = s;
-            ix[istr * nrot] = (pbase + pstep * i) * 2 + (rev ? 1 : 0);
+            cs[2 * (int64_t)nrot] = c;
+            cs[2 * (int64_t)nrot + 1] = s;
+            ix[nrot] = (pbase + pstep * i) * 2 + (rev ? 1 : 0);
           } else {
             status = 2;
           }
@@ -342,7 +341,6 @@ VI_HD int vi_tql_values_flat(int n, vi_svec d, vi_svec e, vi_tape tape, int32_t*
   const int64_t sd = d.stride, se = e.stride;
   double* const cs = tape.c.p;
   int32_t* const ix = tape.ix.p;
-  const int64_t cstr = tape.c.stride, istr = tape.ix.stride;
   const int32_t cap = tape.cap;
   int phase = active ? VI_QL_BLOCK : VI_QL_DONE;
   // block state
@@ -398,9 +396,9 @@ VI_HD int vi_tql_values_flat(int n, vi_svec d, vi_svec e, vi_tape tape, int32_t*
         if (i + 1 <= mm - 1 && vi_ql_negl(r2 * ri, dnew, D[(int64_t)(i + 2) * sd])) mt1 = i + 1;
         dnext = di;
         if (nrot < cap) {
-          cs[cstr * nrot] = c;
-          cs[cstr * nrot + 1] = s;
-          ix[istr * nrot] = (pbase + pstep * i) * 2 + (rev ? 1 : 0);
+          cs[2 * (int64_t)nrot] = c;
+          cs[2 * (int64_t)nrot + 1] = s;
+          ix[nrot] = (pbase + pstep * i) * 2 + (rev ? 1 : 0);
         } else {
           status = 2;
         }
