@@ -290,10 +290,7 @@ __device__ __forceinline__ vi_tape tape_of(const SysBuf& B, int64_t s) {
 template <int DIR>
 __device__ __forceinline__ void tape_replay(vi_svec w, const double2* __restrict__ cs,
                                             const int32_t* __restrict__ ix, int32_t nrot, int32_t nmax) {
-#ifndef VI_REPLAY_NB
-#define VI_REPLAY_NB 8
-#endif
-  constexpr int NB = VI_REPLAY_NB;
+  constexpr int NB = 8;
   double2 cur[NB], nxt[NB];
   int32_t icur[NB], inxt[NB];
   auto fetch = [&](int32_t base, double2 (&c)[NB], int32_t (&id)[NB]) {
@@ -309,35 +306,16 @@ __device__ __forceinline__ void tape_replay(vi_svec w, const double2* __restrict
     }
   };
   fetch(0, cur, icur);
-  // Consecutive rotations of a QL sweep share an element ((i, i+1) then (i-1, i)).  The shared one is carried in
-  // a register, and the other input of the NEXT rotation is loaded before THIS rotation's results are stored, so
-  // neither a shared-memory load nor a store-to-load round trip sits on the dependent chain (two FMA levels are
-  // left).  upi / upj, va / vb: indices and values of the inputs of the rotation about to be applied.
-  int upi = icur[0] >> 1;
-  int upj = (icur[0] & 1) ? upi - 1 : upi + 1;
-  double va = w[upi], vb = w[upj];
   for (int32_t base = 0; base < nmax; base += NB) {
     fetch(base + NB, nxt, inxt);
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
-      const int pi = upi, pj = upj;
-      const double a = va, bb = vb;
-      const int32_t ncode = (q + 1 < NB) ? icur[q + 1] : inxt[0];
-      const int npi = ncode >> 1;
-      const int npj = (ncode & 1) ? npi - 1 : npi + 1;
-      const bool a_new = (npi != pi) && (npi != pj);
-      const bool b_new = (npj != pi) && (npj != pj);
-      double na = 0.0, nb = 0.0;
-      if (a_new) na = w[npi];
-      if (b_new) nb = w[npj];
+      const int pi = icur[q] >> 1;
+      const int pj = (icur[q] & 1) ? pi - 1 : pi + 1;
       const double c = cur[q].x, sn = cur[q].y;
-      double opi, opj;
-      if (DIR > 0) { opj = sn * a + c * bb; opi = c * a - sn * bb; }
-      else { opi = c * a + sn * bb; opj = c * bb - sn * a; }
-      w[pi] = opi; w[pj] = opj;
-      va = a_new ? na : (npi == pi ? opi : opj);
-      vb = b_new ? nb : (npj == pi ? opi : opj);
-      upi = npi; upj = npj;
+      const double a = w[pi], bb = w[pj];
+      if (DIR > 0) { w[pj] = sn * a + c * bb; w[pi] = c * a - sn * bb; }
+      else { w[pi] = c * a + sn * bb; w[pj] = c * bb - sn * a; }
     }
 #pragma unroll
     for (int q = 0; q < NB; ++q) { cur[q] = nxt[q]; icur[q] = inxt[q]; }
