@@ -1,1 +1,3 @@
-for b in 1 2 3 4 6; do echo -n "batch $b: "; VI_TQL_BATCH=$b python tools/time_solver.py 28416 144 2>&1 | tail -1; done
+# scratch: the command the last experiment ran on the GPU box (see git log for the experiments)
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python bench.py --steps 2 --warmup 1 --e2e-steps 1 --no-cpu-baseline | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print(d['ms_per_step'], {k: round(v['ms_per_step'],1) for k,v in d['kernels'].items()})"
