@@ -398,6 +398,28 @@ __global__ void k_tql_smem(int64_t nsys, SysBuf B, int L, int iter_batch) {
   for (int i = 0; i < n; ++i) B.d[base + (int64_t)i * 32] = d[i];
 }
 
+// One system per warp (small Brent rounds, L = 1): lane 0 runs the plain nested-loop QL, which has less
+// per-rotation overhead than the per-lane state machine (that one only pays when several lanes share a warp).
+// Same arithmetic, bit-identical eigenvalues and tape (tests/test_host_math.py).
+__global__ void k_tql_single(int64_t nsys, SysBuf B) {
+  extern __shared__ __align__(16) double sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = B.n;
+  const int T = blockDim.x >> 5;
+  const int64_t s = (int64_t)blockIdx.x * T + warp;
+  if (lane != 0 || s >= nsys || B.st[s] != VI_ST_OK) return;
+  vi_svec d{sm + warp, T}, e{sm + (size_t)n * T + warp, T};
+  const int64_t base = ileave(s, n);
+  for (int i = 0; i < n; ++i) {
+    d[i] = B.d[base + (int64_t)i * 32];
+    e[i] = B.e[base + (int64_t)i * 32];
+  }
+  int32_t nrot = 0;
+  const int q = vi_tql_values(n, d, e, tape_of(B, s), &nrot);
+  if (q != 0) { B.st[s] = VI_ST_NOCONV; return; }
+  B.nrot[s] = nrot;
+  for (int i = 0; i < n; ++i) B.d[base + (int64_t)i * 32] = d[i];
+}
+
 // c = Q u, one WARP per system: the reflectors are applied cooperatively (coalesced V rows, shuffle-tree
 // dot products) to the vector k_replay left in B.g.
 constexpr int kApplyWarps = 8;
@@ -1226,6 +1248,20 @@ int run_ql(int64_t cnt, const SysBuf& B, cudaStream_t s, bool* split) {
   // lanes that reach the (expensive) sweep set-up wait until this many of the warp are there, or nobody rotates
   static const int batch_env = env_int("VI_TQL_BATCH", 0);
   const int iter_batch = batch_env > 0 ? batch_env : (L >= 32 ? 8 : 1);     // sparse lanes: waiting does not pay (measured)
+  // few systems per SM: one system per warp (k_tql_single), as many warps as there are systems.  Past ~16-24 warps per
+  // SM the single-lane form becomes issue-bound (a warp instruction serves one system) and the sparse-lane state
+  // machine wins again.
+  static const int single_max = env_int("VI_TQL_SINGLE_MAX", 16);
+  const int64_t per_sm = (cnt + sm_count() - 1) / sm_count();
+  if (per_sm <= single_max) {
+    int W1 = (int)per_sm;
+    if (W1 > 24) W1 = 24;      // 78 registers per thread
+    if (W1 < 1) W1 = 1;
+    const size_t smem1 = (size_t)W1 * per_sys;
+    VI_CUDA(cudaFuncSetAttribute(k_tql_single, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    VI_KERNEL(VI_K_TQL, s, k_tql_single<<<blocks(cnt, W1), W1 * 32, smem1, s>>>(cnt, B));
+    return VI_OK;
+  }
   VI_KERNEL(VI_K_TQL, s, k_tql_smem<<<blocks(cnt, T), W * 32, smem, s>>>(cnt, B, L, iter_batch));
   return VI_OK;
 }
