@@ -13,6 +13,7 @@ tabs = subprocess.run([sys.executable, "tools/summarize_profiles.py", "gpurun_ou
                       capture_output=True, text=True, check=True).stdout.split("\n\n")
 d = json.load(open("profiles/r01_bench_default.json"))
 d2 = json.load(open("profiles/r01_bench_2gpu.json"))
+d8 = json.load(open("profiles/r01_bench_8gpu.json"))
 ref = json.load(open("profiles/r01_bench_reference.json"))
 launch = [l for l in tabs[0].split("\n") if not l.startswith("| at::")]
 k = d["kernels"]
@@ -36,6 +37,7 @@ tridiagonalisation, sparse-lane QL / replay, normal equations v3, staged eigenve
 `python bench.py --impl reference` -> r01_bench_reference.json)
 
 * fitted records/s, device-resident inputs: **{d['value']:.0f}** ({d['ms_per_step']:.0f} ms per 10 000-record step, covariance included); 2 GPUs: **{d2['value']:.0f}** (weak scaling, {d2['ms_per_step']:.0f} ms per step, NCCL all-gather of the coefficients inside the timed region)
+* 8 GPUs (`r01_bench_8gpu.json`, 2 steps): **{d8['value']:.0f}** records/s device-resident ({d8['ms_per_step']:.0f} ms per step: {100 * d8['value'] / (8 * d['value']):.0f} % of 8 x the single-GPU rate), {d8['e2e']['value']:.0f} end to end (eight ranks share 16 host cores and the host's PCIe / memory bandwidth for 13 GB of covariance per step)
 * end to end (pinned host buffers -> numpy): **{d['e2e']['value']:.0f}** records/s, H2D {d['e2e']['h2d_bytes_per_step'] / 1e6:.0f} MB + D2H {d['e2e']['d2h_bytes_per_step'] / 1e6:.0f} MB per step; 2 GPUs: {d2['e2e']['value']:.0f}
 * reference algorithm on the box's host cores ({d['cpu_baseline']['cores']} processes): {d['cpu_baseline']['value']:.3f} records/s in the same run, {ref['value']:.3f} in the reference arm
 * clocks during the timed region: {d['clocks']}
