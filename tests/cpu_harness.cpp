@@ -12,6 +12,7 @@
 #include "../volumetricinterp_b200/csrc/vi_tridiag.h"
 #include "../volumetricinterp_b200/csrc/vi_tridiag_packed.h"
 #include "../volumetricinterp_b200/csrc/vi_nm.h"
+#include "../volumetricinterp_b200/csrc/vi_ne_split.h"
 
 extern "C" {
 
@@ -229,6 +230,18 @@ int h_system_solve_packed(int n, const double* G, const double* y, const double*
   std::memcpy(C, g.data(), n * sizeof(double));
   return 0;
 }
+
+// Work split of k_ne_dmma3: fills unit (mi | ni << 8 | flags), wbeg / wend per warp; returns 1 if it fits.
+int h_ne3_split(int N, int DT, int* nunits, int* uinfo, int* wbeg, int* wend) {
+  NeSplit sp;
+  const int mt = (N + 15) / 16;
+  if (!ne3_split(N, mt, DT, sp)) return 0;
+  *nunits = sp.nunits;
+  for (int i = 0; i < sp.nunits; ++i) uinfo[i] = sp.uinfo[i];
+  for (int w = 0; w < kW3; ++w) { wbeg[w] = sp.wbeg[w]; wend[w] = sp.wend[w]; }
+  return 1;
+}
+int h_ne3_warps() { return kW3; }
 
 int h_sizeof_shl_params() { return (int)sizeof(vi_shl_params); }
 }

@@ -136,6 +136,44 @@ def test_packed_tridiagonalisation_random(harness, n):
     assert np.allclose(np.abs(ee), np.abs(ee2), rtol=0, atol=1e-12 * np.abs(dd2).max())
 
 
+@pytest.mark.parametrize("N", [1, 8, 12, 16, 27, 48, 100, 144, 150, 160])
+def test_normal_equation_work_split(harness, N):
+    """k_ne_dmma3's units (lower-triangle tiles + one diagonal unit per row block) are dealt to the 16 warps exactly
+    once, at most 7 per warp, contiguously in (row block, tile) order, with balanced tensor sub-partitions."""
+    W = harness.h_ne3_warps()
+    uinfo = (C.c_int * 96)()
+    wbeg, wend = (C.c_int * W)(), (C.c_int * W)()
+    nunits = C.c_int(0)
+    ok = harness.h_ne3_split(N, 7, C.byref(nunits), uinfo, wbeg, wend)
+    mt = (N + 15) // 16
+    if mt * (mt + 1) > 96:          # does not fit the unit table: the launcher falls back to version 2
+        assert ok == 0
+        return
+    assert ok == 1 and nunits.value == mt * (mt + 1)
+    # every lower-triangle element is covered by exactly one unit: full tiles cover rows 16 mi.., columns 8 ni..;
+    # diagonal units the lower 8 rows of tile (mi, 2 mi + 1)
+    cover = np.zeros((16 * mt, 16 * mt), dtype=int)
+    seen = np.zeros(nunits.value, dtype=int)
+    weights = np.zeros(W)
+    for w in range(W):
+        assert 0 <= wbeg[w] <= wend[w] <= nunits.value and wend[w] - wbeg[w] <= 7
+        for u in range(wbeg[w], wend[w]):
+            seen[u] += 1
+            mi, ni, diag, half = uinfo[u] & 255, (uinfo[u] >> 8) & 255, bool(uinfo[u] & (1 << 16)), bool(uinfo[u] & (1 << 17))
+            weights[w] += 3 if diag else 4
+            if not diag:
+                cover[16 * mi:16 * mi + 16, 8 * ni:8 * ni + 8] += 1
+            else:
+                assert ni == 2 * mi + 1 and half == (8 * ni < N)
+                if half:
+                    cover[16 * mi + 8:16 * mi + 16, 8 * ni:8 * ni + 8] += 1
+    assert (seen == 1).all()
+    ii, kk = np.tril_indices(N)
+    assert (cover[ii, kk] == 1).all()
+    sp = [weights[p::4].sum() for p in range(4)]
+    assert max(sp) - min(sp) <= 8
+
+
 def test_nonfinite_system_is_flagged(harness):
     G = np.eye(4)
     G[1, 2] = np.inf
