@@ -243,5 +243,19 @@ int h_ne3_split(int N, int DT, int* nunits, int* uinfo, int* wbeg, int* wend) {
 }
 int h_ne3_warps() { return kW3; }
 
+// Packed-triangle layout of k_tridiag_packed (vi_tridiag_packed.h)
+int h_trp_geometry(int n, int* npad, int* noct, int* nwarp, int* xdoubles, int* ntiles) {
+  *npad = vi_trp_npad(n); *noct = vi_trp_noct(n); *nwarp = vi_trp_nwarp(n);
+  *xdoubles = vi_trp_xdoubles(n); *ntiles = vi_trp_ntiles(n);
+  return vi_trp_doubles(n);
+}
+int h_trp_idx(int n, int i, int c) { return vi_trp_idx(vi_trp_npad(n), i, c); }
+int h_trp_tile_slot(int n, int ip, int q) { return vi_trp_tileoff(vi_trp_npad(n), q) + ip - 4 * q; }
+int h_trp_octet_of(int n, int warp, int slot, int a) {
+  vi_trp_ws W;
+  W.n = n; W.npad = vi_trp_npad(n); W.noct = vi_trp_noct(n); W.nwarp = vi_trp_nwarp(n);
+  return vi_trp_octet_of(W, warp, slot, a);
+}
+
 int h_sizeof_shl_params() { return (int)sizeof(vi_shl_params); }
 }

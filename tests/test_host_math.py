@@ -174,6 +174,28 @@ def test_normal_equation_work_split(harness, N):
     assert max(sp) - min(sp) <= 8
 
 
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 27, 64, 100, 144, 150, 208])
+def test_packed_layout_and_octet_assignment(harness, n):
+    """Storage map of the packed tridiagonalisation: every stored position (i >= 8 floor(c / 8)) has its own slot and
+    the slots fill the array exactly; tile slots likewise; and at every step each active octet belongs to exactly
+    one (warp, slot)."""
+    npad, noct, nwarp, xd, nt = (C.c_int(0) for _ in range(5))
+    total = harness.h_trp_geometry(n, *(C.byref(v) for v in (npad, noct, nwarp, xd, nt)))
+    npad, noct, nwarp, xd, nt = (v.value for v in (npad, noct, nwarp, xd, nt))
+    assert npad % 8 == 0 and npad >= n and noct == npad // 8 and total >= xd + 2 * nt
+    idx = [harness.h_trp_idx(n, i, c) for c in range(npad) for i in range(8 * (c // 8), npad)]
+    assert sorted(idx) == list(range(xd))
+    # the two rows of a row pair are adjacent (one 128-bit access) and columns are contiguous in i
+    assert all(harness.h_trp_idx(n, i + 1, c) == harness.h_trp_idx(n, i, c) + 1
+               for c in range(0, npad, 5) for i in range(8 * (c // 8), npad - 1))
+    slots = [harness.h_trp_tile_slot(n, ip, q) for q in range(noct) for ip in range(4 * q, npad // 2)]
+    assert sorted(slots) == list(range(nt))
+    for a in range(noct):
+        got = [harness.h_trp_octet_of(n, w, sl, a) for w in range(nwarp) for sl in (0, 1)]
+        got = sorted(q for q in got if q >= 0)
+        assert got == list(range(a, noct))
+
+
 def test_nonfinite_system_is_flagged(harness):
     G = np.eye(4)
     G[1, 2] = np.inf
