@@ -76,6 +76,12 @@ const char* vi_last_error(void);
 int vi_basis_sphharmlag(const double* lat, const double* lon, const double* alt, int64_t npts,
                         const vi_shl_params* params, double* A, double* At, void* stream);
 
+/* models/sphharmlag.py:148-184 (grad_basis): gradient of every basis function along (z-hat, theta-hat,
+ * phi-hat) of the model coordinates.  out: npts x 3 x N row-major, the shape the reference returns
+ * (np.array(Ag).T).  Not called on the reference's fit / Estimate path. */
+int vi_grad_basis_sphharmlag(const double* lat, const double* lon, const double* alt, int64_t npts,
+                             const vi_shl_params* params, double* out, void* stream);
+
 /* models/radbasfun.py:83-112 (+ transform_coords :232-256). centers: N x 3 ECEF metres (device). */
 int vi_basis_radbasfun(const double* lat, const double* lon, const double* alt, int64_t npts,
                        const double* centers, int32_t N, double eps, double* A, double* At, void* stream);

@@ -25,6 +25,17 @@ void h_shl_rows(const vi_shl_params* P, const double* lat, const double* lon, co
   }
 }
 
+void h_shl_grad_rows(const vi_shl_params* P, const double* lat, const double* lon, const double* alt,
+                     int64_t npts, double* out) {
+  const int N = P->maxk * P->maxl * P->maxl;
+  for (int64_t p = 0; p < npts; ++p) {
+    double* o = out + p * 3 * (int64_t)N;
+    vi_shl_grad_row(*P, lat[p], lon[p], alt[p], [&](int n, double gz, double gt, double gp) {
+      o[n] = gz; o[N + n] = gt; o[2 * N + n] = gp;
+    });
+  }
+}
+
 void h_shl_coords(const vi_shl_params* P, const double* lat, const double* lon, const double* alt,
                   int64_t npts, double* z, double* th, double* ph) {
   for (int64_t p = 0; p < npts; ++p) vi_shl_coords(*P, lat[p], lon[p], alt[p], z + p, th + p, ph + p);

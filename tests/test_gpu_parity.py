@@ -43,6 +43,26 @@ def test_basis_kernel_matches_reference(cuda, name):
     assert B.shape == (2, 3, N) and np.array_equal(B.reshape(6, N), A[:6])
 
 
+@pytest.mark.parametrize("case", ["g12", "g144"])
+def test_grad_basis_kernel_matches_reference(cuda, case):
+    """vi_grad_basis_sphharmlag against the reference's grad_basis: component- and
+    column-relative 2e-12, shape (npoints, 3, nbasis) as the reference returns it; device result == the CPU
+    harness of the same header is not required, only the reference bar."""
+    import io
+    import os
+    from conftest import GOLDEN
+    from volumetricinterp_b200.models import sphharmlag
+    g = np.load(os.path.join(GOLDEN, "grad_basis.npz"))
+    m = sphharmlag.Model(io.StringIO(str(g[case + "_config_text"])))
+    out = m.grad_basis(g["lat"], g["lon"], g["alt"])
+    ref = g[case + "_grad"]
+    assert out.shape == ref.shape
+    for comp in range(3):
+        for c in range(m.nbasis):
+            r = ref[:, comp, c]
+            assert np.max(np.abs(out[:, comp, c] - r)) <= 2e-12 * max(np.abs(r).max(), 1e-300), (comp, c)
+
+
 # ------------------------------------------------------------------ K2 normal equations
 @pytest.mark.parametrize("name", ["lo8", "lo12", "mid27", "c1_144", "rbf27"])
 def test_normal_equations_strict_bit_exact_and_fast_close(cuda, name):

@@ -3,13 +3,14 @@ vi_brent.h) compiled for the CPU by the TEST-ONLY harness and checked against th
 scipy and LAPACK.  The product never loads this harness; it has no CPU path."""
 import ctypes as C
 import io
+import os
 
 import numpy as np
 import pytest
 import scipy.linalg
 import scipy.optimize
 
-from conftest import dptr, load_golden, product_model
+from conftest import GOLDEN, dptr, load_golden, product_model
 import ref_port as rp
 
 EPS = np.finfo(float).eps
@@ -34,6 +35,27 @@ def test_sphharmlag_rows_match_reference_basis(harness, name):
         ref = g["A"][:, c]
         tol = 2e-12 * max(np.abs(ref).max(), 1e-300)
         assert np.max(np.abs(A[:, c] - ref)) <= tol, (c, np.max(np.abs(A[:, c] - ref)), np.abs(ref).max())
+
+
+@pytest.mark.parametrize("case", ["g12", "g144"])
+def test_sphharmlag_gradient_rows_match_reference(harness, case):
+    """vi_shl_grad_row (csrc/vi_math.h) against the reference's own grad_basis (sphharmlag.py:148-184; fixture
+    written by oracle/make_golden_grad.py from the unmodified reference): component- and column-relative 2e-12."""
+    import io
+    from volumetricinterp_b200.models import sphharmlag
+    g = np.load(os.path.join(GOLDEN, "grad_basis.npz"))
+    m = sphharmlag.Model(io.StringIO(str(g[case + "_config_text"])))
+    P = m.params()
+    n = g["lat"].size
+    out = np.zeros((n, 3, m.nbasis))
+    harness.h_shl_grad_rows(C.byref(P), dptr(g["lat"]), dptr(g["lon"]), dptr(g["alt"]), C.c_int64(n), dptr(out))
+    ref = g[case + "_grad"]
+    assert out.shape == ref.shape
+    for comp in range(3):
+        for c in range(m.nbasis):
+            r = ref[:, comp, c]
+            tol = 2e-12 * max(np.abs(r).max(), 1e-300)
+            assert np.max(np.abs(out[:, comp, c] - r)) <= tol, (comp, c, np.max(np.abs(out[:, comp, c] - r)), np.abs(r).max())
 
 
 def test_radbasfun_rows_match_reference_basis(harness):

@@ -18,6 +18,20 @@ def test_basis_bit_identical(name):
     assert np.array_equal(A, g["A"])
 
 
+@pytest.mark.parametrize("case", ["g12", "g144"])
+def test_grad_basis_bit_identical(case):
+    """oracle grad_basis == the unmodified reference's (fixture from oracle/make_golden_grad.py)."""
+    import json
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "grad_basis.npz"))
+    mk = json.loads(str(g[case + "_model_keys"]))
+    m = rp.SphHarmLag(mk["MAXK"], mk["MAXL"], mk["CAP_LIM"], 78, 262)
+    assert np.array_equal(m.grad_basis(g["lat"], g["lon"], g["alt"]), g[case + "_grad"])
+    # and the value fixture of the same points agrees with the basis (ties the two fixtures together)
+    assert np.array_equal(m.basis(g["lat"], g["lon"], g["alt"]), g[case + "_A"])
+
+
 @pytest.mark.parametrize("name", CASES)
 def test_fit_bit_identical(name):
     g = load_golden(name)

@@ -46,6 +46,7 @@ _i32, _i64, _dbl, _ptr = C.c_int32, C.c_int64, C.c_double, C.c_void_p
 _shl = C.POINTER(ShlParams)
 SIGNATURES = {
     "vi_basis_sphharmlag": [_ptr, _ptr, _ptr, _i64, _shl, _ptr, _ptr, _ptr],
+    "vi_grad_basis_sphharmlag": [_ptr, _ptr, _ptr, _i64, _shl, _ptr, _ptr],
     "vi_basis_radbasfun": [_ptr, _ptr, _ptr, _i64, _ptr, _i32, _dbl, _ptr, _ptr, _ptr],
     "vi_normal_eq_batched": [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "vi_fit_workspace_bytes": [_i32, _i32, _i32, _i32, _i64, C.POINTER(_i64)],

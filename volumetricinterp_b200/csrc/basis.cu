@@ -1,6 +1,7 @@
 // K1 (design matrix) and K4 (Estimate) kernels for both model plug-ins.
 //
 //   vi_basis_sphharmlag   <- models/sphharmlag.py:118-145 (+ transform_coord :324-359)
+//   vi_grad_basis_sphharmlag <- models/sphharmlag.py:148-184
 //   vi_basis_radbasfun    <- models/radbasfun.py:83-112
 //   vi_estimate_*         <- estimate.py:113-121 (basis . C, NaN outside the convex hull;
 //                            hull test = facet half-spaces of the saved hull, estimate.py:153-178)
@@ -278,7 +279,31 @@ int check_shl(const vi_shl_params* P) {
   return VI_OK;
 }
 
+// Gradient of the basis, out[p][comp][n] (npts x 3 x N, the shape the reference returns): one thread per point.
+__global__ void __launch_bounds__(kThreads)
+k_grad_shl(const double* __restrict__ lat, const double* __restrict__ lon, const double* __restrict__ alt,
+           int64_t npts, const __grid_constant__ vi_shl_params P, double* __restrict__ out) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npts) return;
+  const int N = P.maxk * P.maxl * P.maxl;
+  double* o = out + p * 3 * (int64_t)N;
+  vi_shl_grad_row(P, lat[p], lon[p], alt[p], [&](int n, double gz, double gt, double gp) {
+    o[n] = gz; o[N + n] = gt; o[2 * N + n] = gp;
+  });
+}
+
 }  // namespace
+
+extern "C" int vi_grad_basis_sphharmlag(const double* lat, const double* lon, const double* alt, int64_t npts,
+                                        const vi_shl_params* params, double* out, void* stream) {
+  if (int rc = check_shl(params)) return rc;
+  VI_REQUIRE(npts >= 0 && (out != nullptr || npts == 0), "bad arguments");
+  if (npts == 0) return VI_OK;
+  unsigned grid = (unsigned)((npts + kThreads - 1) / kThreads);
+  VI_KERNEL(VI_K_BASIS, vi_stream(stream), k_grad_shl<<<grid, kThreads, 0, vi_stream(stream)>>>(lat, lon, alt, npts, *params, out));
+  VI_LAUNCH_CHECK();
+  return VI_OK;
+}
 
 extern "C" int vi_basis_sphharmlag(const double* lat, const double* lon, const double* alt, int64_t npts,
                                    const vi_shl_params* params, double* A, double* At, void* stream) {

@@ -13,6 +13,7 @@
 //   Laguerre L_k                scipy.special.eval_laguerre (models/sphharmlag.py:141)
 //   Legendre P_v^m, real v      scipy.special.lpmv = Zhang & Jin LPMV/LPMV0 (sphharmlag.py:141)
 //   azimuth A_vm, K_vm          models/sphharmlag.py:278-281, 318-321
+//   gradient of the basis       models/sphharmlag.py:148-184 (dAz :298-301, scipy eval_genlaguerre)
 //   Gaussian RBF                models/radbasfun.py:102-107
 #pragma once
 #include <math.h>
@@ -154,6 +155,73 @@ VI_HD void vi_shl_row(const vi_shl_params& P, double lat, double lon, double alt
         double azs = kv * sin(am * phi);
         int r_neg = l * (l + 1) - am;
         for (int k = 0; k < P.maxk; ++k) emit(k * L2 + r_neg, ez * lag[k] * azs * pneg);
+      }
+    }
+  }
+}
+
+// scipy eval_genlaguerre(n, 1, x) for n = -1 .. maxk-2 (eval_genlaguerre_l: the eval_laguerre recurrence with
+// alpha = 1, times binom(n + 1, n) = n + 1).  out[k] = L^{(1)}_{k-1}(x), out[0] = 0 (scipy returns 0 for n < 0).
+VI_HD void vi_genlaguerre1_all(int maxk, double x, double* out) {
+  out[0] = 0.0;
+  if (maxk > 1) out[1] = 1.0;            // n = 0
+  if (maxk > 2) out[2] = -x + 1.0 + 1.0; // n = 1: -x + alpha + 1
+  double d = -x / 2.0;                   // -x / (alpha + 1)
+  double p = d + 1.0;
+  for (int kk = 0; kk + 3 < maxk; ++kk) {
+    double k = kk + 1.0;
+    d = -x / (k + 2.0) * p + (k / (k + 2.0)) * d;
+    p = d + p;
+    out[kk + 3] = (kk + 3.0) * p;        // n = kk + 2: binom(n + 1, n) = n + 1
+  }
+}
+
+// One row of the GRADIENT of the sphharmlag basis (sphharmlag.py:148-184), components along z-hat, theta-hat,
+// phi-hat:
+//   gz = -0.5 e (L_k + 2 L^{(1)}_{k-1}) P_v^m A_vm 100 / RE
+//   gt = e L_k (-(v+1) x P_v^m + (v-m+1) P_{v+1}^m) A_vm / (y (z/100 + 1) RE)
+//   gp = e L_k P_v^m A'_vm / (y (z/100 + 1) RE)
+// with x = cos theta, y = sin theta, e = exp(-z/2), m signed.  `emit(n, gz, gt, gp)` receives every basis index.
+// P_{v+1}^{-|m|} uses Gamma(v-|m|+2)/Gamma(v+|m|+2) = g1 (v-|m|+1) / (g2 (v+|m|+1)).
+template <class Emit>
+VI_HD void vi_shl_grad_row(const vi_shl_params& P, double lat, double lon, double alt, Emit emit) {
+  double z, theta, phi;
+  vi_shl_coords(P, lat, lon, alt, &z, &theta, &phi);
+  double lag[VI_MAXK_MAX], lag1[VI_MAXK_MAX];
+  vi_laguerre_all(P.maxk, z, lag);
+  vi_genlaguerre1_all(P.maxk, z, lag1);
+  const double e = exp(-0.5 * z);
+  const double x = cos(theta), y = sin(theta);
+  const double den = y * (z / 100.0 + 1.0) * VI_RE;
+  const int L2 = P.maxl * P.maxl;
+  for (int l = 0; l < P.maxl; ++l) {
+    const double v = P.nu[l];
+    for (int am = 0; am <= l; ++am) {
+      const double ppos = vi_lpmv_pos(v, am, x);
+      const double ppos1 = vi_lpmv_pos(v + 1.0, am, x);
+      const double kv = P.kvm[l][am];
+      const double cs = cos(am * phi), sn = sin(am * phi);
+      {
+        // m = +am: A = K cos(m phi), A' = -m K sin(m phi)
+        const double a = kv * cs, da = -1.0 * am * kv * sn;
+        const double tt = -(v + 1.0) * x * ppos + (v - am + 1.0) * ppos1;
+        const int r = l * (l + 1) + am;
+        for (int k = 0; k < P.maxk; ++k)
+          emit(k * L2 + r, -0.5 * e * (lag[k] + 2.0 * lag1[k]) * ppos * a * 100.0 / VI_RE,
+               e * lag[k] * tt * a / den, e * lag[k] * ppos * da / den);
+      }
+      if (am > 0) {
+        // m = -am: A = K sin(|m| phi), A' = |m| K cos(|m| phi); negative-order Legendre by reflection
+        const double sg = (am & 1) ? -1.0 : 1.0;
+        double pneg = ppos, pneg1 = ppos1;
+        if (fabs(ppos) < 1.0e300) pneg = ppos * P.g1[l][am] / P.g2[l][am] * sg;
+        if (fabs(ppos1) < 1.0e300) pneg1 = ppos1 * (P.g1[l][am] * (v - am + 1.0)) / (P.g2[l][am] * (v + am + 1.0)) * sg;
+        const double a = kv * sn, da = am * kv * cs;
+        const double tt = -(v + 1.0) * x * pneg + (v + am + 1.0) * pneg1;
+        const int r = l * (l + 1) - am;
+        for (int k = 0; k < P.maxk; ++k)
+          emit(k * L2 + r, -0.5 * e * (lag[k] + 2.0 * lag1[k]) * pneg * a * 100.0 / VI_RE,
+               e * lag[k] * tt * a / den, e * lag[k] * pneg * da / den);
       }
     }
   }

@@ -110,6 +110,26 @@ class Model(object):
         A = self.basis_device(to(gdlat), to(gdlon), to(gdalt))
         return A.cpu().numpy().reshape(gdlat.shape + (self.nbasis,))
 
+    def grad_basis_device(self, lat, lon, alt, out=None, stream=None):
+        """Gradient of the basis on the device: (npts, 3, N), components along z-hat, theta-hat, phi-hat."""
+        import torch
+        npts = lat.numel()
+        if out is None:
+            out = torch.empty((npts, 3, self.nbasis), dtype=torch.float64, device=lat.device)
+        s = stream if stream is not None else torch.cuda.current_stream(lat.device).cuda_stream
+        _native.check(_native.lib().vi_grad_basis_sphharmlag(
+            lat.data_ptr(), lon.data_ptr(), alt.data_ptr(), npts, C.byref(self.params()), out.data_ptr(), s))
+        return out
+
+    def grad_basis(self, gdlat, gdlon, gdalt):
+        """Drop-in for reference sphharmlag.py:148-184 (numpy in, numpy out; 1-D inputs as the reference's own
+        transform_coord requires there).  Shape (npoints, 3, nbasis), as `np.array(Ag).T` in the reference."""
+        import torch
+        gdlat, gdlon, gdalt = (np.asarray(a, dtype=np.float64) for a in (gdlat, gdlon, gdalt))
+        dev = torch.device('cuda', torch.cuda.current_device())
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a.ravel())).to(dev)
+        return self.grad_basis_device(to(gdlat), to(gdlon), to(gdalt)).cpu().numpy()
+
     # ---- regularisation matrices (host, config-only; SURVEY §8-f rank 2) ---
     def _assemble(self, zfun, tfun):
         """N(N+1)/2 triple products of three 1-D QUADPACK integrals (reference
