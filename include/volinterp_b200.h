@@ -109,18 +109,37 @@ int vi_solve_batched(const double* G, const double* y, const int32_t* rec, const
                      double* C, int32_t* rank, int32_t* status,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
+/* interpolate.py:462-467: vi_solve_batched plus the covariance dC_s = H X0 H, H = pinv(X_s) (cut-off
+ * N eps max|eigenvalue| = scipy.linalg.pinv's rule), X0 = G[rec_s] unregularised.  dC: S x N x N device (NULL: as
+ * vi_solve_batched).  The workspace must hold the covariance scratch too (vi_fit_workspace_bytes with R = S). */
+int vi_solve_cov_batched(const double* G, const double* y, const int32_t* rec, const double* regmats,
+                         const double* lam, int64_t S, int32_t N, int32_t nreg, double rcond,
+                         double* C, double* dC, int32_t* rank, int32_t* status,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
 /* interpolate.py:555-569 for R records: find_reg_param (:97-147, chi2 :152-218, chi2objfunct
  * :220-261), NaN-record rule (:558-563), final eval_C (:566) and chi^2 (:569).
  * At: N x P (transposed design matrix); A: P x N (row-major; needed by VI_METHOD_GCV only, else may be
  * NULL); Wm/bm: masked weights/data from vi_normal_eq_batched.
  * regmats: nreg x N x N.  Outputs: C R x N, dC R x N x N (may be NULL), chi2 R, lam R x nreg,
- * rank R, status R, nsolve (optional, 1 int64: number of eigen-systems solved). */
+ * rank R, status R, nsolve (optional, 1 int64: number of eigen-systems solved).
+ * dC may also be a PINNED HOST pointer (cudaHostAlloc / cudaHostRegister): the covariance is then produced in chunks
+ * of 512 records into a device ring and copied out on a side stream while the next chunk is computed (the R x N x N
+ * block, 1.66 GB at R = 10 k and N = 144, never sits in HBM); `stream` is made to wait for the last copy. */
 int vi_fit_batched(const double* At, const double* A, const double* Wm, const double* bm,
                    const double* G, const double* y, const int32_t* npts,
                    int32_t R, int32_t P, int32_t N,
                    const double* regmats, int32_t nreg, int32_t method,
                    double* C, double* dC, double* chi2, double* lam, int32_t* rank, int32_t* status,
                    int64_t* nsolve, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Diagnostics of the last VI_METHOD_CHI2 search that ran in `workspace` (same R, P, nreg as that call):
+ * table U x VI_NALPHA = chi2(10^-k) as the decade walk of interpolate.py:180-207 saw it (entries the walk
+ * never read are NaN), nu U = len(b) * scale factor of the bracket (interpolate.py:175,181), k_lo U = decade
+ * of the bracket's lower end (alpha = -k_lo; -1 when none), kdone U = distinct table entries evaluated.
+ * U = R * nreg; any output may be NULL.  Device pointers. */
+int vi_fit_search_trace(const void* workspace, int64_t workspace_bytes, int32_t R, int32_t P, int32_t nreg,
+                        double* table, double* nu, int32_t* k_lo, int32_t* kdone, void* stream);
 
 /* estimate.py:113-121: out[r][p] = sum_n basis(p)[n] * C[r][n], NaN outside the hull.
  * C: Rsel x N (device).  hull_eq: F x 4 facet equations [n|d] of ConvexHull(hull_vert) (inside iff

@@ -51,8 +51,10 @@ SIGNATURES = {
     "vi_normal_eq_batched": [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "vi_fit_workspace_bytes": [_i32, _i32, _i32, _i32, _i64, C.POINTER(_i64)],
     "vi_solve_batched": [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _dbl, _ptr, _ptr, _ptr, _ptr, _i64, _ptr],
+    "vi_solve_cov_batched": [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i32, _i32, _dbl, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr],
     "vi_fit_batched": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _ptr, _i32, _i32,
                        _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, C.POINTER(_i64), _ptr, _i64, _ptr],
+    "vi_fit_search_trace": [_ptr, _i64, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr],
     "vi_estimate_sphharmlag": [_ptr, _ptr, _ptr, _i64, _shl, _ptr, _i32, _ptr, _i32, _ptr, _ptr],
     "vi_estimate_radbasfun": [_ptr, _ptr, _ptr, _i64, _ptr, _i32, _dbl, _ptr, _i32, _ptr, _i32, _ptr, _ptr],
     "vi_fit_host": [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _ptr, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],

@@ -109,6 +109,27 @@ void sysbuf_carve(Bump& b, SysBuf& S, int64_t cap, int n, int nreg, int P) {
 
 constexpr int kCovChunk = 512;     // records whose eigenvector / H / T scratch is held at once
 
+// side stream + events of the covariance host sink (per device; created on first use, kept for the process)
+struct CovSink {
+  cudaStream_t copy = nullptr;
+  cudaEvent_t ready[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
+  int init() {
+    if (copy) return VI_OK;
+    VI_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      VI_CUDA(cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming));
+      VI_CUDA(cudaEventCreateWithFlags(&drained[i], cudaEventDisableTiming));
+    }
+    return VI_OK;
+  }
+};
+CovSink& cov_sink() {
+  static CovSink sinks[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return sinks[(dev >= 0 && dev < 64) ? dev : 0];
+}
+
 struct UnitBuf {      // one search unit = (record, regulariser)
   double* table;      // U x VI_NALPHA
   vi_brent* br;       // U
@@ -124,6 +145,7 @@ struct UnitBuf {      // one search unit = (record, regulariser)
   double* fsum;       // U   GCV objective being accumulated
   double* alpha;      // U   abscissa under evaluation
   int32_t* count;     // 1
+  int32_t* klo;       // U   bracket decade found by the walk (table index of its lower end; -1: none)
 };
 
 void unit_carve(Bump& b, UnitBuf& Ub, int64_t U) {
@@ -141,11 +163,13 @@ void unit_carve(Bump& b, UnitBuf& Ub, int64_t U) {
   Ub.fsum = b.take<double>(U);
   Ub.alpha = b.take<double>(U);
   Ub.count = b.take<int32_t>(8);
+  Ub.klo = b.take<int32_t>(U);
 }
 
 int64_t cov_scratch_bytes(int64_t R, int n) {
   int64_t cc = R < kCovChunk ? R : kCovChunk;
-  return (3 * cc * (int64_t)n * n + cc * n) * (int64_t)sizeof(double) + 4096;
+  // E, H, T and a two-chunk ring for the covariance when it is streamed to a pinned host buffer
+  return (5 * cc * (int64_t)n * n + cc * n) * (int64_t)sizeof(double) + 8192;
 }
 
 int64_t gcv_scratch_bytes(int64_t R, int64_t P, int64_t U) { return R * P * 4 + R * 4 + U * 8 + 4096; }
@@ -158,13 +182,31 @@ int64_t per_system_bytes(int n, int nreg, int P) {
 }
 
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  static int cache[64] = {0};          // per device ordinal: a process may drive several (different) GPUs
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = (dev >= 0 && dev < 64) ? dev : 0;
+  if (cache[slot] == 0) {
+    int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[slot] = n;
   }
-  return n;
+  return cache[slot];
+}
+
+// Scratch budget for the in-flight eigen-systems when the caller does not size the batch itself: half of the
+// device memory that is free right now, at most 32 GiB (VI_SCRATCH_GIB overrides the ceiling).
+int64_t scratch_budget_bytes() {
+  int64_t ceil_gib = 32;
+  if (const char* e = getenv("VI_SCRATCH_GIB")) { long v = atol(e); if (v >= 1) ceil_gib = v; }
+  int64_t budget = ceil_gib << 30;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > 0) {
+    const int64_t half = (int64_t)(free_b / 2);
+    if (half < budget) budget = half;
+  }
+  if (budget < ((int64_t)256 << 20)) budget = (int64_t)256 << 20;
+  return budget;
 }
 
 int env_int(const char* name, int dflt) {
@@ -188,7 +230,7 @@ int64_t ql_wave(int n) { return (int64_t)sm_count() * ql_warps(n) * ql_lanes_max
 
 int64_t default_system_cap(int64_t wanted, int n, int nreg, int P) {
   int64_t per = per_system_bytes(n, nreg, P);
-  int64_t budget = (int64_t)32 << 30;   // 32 GiB of scratch by default (of 180 GB)
+  int64_t budget = scratch_budget_bytes();
   int64_t cap = budget / per;
   // whole waves of the QL kernel (thread per system, residency bounded by 2n doubles of shared memory per
   // system): a chunk of 1.1 waves would cost two
@@ -492,14 +534,18 @@ __host__ __device__ inline int eigvec_stage_doubles(int n) {
   return (tape > rows ? tape : rows) + 2;
 }
 
+// GLOBAL = true: orders whose n x ld block does not fit shared memory keep the eigenvector block in its output
+// array (row-major, thread i owns column i: every access is coalesced across the CTA); only the staging buffers
+// live in shared memory.  Functional path for large models (N > VI_NMAX_SMEM), not a tuned one.
+template <bool GLOBAL>
 __global__ void k_eigvec(int64_t s0, SysBuf B, double pinv_rtol, double* __restrict__ E, double* __restrict__ dinv) {
   extern __shared__ __align__(16) double sm[];
-  const int n = B.n, i = threadIdx.x, ld = B.ld, nt = blockDim.x;
+  const int n = B.n, i = threadIdx.x, ld = GLOBAL ? B.n : B.ld, nt = blockDim.x;
   const int64_t s = s0 + blockIdx.x;
   if (B.st[s] != VI_ST_OK || B.rec[s] < 0) return;
   const int64_t base = ileave(s, n);
-  double* stage = sm + (size_t)n * ld;
-  double* col = sm + i;                          // this thread's column of Z (stride ld)
+  double* stage = GLOBAL ? sm : sm + (size_t)n * ld;
+  double* col = (GLOBAL ? E + (int64_t)blockIdx.x * n * n : sm) + i;      // this thread's column of Z (stride ld)
   if (i < n)
     for (int r = 0; r < n; ++r) col[r * ld] = (r == i) ? 1.0 : 0.0;
   // ---- Z: replay the tape backwards (vi_tape_apply_z order) ------------------------------------------------
@@ -588,8 +634,10 @@ __global__ void k_eigvec(int64_t s0, SysBuf B, double pinv_rtol, double* __restr
     }
   }
   if (i < n) {
-    double* Es = E + (int64_t)blockIdx.x * n * n;
-    for (int r = 0; r < n; ++r) Es[(int64_t)r * n + i] = col[r * ld];
+    if (!GLOBAL) {
+      double* Es = E + (int64_t)blockIdx.x * n * n;
+      for (int r = 0; r < n; ++r) Es[(int64_t)r * n + i] = col[r * ld];
+    }
     double lmax = 0.0;
     for (int m = 0; m < n; ++m) lmax = fmax(lmax, fabs(B.d[base + (int64_t)m * 32]));
     const double l = B.d[base + (int64_t)i * 32];
@@ -662,11 +710,11 @@ k_bgemm(const double* __restrict__ A, int64_t strideA, const double* __restrict_
   }
 }
 
-__global__ void k_cov_nan(int64_t s0, int64_t r0, int n, SysBuf B, double* __restrict__ dC) {
+__global__ void k_cov_nan(int64_t s0, int n, SysBuf B, double* __restrict__ dC_chunk) {
   const int64_t s = s0 + blockIdx.x;
   if (B.st[s] == VI_ST_OK && B.rec[s] >= 0) return;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
-  double* out = dC + (r0 + s) * (int64_t)n * n;
+  double* out = dC_chunk + (int64_t)blockIdx.x * n * n;
   for (int e = threadIdx.x; e < n * n; e += blockDim.x) out[e] = nan;
 }
 
@@ -921,6 +969,7 @@ __global__ void k_bracket(int64_t U, int nreg, const int32_t* __restrict__ npts,
   int r = (int)(u / nreg);
   Ub.active[u] = 0;
   Ub.nu[u] = 0.0;
+  Ub.klo[u] = -1;
   if (npts[r] <= 0) { Ub.status[u] = VI_ST_EMPTY; return; }
   const double* tab = Ub.table + u * VI_NALPHA;
   vi_bracket br = vi_chi2_bracket(tab, 1, npts[r]);
@@ -932,6 +981,7 @@ __global__ void k_bracket(int64_t U, int nreg, const int32_t* __restrict__ npts,
   }
   Ub.status[u] = br.status;
   Ub.nu[u] = br.nu;
+  Ub.klo[u] = br.k_lo;
   if (br.status != VI_ST_OK) return;
   const int k = br.k_lo;
   vi_brent b;
@@ -1316,6 +1366,30 @@ int run_chi2(int64_t cnt, const double* At, const double* Wm, const double* bm, 
   return VI_OK;
 }
 
+// dC chunk = H (A^T W A) H for the systems [c0, c0 + nc) of the current batch (interpolate.py:464-467): eigenvectors,
+// H = E diag(scl / lambda | cut-off N eps max|lambda|) E^T, T = H G, out = T H; NaN blocks for failed systems.
+int run_cov_chunk(int64_t c0, int64_t nc, int N, const SysBuf& B, const double* G, double* covE, double* covH,
+                  double* covT, double* covD, double* out, cudaStream_t st) {
+  const int64_t NN = (int64_t)N * N;
+  size_t smem_e = ((size_t)N * B.ld + eigvec_stage_doubles(N)) * sizeof(double);
+  const bool ev_global = smem_e > 227 * 1024;       // N > ~160: eigenvector block stays in global memory
+  if (ev_global) smem_e = (size_t)eigvec_stage_doubles(N) * sizeof(double);
+  if (ev_global) VI_CUDA(cudaFuncSetAttribute(k_eigvec<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+  else VI_CUDA(cudaFuncSetAttribute(k_eigvec<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+  const unsigned tiles = (unsigned)((N + 63) / 64);
+  VI_CUDA(cudaMemsetAsync(covD, 0, nc * N * sizeof(double), st));
+  if (ev_global)
+    VI_KERNEL(VI_K_COV, st, k_eigvec<true><<<(unsigned)nc, (N + 31) / 32 * 32, smem_e, st>>>(c0, B, (double)N * VI_EPS, covE, covD));
+  else
+    VI_KERNEL(VI_K_COV, st, k_eigvec<false><<<(unsigned)nc, (N + 31) / 32 * 32, smem_e, st>>>(c0, B, (double)N * VI_EPS, covE, covD));
+  dim3 grid(tiles, tiles, (unsigned)nc);
+  VI_KERNEL(VI_K_COV, st, k_bgemm<true><<<grid, 256, 0, st>>>(covE, NN, covE, NN, nullptr, covD, covH, NN, N));
+  VI_KERNEL(VI_K_COV, st, k_bgemm<false><<<grid, 256, 0, st>>>(covH, NN, G, NN, B.rec + c0, nullptr, covT, NN, N));
+  VI_KERNEL(VI_K_COV, st, k_bgemm<false><<<grid, 256, 0, st>>>(covT, NN, covH, NN, nullptr, nullptr, out, NN, N));
+  VI_KERNEL(VI_K_COV, st, k_cov_nan<<<(unsigned)nc, 256, 0, st>>>(c0, N, B, out));
+  return VI_OK;
+}
+
 }  // namespace
 
 extern "C" int vi_fit_workspace_bytes(int32_t R, int32_t P, int32_t N, int32_t nreg, int64_t systems, int64_t* bytes) {
@@ -1348,19 +1422,27 @@ static int64_t cap_for_workspace(int64_t ws_bytes, int64_t U, int n, int nreg, i
   return cap;
 }
 
-extern "C" int vi_solve_batched(const double* G, const double* y, const int32_t* rec, const double* regmats,
-                                const double* lam, int64_t S, int32_t N, int32_t nreg, double rcond,
-                                double* C, int32_t* rank, int32_t* status,
-                                void* workspace, int64_t workspace_bytes, void* stream) {
+extern "C" int vi_solve_cov_batched(const double* G, const double* y, const int32_t* rec, const double* regmats,
+                                    const double* lam, int64_t S, int32_t N, int32_t nreg, double rcond,
+                                    double* C, double* dC, int32_t* rank, int32_t* status,
+                                    void* workspace, int64_t workspace_bytes, void* stream) {
   VI_REQUIRE(G && y && C && rank && status && workspace, "NULL argument");
   VI_REQUIRE(S >= 0 && N >= 1 && N <= 1024 && nreg >= 0, "bad shape");
   VI_REQUIRE(nreg == 0 || (regmats && lam), "regmats/lam missing");
   if (S == 0) return VI_OK;
   cudaStream_t st = vi_stream(stream);
-  int64_t cap = cap_for_workspace(workspace_bytes, 0, N, nreg, 1, 0);
+  const int64_t cc = S < kCovChunk ? S : kCovChunk;
+  int64_t cap = cap_for_workspace(workspace_bytes, 0, N, nreg, 1, dC ? S : 0);
   if (cap < 32) { vi_set_error("workspace too small (%lld bytes)", (long long)workspace_bytes); return VI_EWORKSPACE; }
   if (cap > vi_align_up(S, 32)) cap = vi_align_up(S, 32);
   Bump b{reinterpret_cast<char*>(workspace), 0, workspace_bytes};
+  double *covE = nullptr, *covH = nullptr, *covT = nullptr, *covD = nullptr;
+  if (dC) {
+    covE = b.take<double>(cc * (int64_t)N * N);
+    covH = b.take<double>(cc * (int64_t)N * N);
+    covT = b.take<double>(cc * (int64_t)N * N);
+    covD = b.take<double>(cc * (int64_t)N);
+  }
   SysBuf B;
   sysbuf_carve(b, B, cap, N, nreg, 1);
   for (int64_t s0 = 0; s0 < S; s0 += cap) {
@@ -1368,10 +1450,23 @@ extern "C" int vi_solve_batched(const double* G, const double* y, const int32_t*
     VI_KERNEL(VI_K_MISC, st, k_setup_solve<<<blocks(cap, 256), 256, 0, st>>>(s0, cnt, nreg, rec, lam, B));
     VI_LAUNCH_CHECK();
     if (int rc = run_systems(cnt, G, y, regmats, B, rcond, C + s0 * N, B.rank, st)) return rc;
+    if (dC)
+      for (int64_t c0 = 0; c0 < cnt; c0 += cc) {
+        const int64_t nc = (cnt - c0 < cc) ? cnt - c0 : cc;
+        if (int rc = run_cov_chunk(c0, nc, N, B, G, covE, covH, covT, covD, dC + (s0 + c0) * (int64_t)N * N, st)) return rc;
+      }
     VI_KERNEL(VI_K_MISC, st, k_copy_status<<<blocks(cnt, 256), 256, 0, st>>>(cnt, B, rank + s0, status + s0));
     VI_LAUNCH_CHECK();
   }
   return VI_OK;
+}
+
+extern "C" int vi_solve_batched(const double* G, const double* y, const int32_t* rec, const double* regmats,
+                                const double* lam, int64_t S, int32_t N, int32_t nreg, double rcond,
+                                double* C, int32_t* rank, int32_t* status,
+                                void* workspace, int64_t workspace_bytes, void* stream) {
+  return vi_solve_cov_batched(G, y, rec, regmats, lam, S, N, nreg, rcond, C, nullptr, rank, status, workspace,
+                              workspace_bytes, stream);
 }
 
 extern "C" int vi_fit_batched(const double* At, const double* A, const double* Wm, const double* bm,
@@ -1385,10 +1480,6 @@ extern "C" int vi_fit_batched(const double* At, const double* A, const double* W
   VI_REQUIRE(method == VI_METHOD_NONE || method == VI_METHOD_CHI2 || method == VI_METHOD_GCV, "unknown method %d", method);
   VI_REQUIRE(method == VI_METHOD_NONE || (nreg >= 1 && regmats && lam), "chi2 / gcv need regularisation matrices");
   VI_REQUIRE(method != VI_METHOD_GCV || A != nullptr, "gcv needs the row-major design matrix A");
-  if (dC != nullptr && N > VI_NMAX_SMEM) {
-    vi_set_error("covariance output needs nbasis <= %d (got %d)", VI_NMAX_SMEM, N);
-    return VI_EUNSUPPORTED;
-  }
   if (nsolve) *nsolve = 0;
   if (R == 0) return VI_OK;
   if (method == VI_METHOD_NONE) nreg = 0;
@@ -1412,6 +1503,7 @@ extern "C" int vi_fit_batched(const double* At, const double* A, const double* W
   double* covH = b.take<double>(cc * (int64_t)N * N);
   double* covT = b.take<double>(cc * (int64_t)N * N);
   double* covD = b.take<double>(cc * (int64_t)N);
+  double* covRing = b.take<double>(2 * cc * (int64_t)N * N);
   if (cap > most) cap = most;
   SysBuf B;
   sysbuf_carve(b, B, cap, N, nreg, P);
@@ -1422,6 +1514,7 @@ extern "C" int vi_fit_batched(const double* At, const double* A, const double* W
     for (int k = 0; k < VI_NALPHA; ++k) h_tab[k] = pow(10.0, -(double)k);   // np.power(10., alpha), interpolate.py:250
     VI_CUDA(cudaMemcpyAsync(pow10tab, h_tab, sizeof(h_tab), cudaMemcpyHostToDevice, st));
     VI_CUDA(cudaMemsetAsync(Ub.tabbad, 0, U * sizeof(int32_t), st));
+    VI_CUDA(cudaMemsetAsync(Ub.table, 0xff, U * VI_NALPHA * sizeof(double), st));   // unevaluated entries read as NaN (vi_fit_search_trace)
     VI_CUDA(cudaMemsetAsync(Ub.count, 0, 8 * sizeof(int32_t), st));
     // ---- phase 1: chi2(10^-k) table for every unit -------------------------------------
     VI_KERNEL(VI_K_MISC, st, k_kstar<<<(unsigned)U, 256, 0, st>>>(nreg, N, G, regmats, pow10tab, Ub.kstar));
@@ -1509,6 +1602,21 @@ extern "C" int vi_fit_batched(const double* At, const double* A, const double* W
     }
   }
   // ---- phase 3: final solve with the found parameters (interpolate.py:566-569) -----------
+  // dC may be a device pointer or a PINNED HOST pointer: in the second case every chunk of kCovChunk records is
+  // computed into a two-slot device ring and copied out on a side stream while the next chunk is computed, so the
+  // R x N x N block (1.66 GB at 10 k records, N = 144) neither occupies HBM nor serialises behind the fit.
+  bool cov_to_host = false;
+  int64_t cov_chunk = 0;
+  CovSink& sink = cov_sink();
+  if (dC != nullptr) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, dC) == cudaSuccess && pa.type == cudaMemoryTypeHost) {
+      cov_to_host = true;
+      if (int rc = sink.init()) return rc;
+    } else {
+      (void)cudaGetLastError();
+    }
+  }
   for (int64_t r0 = 0; r0 < R; r0 += cap) {
     int64_t cnt = (R - r0 < cap) ? R - r0 : cap;
     VI_KERNEL(VI_K_MISC, st, k_setup_final<<<blocks(cap, 128), 128, 0, st>>>(r0, cnt, nreg, method, npts, B, Ub, lam, status));
@@ -1517,25 +1625,57 @@ extern "C" int vi_fit_batched(const double* At, const double* A, const double* W
     if (int rc = run_chi2(cnt, At, Wm, bm, P, B, C + r0 * N, B.chi2, st)) return rc;
     if (dC != nullptr) {
       const int64_t NN = (int64_t)N * N;
-      const size_t smem_e = ((size_t)N * B.ld + eigvec_stage_doubles(N)) * sizeof(double);
-      VI_CUDA(cudaFuncSetAttribute(k_eigvec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
-      const unsigned tiles = (unsigned)((N + 63) / 64);
       for (int64_t c0 = 0; c0 < cnt; c0 += cc) {
         const int64_t nc = (cnt - c0 < cc) ? cnt - c0 : cc;
-        VI_CUDA(cudaMemsetAsync(covD, 0, nc * N * sizeof(double), st));
-        VI_KERNEL(VI_K_COV, st, k_eigvec<<<(unsigned)nc, (N + 31) / 32 * 32, smem_e, st>>>(c0, B, (double)N * VI_EPS, covE, covD));
-        dim3 grid(tiles, tiles, (unsigned)nc);
-        VI_KERNEL(VI_K_COV, st, k_bgemm<true><<<grid, 256, 0, st>>>(covE, NN, covE, NN, nullptr, covD, covH, NN, N));
-        VI_KERNEL(VI_K_COV, st, k_bgemm<false><<<grid, 256, 0, st>>>(covH, NN, G, NN, B.rec + c0, nullptr, covT, NN, N));
-        VI_KERNEL(VI_K_COV, st, k_bgemm<false><<<grid, 256, 0, st>>>(covT, NN, covH, NN, nullptr, nullptr, dC + (r0 + c0) * NN, NN, N));
-        VI_KERNEL(VI_K_COV, st, k_cov_nan<<<(unsigned)nc, 256, 0, st>>>(c0, r0, N, B, dC));
+        double* dst = dC + (r0 + c0) * NN;
+        double* out = dst;
+        const int slot = (int)(cov_chunk & 1);
+        if (cov_to_host) {        // chunk goes to the ring; wait until the copy that last used this slot has drained
+          out = covRing + (int64_t)slot * cc * NN;
+          if (cov_chunk >= 2) VI_CUDA(cudaStreamWaitEvent(st, sink.drained[slot], 0));
+        }
+        if (int rc = run_cov_chunk(c0, nc, N, B, G, covE, covH, covT, covD, out, st)) return rc;
+        if (cov_to_host) {
+          VI_CUDA(cudaEventRecord(sink.ready[slot], st));
+          VI_CUDA(cudaStreamWaitEvent(sink.copy, sink.ready[slot], 0));
+          VI_CUDA(cudaMemcpyAsync(dst, out, nc * NN * sizeof(double), cudaMemcpyDeviceToHost, sink.copy));
+          VI_CUDA(cudaEventRecord(sink.drained[slot], sink.copy));
+        }
+        ++cov_chunk;
       }
     }
     VI_KERNEL(VI_K_MISC, st, k_finalize<<<(unsigned)cnt, 64, 0, st>>>(r0, cnt, N, B, C, chi2, rank, status));
     VI_LAUNCH_CHECK();
     solved += cnt;
   }
+  if (cov_to_host) {        // the caller's stream order covers the copies: `st` waits for both slots
+    for (int slot = 0; slot < 2 && slot < cov_chunk; ++slot) VI_CUDA(cudaStreamWaitEvent(st, sink.drained[slot], 0));
+  }
   if (nsolve) *nsolve = solved;
+  return VI_OK;
+}
+
+// Diagnostics of the last VI_METHOD_CHI2 search that ran in `workspace` (same R, P, nreg): the chi2(10^-k) table
+// (entries the lazy walk never evaluated are NaN), nu = npts * scale factor of the bracket, the bracket decade and
+// the number of distinct table entries evaluated.  This is what the parity report compares with the reference's
+// own (alpha, chi2 - nu) trace (interpolate.py:180-207).
+extern "C" int vi_fit_search_trace(const void* workspace, int64_t workspace_bytes, int32_t R, int32_t P, int32_t nreg,
+                                   double* table, double* nu, int32_t* k_lo, int32_t* kdone, void* stream) {
+  VI_REQUIRE(workspace && R >= 0 && P >= 1 && nreg >= 1, "bad arguments");
+  if (R == 0) return VI_OK;
+  cudaStream_t st = vi_stream(stream);
+  const int64_t U = (int64_t)R * nreg;
+  Bump b{reinterpret_cast<char*>(const_cast<void*>(workspace)), 0, workspace_bytes};
+  b.take<int32_t>((int64_t)R * P);
+  b.take<int32_t>(R);
+  b.take<int64_t>(U);
+  UnitBuf Ub;
+  unit_carve(b, Ub, U);
+  VI_REQUIRE(b.off <= workspace_bytes, "workspace smaller than the one the fit ran in");
+  if (table) VI_CUDA(cudaMemcpyAsync(table, Ub.table, U * VI_NALPHA * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (nu) VI_CUDA(cudaMemcpyAsync(nu, Ub.nu, U * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (k_lo) VI_CUDA(cudaMemcpyAsync(k_lo, Ub.klo, U * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  if (kdone) VI_CUDA(cudaMemcpyAsync(kdone, Ub.kdone, U * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   return VI_OK;
 }
 
@@ -1590,7 +1730,13 @@ extern "C" int vi_fit_host(const double* A, const double* value, const double* e
   if (weight) VI_TRY(cudaMemcpyAsync(dwt, weight, RP * 8, cudaMemcpyHostToDevice, s));
   if (nreg > 0) VI_TRY(cudaMemcpyAsync(dreg, regmats, (size_t)nreg * NN * 8, cudaMemcpyHostToDevice, s));
   if (rc == VI_OK) {
-    VI_KERNEL(VI_K_MISC, s, k_transpose<<<blocks((int64_t)PN, 256), 256, 0, s>>>(dA, P, N, dAt));
+    // (not VI_KERNEL: its launch check returns, which would skip cleanup())
+    vi_prof_launch_begin(VI_K_MISC, s);
+    k_transpose<<<blocks((int64_t)PN, 256), 256, 0, s>>>(dA, P, N, dAt);
+    vi_prof_launch_end(VI_K_MISC, s);
+    VI_TRY(cudaGetLastError());
+  }
+  if (rc == VI_OK) {
     rc = vi_normal_eq_batched(dA, dval, derr, dwt, R, P, N, ne_mode, dG, dy, nullptr, dnp, dWm, dbm, s);
   }
   if (rc == VI_OK)

@@ -610,14 +610,15 @@ extern "C" int vi_normal_eq_batched(const double* A, const double* value, const 
     VI_KERNEL(VI_K_NORMAL_EQ, s, k_prep<<<R, 256, 0, s>>>(value, error, weight, P, sWbb, npts, Wm, bm));
     VI_LAUNCH_CHECK();
   }
-  if (mode == VI_NE_STRICT) {
+  auto strict = [&]() -> int {
     int nsb = (N + kSB - 1) / kSB;
     size_t smem = (size_t)(2 * kSJ * kSB + 2 * kSJ) * sizeof(double);
     VI_CUDA(cudaFuncSetAttribute(k_ne_strict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VI_KERNEL(VI_K_NORMAL_EQ, s, k_ne_strict<<<(unsigned)(R * nsb * nsb), 256, smem, s>>>(A, value, error, weight, P, N, nsb, G, y));
     VI_LAUNCH_CHECK();
     return VI_OK;
-  }
+  };
+  if (mode == VI_NE_STRICT) return strict();
   if (mode != VI_NE_FAST) { vi_set_error("unknown normal-equation mode %d", mode); return VI_EINVAL; }
   const int mt = (N + 15) / 16;
   const int nt = (N + 7) / 8 + 1;             // + rhs column tile
@@ -627,10 +628,9 @@ extern "C" int vi_normal_eq_batched(const double* A, const double* value, const 
       if (8 * ni <= 16 * mi + 15 && 8 * ni < N) ++ntiles;
     ++ntiles;
   }
-  if (ntiles > kDW * kDT || ntiles > 255) {
-    vi_set_error("VI_NE_FAST supports nbasis <= %d (got %d): use VI_NE_STRICT", VI_NMAX_SMEM, N);
-    return VI_EUNSUPPORTED;
-  }
+  // the tensor-core kernels keep one record's whole tile set in one CTA (nbasis <= VI_NMAX_SMEM); larger models
+  // (the reference has no limit: radbasfun NUMGRIDPNT=7 is N = 343, interpolate.py:456) run the tiled strict kernel
+  if (ntiles > kDW * kDT || ntiles > 255) return strict();
   const int cols = (16 * mt > 8 * nt) ? 16 * mt : 8 * nt;
   const int tpw = (ntiles + kDW - 1) / kDW;
   if (Wm && bm && !getenv("VI_NE_V2")) {

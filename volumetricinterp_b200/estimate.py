@@ -15,6 +15,21 @@ import numpy as np
 from scipy.spatial import ConvexHull
 
 
+def hull_halfspaces(hull_vert):
+    """Facet half-spaces [n | d] of ConvexHull(hull_vert) for the in-kernel test n.x + d <= 0, with the
+    distance tolerance of the reference's decision folded into d.  The reference asks Qhull whether
+    hull_vert + {p} has the same vertices as hull_vert (estimate.py:167-177); Qhull only makes p a vertex when it
+    lies farther outside a facet than its roundoff allowance (qh_detroundoff: DISTround =
+    eps (1.01 dim sqrt(dim) + 1) max|coord|, a point counts as outside beyond about 6 DISTround when coplanar
+    facets are merged, the 3-d default), so gates ON the hull -- its own vertices, points on facets -- are inside.
+    A bare `<= 0` decides those by rounding noise of the ECEF coordinates (~1e-9 m at 6.4e6 m)."""
+    hv = np.asarray(hull_vert, dtype=np.float64)
+    eq = np.array(ConvexHull(hv).equations, dtype=np.float64, order='C')
+    dist_round = np.finfo(np.float64).eps * (1.01 * 3.0 * np.sqrt(3.0) + 1.0) * np.abs(hv).max()
+    eq[:, 3] -= 6.0 * dist_round
+    return eq
+
+
 class Estimate(object):
 
     def __init__(self, param_file, timetol=60., timeinterp=False):
@@ -40,7 +55,7 @@ class Estimate(object):
         self.model_name = config.get('MODEL', 'NAME')
         m = importlib.import_module('.models.' + self.model_name, package=__package__)
         self.model = m.Model(io.StringIO(config_text))
-        self.hull_eq = np.ascontiguousarray(ConvexHull(self.hull_vert).equations)
+        self.hull_eq = hull_halfspaces(self.hull_vert)
         self._dev = {}
 
     def loadh5(self, filename):
@@ -55,26 +70,28 @@ class Estimate(object):
         self.config_text = txt.decode('utf-8') if isinstance(txt, (bytes, np.bytes_)) else str(txt)
 
     def get_C(self, time):
-        """estimate.py:180-221: nearest record within timetol, or linear interpolation in time."""
-        t0 = (time - dt.datetime.utcfromtimestamp(0)).total_seconds()
-        mt = np.mean(self.time, axis=1)
-        try:
-            if self.timeinterp:
-                i = np.argwhere((t0 >= mt[:-1]) & (t0 < mt[1:])).flatten()[0]
-                T = (t0 - mt[i]) / (mt[i + 1] - mt[i])
-                C = (1 - T) * self.Coeffs[i, :] + T * self.Coeffs[i + 1, :]
-                dC = None
-                if self.Covariance is not None:
-                    dC = (1 - T) * self.Covariance[i, :, :] + T * self.Covariance[i + 1, :, :]
-            else:
-                i = np.argmin(np.abs(mt - t0))
-                if np.abs(mt[i] - t0) > self.timetol:
-                    raise IndexError
-                C = self.Coeffs[i]
-                dC = self.Covariance[i] if self.Covariance is not None else None
-        except IndexError:
+        """Coefficients (and covariance) in force at `time` -- the selection rule of estimate.py:180-221: the record
+        whose mid-time is closest, provided it is within `timetol` seconds; with `timeinterp` the two records whose
+        mid-times bracket `time`, blended linearly.  ValueError when the file does not cover `time`."""
+        t = (time - dt.datetime.utcfromtimestamp(0)).total_seconds()
+        mid = np.asarray(self.time, dtype=float).mean(axis=1)
+        cov = self.Covariance
+        if self.timeinterp:
+            # left neighbour: last record with mid <= t (records are in file order, as the reference assumes)
+            hit = np.flatnonzero((mid[:-1] <= t) & (t < mid[1:]))
+            if hit.size == 0:
+                raise ValueError('Requested time out of range of data file.')
+            j = int(hit[0])
+            frac = (t - mid[j]) / (mid[j + 1] - mid[j])
+            blend = lambda a: (1 - frac) * a[j] + frac * a[j + 1]
+            return blend(self.Coeffs), (blend(cov) if cov is not None else None)
+        if mid.size == 0:
             raise ValueError('Requested time out of range of data file.')
-        return C, dC
+        gap = np.abs(mid - t)
+        j = int(np.argmin(gap))
+        if gap[j] > self.timetol:
+            raise ValueError('Requested time out of range of data file.')
+        return self.Coeffs[j], (cov[j] if cov is not None else None)
 
     def _device_consts(self, dev):
         import torch

@@ -28,20 +28,26 @@ class Interpolate(object):
         self.ne_mode = _native.NE_FAST
         self.calc_covariance = True
 
+    # attribute <- (section, key, converter): the reference's configuration schema (interpolate.py:64-88)
+    _CONFIG_SCHEMA = (
+        ('param', 'DEFAULT', 'PARAM', str),
+        ('filename', 'DEFAULT', 'FILENAME', str),
+        ('outputfilename', 'DEFAULT', 'OUTPUTFILENAME', str),
+        ('regularization_list', 'DEFAULT', 'REGULARIZATION_LIST', lambda v: [x for x in v.split(',') if x]),
+        ('reg_method', 'DEFAULT', 'REGULARIZATION_METHOD', str),
+        ('errlim', 'DEFAULT', 'ERRLIM', lambda v: [float(x) for x in v.split(',')]),
+        ('chi2lim', 'DEFAULT', 'CHI2LIM', lambda v: [float(x) for x in v.split(',')]),
+        ('goodfitcode', 'DEFAULT', 'GOODFITCODE', lambda v: [int(x) for x in v.split(',')]),
+        ('model_name', 'MODEL', 'NAME', str),
+    )
+
     def read_config(self, config_file):
-        """Same keys as the reference (interpolate.py:64-88)."""
-        config = configparser.ConfigParser()
+        """Read the keys listed in _CONFIG_SCHEMA into attributes of the same names the reference uses."""
+        parser = configparser.ConfigParser()
         with open(config_file) as f:
-            config.read_file(f)
-        self.regularization_list = list(filter(None, config.get('DEFAULT', 'REGULARIZATION_LIST').split(',')))
-        self.reg_method = config.get('DEFAULT', 'REGULARIZATION_METHOD')
-        self.filename = config.get('DEFAULT', 'FILENAME')
-        self.outputfilename = config.get('DEFAULT', 'OUTPUTFILENAME')
-        self.param = config.get('DEFAULT', 'PARAM')
-        self.errlim = [float(i) for i in config.get('DEFAULT', 'ERRLIM').split(',')]
-        self.chi2lim = [float(i) for i in config.get('DEFAULT', 'CHI2LIM').split(',')]
-        self.goodfitcode = [int(i) for i in config.get('DEFAULT', 'GOODFITCODE').split(',')]
-        self.model_name = config.get('MODEL', 'NAME')
+            parser.read_file(f)
+        for attr, section, key, conv in self._CONFIG_SCHEMA:
+            setattr(self, attr, conv(parser.get(section, key)))
 
     # ------------------------------------------------------------------ fit
     def eval_reg_matrices(self):
@@ -92,11 +98,8 @@ class Interpolate(object):
         return Ad, Ad.t().contiguous(), t(np.asarray(b)[None, :]), t(np.asarray(W)[None, :])
 
     def eval_C(self, A, b, W, reg_matrices, reg_params, calccov=False):
-        """interpolate.py:432-469 for one record (A (P,N), b (P,), W (P,))."""
+        """interpolate.py:432-469 for one record (A (P,N), b (P,), W (P,)): C, or (C, dC) with calccov."""
         import torch
-        import ctypes as C
-        if calccov:
-            raise NotImplementedError('covariance is produced by calc_coeffs')
         Ad, At, bd, Wd = self._one_record(A, b, W)
         G, y, _, npts, Wm, bm = _fit.normal_equations_device(Ad, bd, None, Wd, self.ne_mode)
         names = [r for r in self.regularization_list if r in reg_params]
@@ -106,15 +109,18 @@ class Interpolate(object):
         regs = torch.from_numpy(np.stack([reg_matrices[r] for r in names])).to(dev) if nreg else None
         lam = torch.tensor([[float(reg_params[r]) for r in names]], dtype=torch.float64, device=dev) if nreg else None
         Cf = torch.empty((1, N), dtype=torch.float64, device=dev)
+        dC = torch.empty((1, N, N), dtype=torch.float64, device=dev) if calccov else None
         rank = torch.zeros((1,), dtype=torch.int32, device=dev)
         status = torch.zeros((1,), dtype=torch.int32, device=dev)
         ws = _fit._workspace(dev, 1, Ad.shape[0], N, nreg, 32)
-        _native.check(_native.lib().vi_solve_batched(
+        _native.check(_native.lib().vi_solve_cov_batched(
             G.data_ptr(), y.data_ptr(), None, regs.data_ptr() if nreg else None, lam.data_ptr() if nreg else None,
-            1, N, nreg, np.finfo(float).eps, Cf.data_ptr(), rank.data_ptr(), status.data_ptr(),
-            ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
+            1, N, nreg, np.finfo(float).eps, Cf.data_ptr(), dC.data_ptr() if calccov else None, rank.data_ptr(),
+            status.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
         if int(status.item()) == _native.ST_NONFINITE:
             raise ValueError('array must not contain infs or NaNs')
+        if calccov:
+            return Cf[0].cpu().numpy(), dC[0].cpu().numpy()
         return Cf[0].cpu().numpy()
 
     def find_reg_param(self, A, b, W, reg_matrices, method=None):
