@@ -165,11 +165,11 @@ int vi_estimate_sphharmlag_host(const double* lat, const double* lon, const doub
  * chains, mode 1 = mma.sync m8n8k4 f64 (DMMA).  Writes achieved TFLOP/s to *tflops (host). */
 int vi_fp64_peak_probe(int32_t mode, int32_t iters, double* tflops, void* stream);
 
-/* Launch accounting (diagnostics; not thread safe).  Kinds, in order: basis, normal_eq, tridiag, tql,
- * apply, chi2, covariance, estimate, misc.  vi_profile_read returns, per kind, the device milliseconds
+/* Launch accounting (diagnostics; not thread safe).  Kinds, in order: basis, normal_eq, tridiag (band
+ * reduction / one-stage Householder), tql, apply, chi2, covariance, estimate, misc, chase (band -> tridiagonal).  vi_profile_read returns, per kind, the device milliseconds
  * (CUDA events on the launching stream; only while enabled) and the number of kernel launches (always
  * counted) since the last vi_profile_reset. */
-#define VI_PROFILE_KINDS 9
+#define VI_PROFILE_KINDS 10
 int vi_profile_enable(int32_t on);
 int vi_profile_reset(void);
 int vi_profile_read(double* ms_by_kind, int64_t* launches_by_kind, int32_t nkinds);

@@ -52,10 +52,11 @@ def harness():
     so = os.path.join(ROOT, "tests", "_cpu_harness.so")
     deps = [src] + [os.path.join(ROOT, "volumetricinterp_b200", "csrc", f)
                     for f in ("vi_math.h", "vi_tql.h", "vi_brent.h", "vi_tridiag.h", "vi_tridiag_packed.h", "vi_ne_split.h",
-                              "vi_nm.h")] + \
-        [os.path.join(ROOT, "include", "volinterp_b200.h")]
+                              "vi_nm.h", "vi_simt.h", "vi_band.h", "vi_chase.h")] + \
+        [os.path.join(ROOT, "include", "volinterp_b200.h"), os.path.join(ROOT, "tests", "cuda_emu.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"), "-o", so, src])
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
+                               "-I", os.path.join(ROOT, "tests"), "-o", so, src])
     return C.CDLL(so)
 
 

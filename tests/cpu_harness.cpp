@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstring>
 #include <vector>
+#define VI_EMU 1
 #include "../volumetricinterp_b200/csrc/vi_math.h"
 #include "../volumetricinterp_b200/csrc/vi_tql.h"
 #include "../volumetricinterp_b200/csrc/vi_brent.h"
@@ -13,6 +14,8 @@
 #include "../volumetricinterp_b200/csrc/vi_tridiag_packed.h"
 #include "../volumetricinterp_b200/csrc/vi_nm.h"
 #include "../volumetricinterp_b200/csrc/vi_ne_split.h"
+#include "../volumetricinterp_b200/csrc/vi_band.h"
+#include "../volumetricinterp_b200/csrc/vi_chase.h"
 
 extern "C" {
 
@@ -267,6 +270,65 @@ int h_trp_octet_of(int n, int warp, int slot, int a) {
   W.n = n; W.npad = vi_trp_npad(n); W.noct = vi_trp_noct(n); W.nwarp = vi_trp_nwarp(n);
   return vi_trp_octet_of(W, warp, slot, a);
 }
+
+// Two-stage pipeline of kernels k_band + k_chase + QL + back-transformation (csrc/vi_band.h, vi_chase.h), the device
+// code itself executed by the CUDA-on-CPU model of tests/cuda_emu.h (one fiber per CUDA thread):
+//   X -> band (one CTA) -> tridiagonal (one warp) -> QL with tape -> truncated solve -> C = Q1 Q2 c~.
+// bandout (optional): 9 * npad doubles, the band stage 1 produced.
+int h_system_solve_two_stage(int n, const double* G, const double* y, const double* regs, const double* lam, int nreg,
+                             double rcond, double* C, int* rank, double* dd, double* ee, int* bad, double* bandout) {
+  const int nt = vi_bnd_threads(n), np = vi_bnd_npad(n);
+  std::vector<double> smem(vi_bnd_doubles(n) + 2), Vg(vi_bnd_vdoubles(n) + 64, 0.0), band(vi_bnd_band_doubles(n), 0.0);
+  std::vector<double> refl(vi_chs_rdoubles(n) + 8, 0.0);
+  double* base = smem.data();
+  if (reinterpret_cast<uintptr_t>(base) & 15) base += 1;
+  double scl = 1.0, badf = 0.0;
+  emu::run_cta(0, nt, [&]() {
+    vi_bnd_ws S;
+    vi_bnd_carve(S, base, n);
+    vi_bnd_load(S, G, y, regs, lam, nreg, nullptr, 0.0, 0.0);
+    const bool isbad = S.sc[1] != 0.0;
+    if (!isbad) { vi_bnd_reduce(S, Vg.data()); vi_bnd_store_band(S, band.data()); }
+    if (vi_tid() == 0) { scl = S.sc[0]; badf = S.sc[1]; }
+  });
+  *bad = badf != 0.0;
+  if (*bad) return 0;
+  if (bandout) std::memcpy(bandout, band.data(), 9 * (size_t)np * sizeof(double));
+  std::vector<double> work(vi_chs_doubles(n) + 2, 0.0);
+  double* Bw = work.data();
+  double* gw = Bw + VI_CHS_LDB * (np + 8);
+  emu::run_cta(0, 32, [&]() {
+    vi_chs_load(Bw, gw, band.data(), n);
+    vi_chs_reduce(Bw, gw, n, refl.data());
+  });
+  std::vector<double> d(n), e(n, 0.0), g(gw, gw + n);
+  for (int j = 0; j < n; ++j) { d[j] = Bw[j * VI_CHS_LDB]; if (j + 1 < n) e[j] = Bw[j * VI_CHS_LDB + 1]; }
+  for (int i = 0; i < n; ++i) { dd[i] = d[i]; ee[i] = e[i]; }
+  int cap = 2 * n * n + 64;
+  std::vector<double> tcs(2 * (size_t)cap);
+  std::vector<int32_t> ti(cap);
+  vi_tape tape{{tcs.data(), 2}, {tcs.data() + 1, 2}, {ti.data(), 1}, cap};
+  int32_t nr = 0;
+  int st = vi_tql_values(n, {d.data(), 1}, {e.data(), 1}, tape, &nr);
+  if (st != 0) return st;
+  vi_tape_apply_zt({g.data(), 1}, tape, nr);
+  *rank = vi_spectral_divide(n, {d.data(), 1}, {g.data(), 1}, rcond);
+  vi_tape_apply_z({g.data(), 1}, tape, nr);
+  for (int i = 0; i < n; ++i) g[i] *= scl;
+  std::vector<double> u(np + 8, 0.0);
+  std::memcpy(u.data(), g.data(), n * sizeof(double));
+  emu::run_cta(0, 32, [&]() {
+    vi_chs_apply_q(u.data(), n, refl.data());
+    vi_bnd_apply_q(u.data(), n, Vg.data());
+  });
+  std::memcpy(C, u.data(), n * sizeof(double));
+  return 0;
+}
+int h_bnd_threads(int n) { return vi_bnd_threads(n); }
+int h_bnd_smem_bytes(int n) { return vi_bnd_doubles(n) * 8; }
+int h_chs_nrefl(int n) { return vi_chs_nrefl(n); }
+int h_chs_off(int n, int s) { return vi_chs_off(n, s); }
+int h_bnd_el(int r, int c) { return vi_bnd_el(r, c); }
 
 int h_sizeof_shl_params() { return (int)sizeof(vi_shl_params); }
 }

@@ -69,6 +69,7 @@ def test_radbasfun_rows_match_reference_basis(harness):
 
 
 PACKED = -1
+TWO_STAGE = -2      # band reduction + bulge chasing (vi_band.h, vi_chase.h), device code run by tests/cuda_emu.h
 
 
 def _system(harness, G, y, regs, lam, nt):
@@ -78,7 +79,10 @@ def _system(harness, G, y, regs, lam, nt):
     dd, ee = np.zeros(n), np.zeros(n)
     regs = np.ascontiguousarray(regs)
     lam = np.ascontiguousarray(lam, dtype=float)
-    if nt == PACKED:      # the packed-triangle kernel's phases (vi_tridiag_packed.h), thread count fixed by n
+    if nt == TWO_STAGE:
+        st = harness.h_system_solve_two_stage(n, dptr(G), dptr(y), dptr(regs), dptr(lam), len(lam), C.c_double(EPS),
+                                              dptr(Cq), C.byref(rank), dptr(dd), dptr(ee), C.byref(bad), None)
+    elif nt == PACKED:      # the packed-triangle kernel's phases (vi_tridiag_packed.h), thread count fixed by n
         st = harness.h_system_solve_packed(n, dptr(G), dptr(y), dptr(regs), dptr(lam), len(lam), C.c_double(EPS),
                                            dptr(Cq), C.byref(rank), dptr(dd), dptr(ee), C.byref(bad))
     else:
@@ -88,7 +92,8 @@ def _system(harness, G, y, regs, lam, nt):
 
 
 @pytest.mark.parametrize("name,nt", [("lo8", 8), ("lo8", 32), ("lo12", 48), ("lo12_two", 12),
-                                     ("lo8", PACKED), ("lo12", PACKED), ("lo12_two", PACKED)])
+                                     ("lo8", PACKED), ("lo12", PACKED), ("lo12_two", PACKED),
+                                     ("lo8", TWO_STAGE), ("lo12", TWO_STAGE), ("lo12_two", TWO_STAGE)])
 def test_system_pipeline_matches_lstsq_low_order(harness, name, nt):
     """tridiagonalise (CTA phases run thread by thread) + tape QL + truncated solve + back-transform
     == scipy.linalg.lstsq (interpolate.py:462) on full-rank systems."""
@@ -114,7 +119,7 @@ def test_system_pipeline_matches_lstsq_low_order(harness, name, nt):
             assert np.max(np.abs(Cq - ref)) <= 50 * EPS * cond * np.abs(ref).max()
 
 
-@pytest.mark.parametrize("nt", [576, PACKED])
+@pytest.mark.parametrize("nt", [576, PACKED, TWO_STAGE])
 def test_system_pipeline_rank_deficient(harness, nt):
     """N = 144: numerical rank and fitted densities agree with lstsq where the solve is well posed."""
     g = load_golden("c1_144")
@@ -156,6 +161,81 @@ def test_packed_tridiagonalisation_random(harness, n):
                                               max(32, (n + 31) // 32 * 32))
     assert np.allclose(dd, dd2, rtol=0, atol=1e-12 * np.abs(dd2).max())
     assert np.allclose(np.abs(ee), np.abs(ee2), rtol=0, atol=1e-12 * np.abs(dd2).max())
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 9, 15, 16, 17, 27, 40, 65, 100, 144, 168])
+def test_two_stage_tridiagonalisation_random(harness, n):
+    """Band reduction (DMMA block reflectors, one CTA) + bulge chasing (one warp): the device code of vi_band.h /
+    vi_chase.h executed by the CUDA-on-CPU model.  T has the spectrum of X and Q1 Q2 T+ Q2^T Q1^T y solves the
+    system, for orders around every block / warp-count boundary up to the largest the two-stage path takes."""
+    rng = np.random.default_rng(300 + n)
+    M = rng.standard_normal((n, n))
+    X = M @ M.T + n * np.eye(n)
+    y = rng.standard_normal(n)
+    st, bad, rank, Cq, dd, ee = _system(harness, np.ascontiguousarray(X), y, np.zeros((1, n, n)), [0.0], TWO_STAGE)
+    assert bad == 0 and st == 0 and rank == n
+    T = np.diag(dd) + np.diag(ee[:-1], 1) + np.diag(ee[:-1], -1)
+    ev, evT = np.linalg.eigvalsh(X), np.linalg.eigvalsh(T)
+    scl = np.abs(ev).max() / np.abs(evT).max()
+    assert np.allclose(evT * scl, ev, rtol=0, atol=1e-13 * np.abs(ev).max())
+    ref = np.linalg.solve(X, y)
+    assert np.max(np.abs(Cq - ref)) <= 1e-12 * np.abs(ref).max()
+
+
+def test_two_stage_band_is_orthogonally_similar(harness):
+    """Stage 1 alone: the band it hands to stage 2 (half-width 8) has the spectrum of X, also for an indefinite,
+    graded matrix like the regularised systems of the fit."""
+    n = 100
+    rng = np.random.default_rng(5)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    ev = rng.standard_normal(n) * 10.0 ** rng.uniform(-14, 0, n)
+    X = (Q * ev) @ Q.T
+    X = 0.5 * (X + X.T)
+    y = rng.standard_normal(n)
+    npad = (n + 7) // 8 * 8
+    band = np.zeros(9 * npad)
+    Cq, dd, ee = np.zeros(n), np.zeros(n), np.zeros(n)
+    rank, bad = C.c_int(0), C.c_int(0)
+    regs, lam = np.zeros((1, n, n)), np.zeros(1)
+    st = harness.h_system_solve_two_stage(n, dptr(X), dptr(y), dptr(regs), dptr(lam), 1, C.c_double(EPS), dptr(Cq),
+                                          C.byref(rank), dptr(dd), dptr(ee), C.byref(bad), dptr(band))
+    assert st == 0 and bad.value == 0
+    Bm = np.zeros((n, n))
+    for j in range(n):
+        for d in range(9):
+            if j + d < n:
+                Bm[j + d, j] = Bm[j, j + d] = band[9 * j + d]
+    scl = 2.0 ** -np.frexp(np.abs(X).max())[1]
+    evb = np.sort(np.linalg.eigvalsh(Bm) / scl)
+    assert np.allclose(evb, np.sort(np.linalg.eigvalsh(X)), rtol=0, atol=1e-14 * np.abs(ev).max())
+    assert np.abs(band.reshape(npad, 9)[n:]).max(initial=0.0) == 0.0
+
+
+def test_two_stage_layout(harness):
+    """Block layout of vi_band.h: the element map of a block is a bijection, and each of the three fragment access
+    patterns touches 16 distinct 8-byte bank pairs per half warp (64-bit accesses) / 8 distinct 16-byte slots per
+    quarter warp (128-bit accumulator pairs): shared-memory bank-conflict free.  Reflector offsets of vi_chase.h
+    match a direct count."""
+    el = np.array([[harness.h_bnd_el(r, c) for c in range(8)] for r in range(8)])
+    assert sorted(el.ravel()) == list(range(64))
+    lanes = np.arange(32)
+    for t in (0, 1):
+        a_norm = np.array([el[l // 4, 4 * t + l % 4] for l in lanes])          # A operand of a stored block
+        a_tran = np.array([el[4 * t + l % 4, l // 4] for l in lanes])          # A operand of its transpose
+        for pat in (a_norm, a_tran):
+            for half in (pat[:16], pat[16:]):
+                assert len(set(half % 16)) == 16
+    acc = np.array([el[l // 4, 2 * (l % 4)] for l in lanes])                     # accumulator pair (even column)
+    assert (acc % 2 == 0).all() and all(el[l // 4, 2 * (l % 4) + 1] == acc[l] + 1 for l in lanes)
+    for q in range(4):
+        assert len(set((acc[8 * q:8 * q + 8] // 2) % 8)) == 8
+    for n in (3, 9, 16, 17, 100, 144, 168):
+        off = 0
+        for s in range(max(n - 2, 0)):
+            assert harness.h_chs_off(n, s) == off
+            off += (n - 1 - s + 7) // 8
+        assert harness.h_chs_nrefl(n) == off
+    assert harness.h_bnd_threads(144) == 256 and harness.h_bnd_smem_bytes(144) <= (233472 - 2048) // 2
 
 
 @pytest.mark.parametrize("N", [1, 8, 12, 16, 27, 48, 100, 144, 150, 160])

@@ -64,7 +64,7 @@ SIGNATURES = {
     "vi_profile_reset": [],
     "vi_profile_read": [_ptr, _ptr, _i32],
 }
-PROFILE_KINDS = ("basis", "normal_eq", "tridiag", "tql", "apply", "chi2", "covariance", "estimate", "misc")
+PROFILE_KINDS = ("basis", "normal_eq", "tridiag", "tql", "apply", "chi2", "covariance", "estimate", "misc", "chase")
 
 
 def profile_read():

@@ -31,6 +31,8 @@
 #include "vi_tql.h"
 #include "vi_tridiag.h"
 #include "vi_tridiag_packed.h"
+#include "vi_band.h"
+#include "vi_chase.h"
 
 namespace {
 
@@ -54,8 +56,10 @@ struct Bump {
 struct SysBuf {
   int64_t cap;         // systems held at once (multiple of 32)
   int n, nreg, tapecap, nt, use_gx, ld, nchunk;
+  int two_stage;       // tridiagonalisation by band reduction + bulge chasing (vi_band.h, vi_chase.h)
+  int64_t vstride;     // doubles of reflector storage per system
   size_t smem;
-  double *V, *d, *e, *g, *tau, *scl, *tcs, *lam, *Csys, *chi2, *chi2p, *Xg;
+  double *V, *d, *e, *g, *tau, *scl, *tcs, *lam, *Csys, *chi2, *chi2p, *Xg, *band;
   int32_t *tix, *st, *rec, *rank, *nrot, *unit, *kidx, *gate;
 };
 
@@ -63,6 +67,12 @@ struct SysBuf {
 struct Downdate { const double* A; const double* Wm; const double* bm; int P; };
 
 constexpr int kChiGates = 1024;    // gates per CTA in k_chi2 (partial sums combined in fixed order)
+
+// two-stage reduction: orders whose panel fits the QR warp's registers and whose blocks fit one CTA's shared memory
+bool two_stage_ok(int n) {
+  static const bool off = getenv("VI_ONE_STAGE") != nullptr;
+  return !off && n <= VI_BND_NMAX && (size_t)vi_bnd_doubles(n) * sizeof(double) <= 227 * 1024;
+}
 
 int tri_threads(int n) {
   const int npair = vi_tri_npair(n);
@@ -85,7 +95,14 @@ void sysbuf_carve(Bump& b, SysBuf& S, int64_t cap, int n, int nreg, int P) {
   size_t smem_aux = (size_t)vi_tri_aux_doubles(n, S.nt) * sizeof(double);
   S.use_gx = (smem_x + smem_aux > 227 * 1024) ? 1 : 0;
   S.smem = S.use_gx ? smem_aux : smem_x + smem_aux;
-  S.V = b.take<double>(cap * n * n);
+  S.two_stage = two_stage_ok(n) ? 1 : 0;
+  S.vstride = (int64_t)n * n;
+  if (S.two_stage) {
+    const int64_t need = (int64_t)vi_bnd_vdoubles(n) + vi_chs_rdoubles(n) + 8;
+    if (need > S.vstride) S.vstride = need;
+  }
+  S.V = b.take<double>(cap * S.vstride);
+  S.band = S.two_stage ? b.take<double>(cap * (int64_t)vi_bnd_band_doubles(n)) : nullptr;
   S.d = b.take<double>(cap * n);
   S.e = b.take<double>(cap * n);
   S.g = b.take<double>(cap * n);
@@ -272,7 +289,7 @@ k_tridiag(const double* __restrict__ G, const double* __restrict__ y, const doub
   vi_tri_load(S, n, G + (int64_t)r * n * n, y + (int64_t)r * n, regs, B.lam + s * (B.nreg > 0 ? B.nreg : 1), B.nreg, tid, nt,
               arow, wj, bj);
   const bool bad = S.sc[1] != 0.0;
-  if (!bad) vi_tri_reduce(S, n, B.V + s * (int64_t)n * n, tid, nt);
+  if (!bad) vi_tri_reduce(S, n, B.V + s * B.vstride, tid, nt);
   const int64_t base = ileave(s, n);
   if (!bad)
     for (int i = tid; i < n; i += nt) {
@@ -307,7 +324,7 @@ k_tridiag_packed(const double* __restrict__ G, const double* __restrict__ y, con
   vi_trp_load(W, G + (int64_t)r * n * n, y + (int64_t)r * n, regs, B.lam + s * (B.nreg > 0 ? B.nreg : 1), B.nreg, tid, nt,
               arow, wj, bj);
   const bool bad = W.sc[1] != 0.0;
-  if (!bad) vi_trp_reduce(W, B.V + s * (int64_t)n * n, tid, nt);
+  if (!bad) vi_trp_reduce(W, B.V + s * B.vstride, tid, nt);
   const int64_t base = ileave(s, n);
   if (!bad)
     for (int i = tid; i < n; i += nt) {
@@ -317,6 +334,87 @@ k_tridiag_packed(const double* __restrict__ G, const double* __restrict__ y, con
       B.tau[base + (int64_t)i * 32] = W.tau[i];
     }
   if (tid == 0) { B.scl[s] = W.sc[0]; B.st[s] = bad ? VI_ST_NONFINITE : VI_ST_OK; }
+}
+
+// ---- two-stage tridiagonalisation (vi_band.h, vi_chase.h) ---------------------------------------------------------
+// Stage 1, one CTA per system: X in 8 x 8 blocks in shared memory (87.5 KB at n = 144 + 25 KB of panel factors: two
+// CTAs per SM), reduced to a band of half-width 8 by 17 block-reflector steps whose O(n^3) work is DMMA.  Writes the
+// band and g = Q1^T y to B.band, T and V of every panel to B.V.
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_band(const double* __restrict__ G, const double* __restrict__ y, const double* __restrict__ regs, SysBuf B, Downdate dd) {
+  extern __shared__ __align__(16) double sm[];
+  const int64_t s = blockIdx.x;
+  const int r = B.rec[s];
+  if (r < 0) { if (threadIdx.x == 0) B.st[s] = kSkip; return; }
+  const int n = B.n;
+  vi_bnd_ws W;
+  vi_bnd_carve(W, sm, n);
+  const double* arow = nullptr;
+  double wj = 0.0, bj = 0.0;
+  if (dd.A != nullptr) {
+    const int j = B.gate[s];
+    arow = dd.A + (int64_t)j * n;
+    wj = dd.Wm[(int64_t)r * dd.P + j];
+    bj = dd.bm[(int64_t)r * dd.P + j];
+  }
+  vi_bnd_load(W, G + (int64_t)r * n * n, y + (int64_t)r * n, regs, B.lam + s * (B.nreg > 0 ? B.nreg : 1), B.nreg, arow, wj, bj);
+  const bool bad = W.sc[1] != 0.0;
+  if (!bad) {
+    vi_bnd_reduce(W, B.V + s * B.vstride);
+    vi_bnd_store_band(W, B.band + s * (int64_t)vi_bnd_band_doubles(n));
+  }
+  if (threadIdx.x == 0) { B.scl[s] = W.sc[0]; B.st[s] = bad ? VI_ST_NONFINITE : VI_ST_OK; }
+}
+
+// Stage 2, one WARP per system: band -> tridiagonal by bulge chasing, four sweeps in flight (one per 8 lanes).
+// Leaves d, e, g = Q2^T Q1^T y in the interleaved layout the QL kernels read; reflectors behind stage 1's in B.V.
+constexpr int kChaseWarps = 4;
+__global__ void __launch_bounds__(kChaseWarps * 32)
+k_chase(int64_t nsys, SysBuf B) {
+  extern __shared__ __align__(16) double sm[];
+  const int n = B.n, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t s = (int64_t)blockIdx.x * kChaseWarps + warp;
+  if (s >= nsys || B.st[s] != VI_ST_OK) return;
+  const int np = vi_bnd_npad(n);
+  double* Bw = sm + (size_t)warp * vi_chs_doubles(n);
+  double* g = Bw + VI_CHS_LDB * (np + 8);
+  vi_chs_load(Bw, g, B.band + s * (int64_t)vi_bnd_band_doubles(n), n);
+  vi_chs_reduce(Bw, g, n, B.V + s * B.vstride + vi_bnd_vdoubles(n));
+  const int64_t base = ileave(s, n);
+  for (int i = lane; i < n; i += 32) {
+    B.d[base + (int64_t)i * 32] = Bw[i * VI_CHS_LDB];
+    B.e[base + (int64_t)i * 32] = (i + 1 < n) ? Bw[i * VI_CHS_LDB + 1] : 0.0;
+    B.g[base + (int64_t)i * 32] = g[i];
+  }
+}
+
+// c = Q1 Q2 u, one warp per system (two-stage counterpart of k_apply)
+__global__ void __launch_bounds__(kChaseWarps * 32)
+k_apply_ts(int64_t nsys, SysBuf B, double* __restrict__ Cout, int32_t* __restrict__ rank_out) {
+  extern __shared__ __align__(16) double sm[];
+  const int n = B.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t s = (int64_t)blockIdx.x * kChaseWarps + warp;
+  if (s >= nsys) return;
+  const int st = B.st[s];
+  if (st == kSkip) return;
+  double* Cs = Cout + s * (int64_t)n;
+  if (st != VI_ST_OK) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int i = lane; i < n; i += 32) Cs[i] = nan;
+    if (lane == 0) rank_out[s] = 0;
+    return;
+  }
+  const int np = vi_bnd_npad(n);
+  double* u = sm + (size_t)warp * (np + 8);
+  const int64_t base = ileave(s, n);
+  for (int i = lane; i < np + 8; i += 32) u[i] = (i < n) ? B.g[base + (int64_t)i * 32] : 0.0;
+  __syncwarp();
+  const double* Vg = B.V + s * B.vstride;
+  vi_chs_apply_q(u, n, Vg + vi_bnd_vdoubles(n));
+  vi_bnd_apply_q(u, n, Vg);
+  for (int i = lane; i < n; i += 32) Cs[i] = u[i];
+  if (lane == 0) rank_out[s] = B.rank[s];
 }
 
 __device__ __forceinline__ vi_tape tape_of(const SysBuf& B, int64_t s) {
@@ -484,7 +582,7 @@ k_apply(int64_t nsys, SysBuf B, double* __restrict__ Cout, int32_t* __restrict__
   const int64_t base = ileave(s, n);
   for (int i = lane; i < n; i += 32) w[i] = B.g[base + (int64_t)i * 32];
   __syncwarp();
-  const double* V = B.V + s * (int64_t)n * n;
+  const double* V = B.V + s * B.vstride;
   for (int j = n - 3; j >= 0; --j) {
     const double t = B.tau[base + (int64_t)j * 32];
     if (t == 0.0) continue;
@@ -531,7 +629,13 @@ __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %
 __host__ __device__ inline int eigvec_stage_doubles(int n) {
   const int tape = 2 * kEvTape * 2 + (2 * kEvTape + 1) / 2;                  // (c, s) pairs + int32 codes, two buffers
   const int rows = 2 * kEvRows * ((n + 1) & ~1) + 2 * kEvRows;               // rows + their tau, two buffers
-  return (tape > rows ? tape : rows) + 2;
+  const int npad = (n + 7) & ~7;
+  const int pan = 2 * (64 + 8 * (npad > 8 ? npad - 8 : 0));                  // two-stage: T + V of a panel, two buffers
+  const int refl = 2 * 128 * 8;                                              // two-stage: 128 reflectors, two buffers
+  int m = tape > rows ? tape : rows;
+  if (pan > m) m = pan;
+  if (refl > m) m = refl;
+  return m + 2;
 }
 
 // GLOBAL = true: orders whose n x ld block does not fit shared memory keep the eigenvector block in its output
@@ -586,12 +690,105 @@ __global__ void k_eigvec(int64_t s0, SysBuf B, double pinv_rtol, double* __restr
       __syncthreads();
     }
   }
+  // ---- E = Q1 Q2 Z (two-stage reduction): stage-2 reflectors in reverse order, then the block reflectors -------
+  if (B.two_stage) {
+    const double* Vg = B.V + s * B.vstride;
+    {
+      constexpr int CH = 128;                                 // reflectors per staged chunk (8 doubles each)
+      const double* R = Vg + vi_bnd_vdoubles(n);
+      const int nrefl = vi_chs_nrefl(n);
+      const int nchunk = (nrefl + CH - 1) / CH;
+      auto load = [&](int c) {                                // chunk c = reflectors [hi - CH, hi), hi = nrefl - c CH
+        const int hi = nrefl - c * CH, lo = hi - CH > 0 ? hi - CH : 0;
+        double* dst = stage + (c & 1) * CH * 8;
+        for (int e = i; e < (hi - lo) * 4; e += nt) cpa16(dst + 2 * e, R + (int64_t)lo * 8 + 2 * e);
+        cpa_commit();
+      };
+      int sw = vi_chs_nsweeps(n) - 1;                         // (sweep, step) of the reflector being applied
+      int kk = sw >= 0 ? vi_chs_nsteps(n, sw) - 1 : 0;
+      if (nchunk > 0) load(0);
+      for (int c = 0; c < nchunk; ++c) {
+        if (c + 1 < nchunk) { load(c + 1); cpa_wait<1>(); } else cpa_wait<0>();
+        __syncthreads();
+        const int hi = nrefl - c * CH, lo = hi - CH > 0 ? hi - CH : 0;
+        const double* src = stage + (c & 1) * CH * 8;
+        for (int idx = hi - 1; idx >= lo; --idx) {
+          const double* rv = src + (idx - lo) * 8;
+          const double tau = rv[0];
+          const int r0 = sw + 1 + 8 * kk;
+          if (i < n && tau != 0.0) {
+            const int L = (n - r0 < 8) ? n - r0 : 8;
+            double x[8], dot = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              x[q] = (q < L) ? col[(r0 + q) * ld] : 0.0;
+              dot = fma((q == 0) ? 1.0 : rv[q], x[q], dot);
+            }
+            dot *= tau;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (q < L) col[(r0 + q) * ld] = fma(-dot, (q == 0) ? 1.0 : rv[q], x[q]);
+          }
+          if (--kk < 0) { --sw; kk = sw >= 0 ? vi_chs_nsteps(n, sw) - 1 : 0; }
+        }
+        __syncthreads();
+      }
+    }
+    {
+      const int npad = vi_bnd_npad(n), nbk = npad >> 3;
+      const int npan = nbk - 1;
+      const int slot = 64 + 8 * (npad - 8);                   // doubles of the largest panel (T + V)
+      auto load = [&](int q) {                                // q-th panel from the end: p = npan - 1 - q
+        const int pp = npan - 1 - q;
+        const int cnt = 64 + 8 * (npad - 8 * (pp + 1));
+        double* dst = stage + (q & 1) * slot;
+        const double* srcp = Vg + vi_bnd_voff(npad, pp);
+        for (int e = i; e < cnt / 2; e += nt) cpa16(dst + 2 * e, srcp + 2 * e);
+        cpa_commit();
+      };
+      if (npan > 0) load(0);
+      for (int q = 0; q < npan; ++q) {
+        if (q + 1 < npan) { load(q + 1); cpa_wait<1>(); } else cpa_wait<0>();
+        __syncthreads();
+        const int pp = npan - 1 - q;
+        const int r0 = 8 * (pp + 1), m = npad - r0;
+        const int mv = (n - r0 < m) ? n - r0 : m;             // rows that exist in the n x n matrix
+        const double* Tm = stage + (q & 1) * slot;
+        const double* Vm = Tm + 64;
+        if (i < n) {
+          double t[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) t[c] = 0.0;
+          for (int r = 0; r < mv; ++r) {
+            const double x = col[(r0 + r) * ld];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) t[c] = fma(Vm[c * m + r], x, t[c]);
+          }
+          double t2[8];
+#pragma unroll
+          for (int a = 0; a < 8; ++a) {
+            double acc = 0.0;
+#pragma unroll
+            for (int c = a; c < 8; ++c) acc = fma(Tm[a * 8 + c], t[c], acc);
+            t2[a] = acc;
+          }
+          for (int r = 0; r < mv; ++r) {
+            double acc = 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc = fma(Vm[c * m + r], t2[c], acc);
+            col[(r0 + r) * ld] -= acc;
+          }
+        }
+        __syncthreads();
+      }
+    }
+  } else
   // ---- E = Q Z: reflectors n-3 .. 0 (vi_tri_backtransform order), rows staged kEvRows at a time ----------------
   {
     const int nld = (n + 1) & ~1;
     double* srow = stage;                                   // [2][kEvRows][nld]
     double* stau = stage + 2 * kEvRows * nld;               // [2][kEvRows]
-    const double* V = B.V + s * (int64_t)n * n;
+    const double* V = B.V + s * B.vstride;
     const int nref = n - 2;                                 // reflectors j = 0 .. n-3
     const int nbatch = nref > 0 ? (nref + kEvRows - 1) / kEvRows : 0;
     auto load = [&](int bidx) {
@@ -749,7 +946,7 @@ k_tql(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, int32_t* 
   vi_tape_apply_z(g, tape, nrot);
   const double scl = B.scl[s];
   for (int i = 0; i < n; ++i) g[i] = g[i] * scl;
-  vi_tri_backtransform(n, B.V + s * (int64_t)n * n, B.tau + base, 32, g.p, g.stride);
+  vi_tri_backtransform(n, B.V + s * B.vstride, B.tau + base, 32, g.p, g.stride);
   for (int i = 0; i < n; ++i) Cs[i] = g[i];
   rank_out[s] = rank;
 }
@@ -1246,6 +1443,21 @@ inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / p
 int run_tridiag(int64_t cnt, const double* G, const double* y, const double* regs, const SysBuf& B, cudaStream_t s,
                 Downdate dd = Downdate{nullptr, nullptr, nullptr, 0}) {
   if (cnt <= 0) return VI_OK;
+  if (B.two_stage) {
+    const size_t smem1 = (size_t)vi_bnd_doubles(B.n) * sizeof(double);
+    const int nt = vi_bnd_threads(B.n);
+    if (nt == 256) {
+      VI_CUDA(cudaFuncSetAttribute(k_band<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      VI_KERNEL(VI_K_TRIDIAG, s, (k_band<256, 2><<<(unsigned)cnt, nt, smem1, s>>>(G, y, regs, B, dd)));
+    } else {
+      VI_CUDA(cudaFuncSetAttribute(k_band<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      VI_KERNEL(VI_K_TRIDIAG, s, (k_band<128, 1><<<(unsigned)cnt, nt, smem1, s>>>(G, y, regs, B, dd)));
+    }
+    const size_t smem2 = (size_t)kChaseWarps * vi_chs_doubles(B.n) * sizeof(double);
+    VI_CUDA(cudaFuncSetAttribute(k_chase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    VI_KERNEL(VI_K_CHASE, s, k_chase<<<blocks(cnt, kChaseWarps), kChaseWarps * 32, smem2, s>>>(cnt, B));
+    return VI_OK;
+  }
   {
     // packed form whenever its working set fits one CTA (two CTAs per SM up to n = 144)
     static const bool force_full = getenv("VI_TRIDIAG_FULL") != nullptr;
@@ -1335,8 +1547,13 @@ int run_apply(int64_t cnt, const SysBuf& B, double rcond, double* Cout, int32_t*
     size_t smem1 = (size_t)kReplayWarps * L * per_sys;
     VI_CUDA(cudaFuncSetAttribute(k_replay, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     VI_KERNEL(VI_K_APPLY, s, k_replay<<<blocks(cnt, kReplayWarps * L), kReplayWarps * 32, smem1, s>>>(cnt, B, rcond, L));
-    size_t smem2 = (size_t)kApplyWarps * B.n * sizeof(double);
-    VI_KERNEL(VI_K_APPLY, s, k_apply<<<blocks(cnt, kApplyWarps), kApplyWarps * 32, smem2, s>>>(cnt, B, Cout, rank_out));
+    if (B.two_stage) {
+      size_t smem2 = (size_t)kChaseWarps * (vi_bnd_npad(B.n) + 8) * sizeof(double);
+      VI_KERNEL(VI_K_APPLY, s, k_apply_ts<<<blocks(cnt, kChaseWarps), kChaseWarps * 32, smem2, s>>>(cnt, B, Cout, rank_out));
+    } else {
+      size_t smem2 = (size_t)kApplyWarps * B.n * sizeof(double);
+      VI_KERNEL(VI_K_APPLY, s, k_apply<<<blocks(cnt, kApplyWarps), kApplyWarps * 32, smem2, s>>>(cnt, B, Cout, rank_out));
+    }
   } else {
     VI_KERNEL(VI_K_TQL, s, k_tql<<<blocks(cnt, 64), 64, 0, s>>>(cnt, B, rcond, Cout, rank_out));
   }

@@ -1,0 +1,560 @@
+// Stage 1 of the two-stage tridiagonalisation: dense symmetric X -> band of half-width 8, one CTA per system,
+// everything that is O(n^3) on the FP64 tensor pipe (mma.sync m8n8k4 f64 = SASS DMMA.8x8x4).
+//
+// Role on the hot path (kernel K3a): the reference solves (A^T W A + lambda R) C = A^T W b with
+// scipy.linalg.lstsq = LAPACK gelsd, rcond = eps (interpolate.py:462) some 70 times per record; here every such
+// system is reduced  X -> band (this file) -> tridiagonal (vi_chase.h) -> eigenvalues + rotation tape (vi_tql.h)
+// and the truncated spectral solve is applied to g = Q^T y.  The one-stage Householder reduction this replaces
+// (vi_tridiag_packed.h) spends 143 dependent steps of BLAS-2 work per system and sits at 6 % of the FP64 peak; the
+// blocked form below needs 17 panel steps whose matrix work is two tensor-core contractions each.
+//
+// Storage: lower triangle of X in 8 x 8 blocks, block (I, J), I >= J, at vi_bnd_blk(I, J) * 64 doubles, element (r, c)
+// at vi_bnd_el(r, c): an xor-swizzled layout in which the three fragment shapes the kernel needs (A-operand of a
+// block, A-operand of its transpose, accumulator) are all shared-memory bank-conflict free (DESIGN.md has the
+// derivation).  The panel factors V, W (m x 8) are column-major with leading dimension = 4 mod 8.
+//
+// Per panel p (block column p, rows below the diagonal block):
+//   P1  warp 0: Householder QR of the m x 8 panel held in registers (one shuffle round per column)
+//   P2  all warps: Y_I = sum_J A_IJ V_J for their block rows (DMMA), partial Gram blocks V^T Y, V^T V, V^T g
+//   P3  all warps: T (compact WY), K = -1/2 T^T (V^T Y); W_I = (Y_I + V_I K) T (DMMA); g -= V T^T V^T g
+//   P4  all warps: trailing update A_IJ -= V_I W_J^T + W_I V_J^T over the lower triangle (DMMA)
+// which is  A <- Q^T A Q,  Q = I - V T V^T  (two-sided block reflector, LAPACK dsytrd/dlatrd algebra in WY form).
+#pragma once
+#include "vi_simt.h"
+
+#ifndef VI_HD
+#if defined(__CUDACC__)
+#define VI_HD __host__ __device__ __forceinline__
+#else
+#define VI_HD inline
+#endif
+#endif
+
+#define VI_BND_MAXT 5            // panel rows per lane in the QR warp: n <= 32 * 5 + 8 = 168
+#define VI_BND_NMAX 168
+#define VI_BND_PART 136          // doubles per warp of partial Gram data: 64 (V^T Y) + 64 (V^T V) + 8 (V^T g)
+
+VI_HD int vi_bnd_npad(int n) { return (n + 7) & ~7; }
+VI_HD int vi_bnd_nbk(int n) { return vi_bnd_npad(n) >> 3; }
+VI_HD int vi_bnd_blk(int nbk, int I, int J) { return J * nbk - (J * (J - 1)) / 2 + (I - J); }
+VI_HD int vi_bnd_nblk(int n) { const int b = vi_bnd_nbk(n); return b * (b + 1) / 2; }
+VI_HD int vi_bnd_el(int r, int c) { return ((c >> 2) << 5) + (((r << 2) + (c & 3)) ^ ((c >> 2) << 3)); }
+VI_HD int vi_bnd_ldv(int n) { const int np = vi_bnd_npad(n); return (np > 8 ? np - 8 : 0) + 4; }
+// warps of the CTA: 8 (two CTAs of 256 threads per SM at n = 144), fewer for tiny systems
+VI_HD int vi_bnd_nwarp(int n) { const int b = vi_bnd_nbk(n); return b >= 9 ? 8 : (b >= 5 ? 4 : (b >= 3 ? 2 : 1)); }
+VI_HD int vi_bnd_threads(int n) { return 32 * vi_bnd_nwarp(n); }
+// shared-memory doubles of one CTA
+VI_HD int vi_bnd_doubles(int n) {
+  const int nt = vi_bnd_threads(n);
+  int part = vi_bnd_nwarp(n) * VI_BND_PART;
+  if (part < nt) part = nt;
+  return vi_bnd_nblk(n) * 64 + 2 * 8 * vi_bnd_ldv(n) + vi_bnd_npad(n) + part + 16;
+}
+// global storage of the block reflectors of one system: per panel p, T (64) then V column-major m x 8,
+// m = npad - 8 (p + 1)
+VI_HD int vi_bnd_voff(int npad, int p) { return 64 * p + 8 * p * (npad - 8) - 32 * p * (p - 1); }
+VI_HD int vi_bnd_vdoubles(int n) { return vi_bnd_voff(vi_bnd_npad(n), vi_bnd_nbk(n) - 1); }
+// band handed to stage 2: column j holds X[j + d][j], d = 0..8, at band[j * 9 + d]; then g (npad doubles)
+VI_HD int vi_bnd_band_doubles(int n) { return 10 * vi_bnd_npad(n); }
+
+struct vi_bnd_ws {
+  double* X;      // blocks
+  double* V;      // 8 x ldv, row i of the matrix at index i - 8
+  double* W;      // 8 x ldv: Y, then W
+  double* g;      // npad  right-hand side being transformed
+  double* part;   // nwarp x VI_BND_PART (aliases the max-reduction scratch of the load phase)
+  double* tau;    // 8
+  double* sc;     // 8: [0] scale 2^-ex, [1] non-finite flag
+  int n, npad, nbk, ldv, nw;
+};
+
+VI_HD void vi_bnd_carve(vi_bnd_ws& S, double* mem, int n) {
+  S.n = n; S.npad = vi_bnd_npad(n); S.nbk = S.npad >> 3; S.ldv = vi_bnd_ldv(n); S.nw = vi_bnd_nwarp(n);
+  const int nt = 32 * S.nw;
+  int part = S.nw * VI_BND_PART;
+  if (part < nt) part = nt;
+  S.X = mem; mem += vi_bnd_nblk(n) * 64;
+  S.V = mem; mem += 8 * S.ldv;
+  S.W = mem; mem += 8 * S.ldv;
+  S.g = mem; mem += S.npad;
+  S.part = mem; mem += part;
+  S.tau = mem; mem += 8;
+  S.sc = mem; mem += 8;
+}
+
+#if defined(__CUDACC__) || defined(VI_EMU)
+
+// X <- scl (0.5 (G + G^T) + sum_r lam[r] Reg_r [- wj a a^T]) in block layout, zero padding, scl = 2^-exponent(max|X|);
+// g <- y [- wj bj a].  Same arithmetic per element as vi_trp_load (GCV downdate: interpolate.py:332-349).
+VI_DEV void vi_bnd_load(const vi_bnd_ws& S, const double* G, const double* y, const double* regs, const double* lam,
+                        int nreg, const double* arow, double wj, double bj) {
+  const int n = S.n, nbk = S.nbk, tid = vi_tid(), nt = vi_nthreads();
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  double mx = 0.0, bad = 0.0;
+  const int nblk = nbk * (nbk + 1) / 2;
+  // one block per warp and trip: lanes cover 4 rows x 8 columns twice (row-major G: 64-byte segments)
+  int I = 0, J = 0;                      // block index b -> (I, J): column-block-major
+  for (int b = 0; b < nblk; ++b) {
+    if ((b % nw) == warp) {
+      double* blk = S.X + b * 64;
+      for (int h = 0; h < 2; ++h) {
+        const int r = (lane >> 3) + 4 * h, c = lane & 7;
+        const int i = 8 * I + r, k = 8 * J + c;
+        double x = 0.0;
+        if (i < n && k < n) {
+          x = 0.5 * (G[(int64_t)i * n + k] + G[(int64_t)k * n + i]);
+          for (int q = 0; q < nreg; ++q) {
+            const double l = lam[q];
+            if (l != 0.0) x = fma(l, regs[((int64_t)q * n + i) * n + k], x);
+          }
+          if (arow) x = x - wj * (arow[i] * arow[k]);
+          if (!(fabs(x) <= 1.79769313486231570e308)) bad = 1.0;
+          mx = fmax(mx, fabs(x));
+        }
+        blk[vi_bnd_el(r, c)] = x;
+      }
+    }
+    if (++I == nbk) { ++J; I = J; }
+  }
+  for (int i = tid; i < S.npad; i += nt) {
+    double t = 0.0;
+    if (i < n) {
+      t = y[i];
+      if (arow) t = t - (wj * bj) * arow[i];
+      if (!(fabs(t) <= 1.79769313486231570e308)) bad = 1.0;
+    }
+    S.g[i] = t;
+  }
+  S.part[tid] = (bad != 0.0) ? -1.0 : mx;
+  vi_cta_sync();
+  if (tid == 0) {
+    double m = 0.0, bd = 0.0;
+    for (int t = 0; t < nt; ++t) { const double r = S.part[t]; if (r < 0.0) bd = 1.0; else m = fmax(m, r); }
+    int ex = 0;
+    double scl = 1.0;
+    if (bd == 0.0 && m > 0.0) { frexp(m, &ex); scl = ldexp(1.0, -ex); }
+    S.sc[0] = scl; S.sc[1] = bd;
+  }
+  vi_cta_sync();
+  const double scl = S.sc[0];
+  if (scl != 1.0)
+    for (int idx = tid; idx < nblk * 64; idx += nt) S.X[idx] *= scl;
+  vi_cta_sync();
+}
+
+// ---- P1: Householder QR of panel p by warp 0 -----------------------------------------------------------------
+// Lane l owns the panel rows r0 + l + 32 t (r0 = 8 (p + 1)), all 8 columns, in registers.  Column j: one shuffle
+// round gives every lane s_c = sum_{i > pivot} a_j[i] a_c[i] for c = j..7 (c = j: the squared norm); then
+// v = (1, a_j scale), beta, tau and the update a_c -= tau (v^T a_c) v are local except for the pivot-row elements.
+// Leaves V (unit lower trapezoidal, zeros above) in S.V, tau in S.tau, R in block (p + 1, p).
+VI_DEV void vi_bnd_panel_qr(const vi_bnd_ws& S, int p) {
+  const int lane = vi_tid() & 31;
+  const int r0 = 8 * (p + 1), npad = S.npad, nbk = S.nbk, ldv = S.ldv;
+  double a[8][VI_BND_MAXT];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int t = 0; t < VI_BND_MAXT; ++t) {
+    const int i = r0 + lane + 32 * t;
+    const bool in = i < npad;
+    const double* blk = S.X + vi_bnd_blk(nbk, in ? (i >> 3) : p + 1, p) * 64;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 8; ++c) a[c][t] = in ? blk[vi_bnd_el(i & 7, c)] : 0.0;
+  }
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int j = 0; j < 8; ++j) {
+    // rows strictly below the pivot row r0 + j: t > 0, or t == 0 and lane > j
+    double s[8];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int c = j; c < 8; ++c) {
+      double acc = (lane > j) ? a[j][0] * a[c][0] : 0.0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int t = 1; t < VI_BND_MAXT; ++t) acc = fma(a[j][t], a[c][t], acc);
+      s[c] = acc;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int c = j; c < 8; ++c) s[c] += vi_shfl_xor(s[c], o);
+    }
+    const double alpha = vi_shfl(a[j][0], j);
+    double beta, tau, scale;
+    vi_reflector_scalars(alpha, s[j], &beta, &tau, &scale);
+    // v in place of column j (rows below the pivot); pivot element becomes beta (R's diagonal)
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int t = 0; t < VI_BND_MAXT; ++t) {
+      const bool below = (t > 0) || (lane > j);
+      if (below) a[j][t] = a[j][t] * scale;
+    }
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int c = j + 1; c < 8; ++c) {
+      const double apc = vi_shfl(a[c][0], j);                 // pivot-row element of column c
+      const double w = tau * (apc + scale * s[c]);            // tau v^T a_c
+      if (lane == j) a[c][0] = a[c][0] - w;
+      else if (lane > j) a[c][0] = fma(-w, a[j][0], a[c][0]);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int t = 1; t < VI_BND_MAXT; ++t) a[c][t] = fma(-w, a[j][t], a[c][t]);
+    }
+    if (lane == j) a[j][0] = beta;
+    if (lane == 0) S.tau[j] = tau;
+  }
+  // write back: V to shared memory, R to block (p + 1, p)
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int t = 0; t < VI_BND_MAXT; ++t) {
+    const int i = r0 + lane + 32 * t;
+    if (i < npad) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int c = 0; c < 8; ++c) {
+        const int piv = r0 + c;
+        S.V[c * ldv + (i - 8)] = (i > piv) ? a[c][t] : (i == piv ? 1.0 : 0.0);
+      }
+    }
+  }
+  if (lane < 8) {
+    double* blk = S.X + vi_bnd_blk(nbk, p + 1, p) * 64;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 8; ++c) blk[vi_bnd_el(lane, c)] = (lane <= c) ? a[c][0] : 0.0;
+  }
+}
+
+// fragment conversions inside a warp ---------------------------------------------------------------------------
+// accumulator (row lane/4, columns 2 (lane%4) + {0,1}) -> A operand of k-step t (row lane/4, column lane%4 + 4 t)
+VI_DEV void vi_bnd_c_to_a(double c0, double c1, double* a0, double* a1) {
+  const int lane = vi_tid() & 31;
+  const int q = lane & ~3, m = lane & 3;
+  // column m + 4 t lives in lane q + (m + 4 t) / 2, element (m + 4 t) % 2 = m % 2
+  const int s0 = q + (m >> 1), s1 = q + (m >> 1) + 2;
+  const double x0 = vi_shfl(c0, s0), y0 = vi_shfl(c1, s0);
+  const double x1 = vi_shfl(c0, s1), y1 = vi_shfl(c1, s1);
+  *a0 = (m & 1) ? y0 : x0;
+  *a1 = (m & 1) ? y1 : x1;
+}
+// accumulator -> B operand of k-step t: element (row = lane%4 + 4 t, column = lane/4)
+VI_DEV void vi_bnd_c_to_b(double c0, double c1, double* b0, double* b1) {
+  const int lane = vi_tid() & 31;
+  const int n = lane >> 2;                       // wanted column
+  const int k0 = lane & 3, k1 = (lane & 3) + 4;  // wanted rows
+  const int s0 = 4 * k0 + (n >> 1), s1 = 4 * k1 + (n >> 1);
+  const double x0 = vi_shfl(c0, s0), y0 = vi_shfl(c1, s0);
+  const double x1 = vi_shfl(c0, s1), y1 = vi_shfl(c1, s1);
+  *b0 = (n & 1) ? y0 : x0;
+  *b1 = (n & 1) ? y1 : x1;
+}
+
+// ---- P2: Y_I = sum_J A_IJ V_J for this warp's block rows; partial Gram blocks ---------------------------------
+VI_DEV void vi_bnd_symm(const vi_bnd_ws& S, int p) {
+  const int tid = vi_tid(), warp = tid >> 5, lane = tid & 31;
+  const int nbk = S.nbk, ldv = S.ldv, nw = S.nw;
+  const int q4 = lane >> 2, m4 = lane & 3;
+  double my0 = 0.0, my1 = 0.0, ss0 = 0.0, ss1 = 0.0, ug = 0.0;
+  // operand offsets that do not depend on the block: B / transposed-A pattern  (col = lane/4, row = lane%4 + 4 t)
+  const int vb = q4 * ldv + m4;                          // + 8 J - 8 + 4 t
+  const int ea0 = lane, ea1 = 32 + (lane ^ 8);           // A operand of a stored block, k-steps 0 and 1
+  const int et0 = vi_bnd_el(m4, q4), et1 = vi_bnd_el(m4 + 4, q4);   // A operand of its transpose
+  for (int I = p + 1 + warp; I < nbk; I += nw) {
+    double y0 = 0.0, y1 = 0.0;
+    for (int J = p + 1; J < nbk; ++J) {
+      const double* vj = S.V + vb + 8 * J - 8;
+      double a0, a1;
+      if (J <= I) {
+        const double* blk = S.X + vi_bnd_blk(nbk, I, J) * 64;
+        a0 = blk[ea0]; a1 = blk[ea1];
+      } else {
+        const double* blk = S.X + vi_bnd_blk(nbk, J, I) * 64;
+        a0 = blk[et0]; a1 = blk[et1];
+      }
+      vi_mma884(y0, y1, a0, vj[0]);
+      vi_mma884(y0, y1, a1, vj[4]);
+    }
+    // Y_I -> shared (W panel), accumulator layout: (row q4, columns 2 m4, 2 m4 + 1)
+    double* wi = S.W + 8 * I - 8 + q4;
+    wi[(2 * m4) * ldv] = y0;
+    wi[(2 * m4 + 1) * ldv] = y1;
+    vi_warp_sync();
+    // partial V_I^T Y_I and V_I^T V_I: A operand = V_I^T (same addresses as V_I as a B operand)
+    const double va0 = S.V[vb + 8 * I - 8], va1 = S.V[vb + 8 * I - 8 + 4];
+    const double yb0 = S.W[vb + 8 * I - 8], yb1 = S.W[vb + 8 * I - 8 + 4];
+    vi_mma884(my0, my1, va0, yb0);
+    vi_mma884(my0, my1, va1, yb1);
+    vi_mma884(ss0, ss1, va0, va0);
+    vi_mma884(ss0, ss1, va1, va1);
+    // partial V_I^T g_I (lanes 0..7: one column each)
+    if (lane < 8) {
+      const double* vc = S.V + lane * ldv + 8 * I - 8;
+      const double* gi = S.g + 8 * I;
+      double acc = 0.0;
+      for (int r = 0; r < 8; ++r) acc = fma(vc[r], gi[r], acc);
+      ug += acc;
+    }
+  }
+  double* pw = S.part + warp * VI_BND_PART;
+  pw[q4 * 8 + 2 * m4] = my0; pw[q4 * 8 + 2 * m4 + 1] = my1;
+  pw[64 + q4 * 8 + 2 * m4] = ss0; pw[64 + q4 * 8 + 2 * m4 + 1] = ss1;
+  if (lane < 8) pw[128 + lane] = ug;
+}
+
+// 8-way select of x[idx], idx in 0..7 (registers cannot be indexed dynamically)
+VI_DEV double vi_sel8(const double (&x)[8], int idx) {
+  const double a = (idx & 1) ? x[1] : x[0], b = (idx & 1) ? x[3] : x[2];
+  const double c = (idx & 1) ? x[5] : x[4], d = (idx & 1) ? x[7] : x[6];
+  const double e = (idx & 2) ? b : a, f = (idx & 2) ? d : c;
+  return (idx & 4) ? f : e;
+}
+
+// ---- P3: T, K = -1/2 T^T (V^T Y), W_I = (Y_I + V_I K) T, g -= V T^T (V^T g); reflectors to global -------------
+VI_DEV void vi_bnd_wpanel(const vi_bnd_ws& S, int p, double* Vg) {
+  const int tid = vi_tid(), warp = tid >> 5, lane = tid & 31;
+  const int nbk = S.nbk, ldv = S.ldv, nw = S.nw, npad = S.npad;
+  const int q4 = lane >> 2, m4 = lane & 3;
+  // sums of the partial Gram blocks: lane holds elements e = lane and lane + 32 (row-major 8 x 8)
+  double my[2] = {0.0, 0.0}, sv[2] = {0.0, 0.0}, ugs = 0.0;
+  for (int w = 0; w < nw; ++w) {
+    const double* pw = S.part + w * VI_BND_PART;
+    my[0] += pw[lane]; my[1] += pw[32 + lane];
+    sv[0] += pw[64 + lane]; sv[1] += pw[96 + lane];
+    if (lane < 8) ugs += pw[128 + lane];
+  }
+  // T (upper triangular, LAPACK dlarft forward/columnwise): lane i (mod 8) builds row i,
+  //   T[i][i] = tau_i,  T[i][j] = -tau_j sum_{k=i}^{j-1} T[i][k] S[k][j]  (i < j),  S = V^T V
+  const int ti = lane & 7;
+  double tr[8];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int j = 0; j < 8; ++j) tr[j] = 0.0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int j = 0; j < 8; ++j) {
+    const double tj = S.tau[j];
+    double acc = 0.0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int k = 0; k < j; ++k) {
+      const int e = k * 8 + j;                                 // S[k][j] -> lane e % 32, register e / 32
+      const double skj = vi_shfl(e < 32 ? sv[0] : sv[1], e & 31);
+      acc = fma(tr[k], skj, acc);                              // tr[k] = 0 for k < i
+    }
+    tr[j] = (ti == j) ? tj : ((ti < j) ? -tj * acc : 0.0);
+  }
+  // every warp has read all the partials: from here on a warp's own slot of S.part is its private scratch
+  vi_cta_sync();
+  double* scr = S.part + warp * VI_BND_PART;                     // [0, 64): T row-major, [64, 128): K row-major
+  if (lane < 8) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 8; ++j) scr[lane * 8 + j] = tr[j];
+  }
+  vi_warp_sync();
+  // B operand T[k][n] (k = lane%4 + 4 t, n = lane/4); the A operand of T^T, (T^T)[r][k] = T[k][r], is the same value
+  const double tb0 = scr[m4 * 8 + q4], tb1 = scr[(m4 + 4) * 8 + q4];
+  // K = -1/2 T^T My: B = My[k][n] = element 8 k + n of the row-major sum held as (lane, lane + 32)
+  double k0 = 0.0, k1 = 0.0;
+  {
+    const double mb0 = vi_shfl(my[0], 8 * m4 + q4);            // k = m4     -> e = 8 m4 + q4 < 32
+    const double mb1 = vi_shfl(my[1], 8 * m4 + q4);            // k = m4 + 4 -> e - 32
+    vi_mma884(k0, k1, tb0, mb0);
+    vi_mma884(k0, k1, tb1, mb1);
+  }
+  scr[64 + q4 * 8 + 2 * m4] = -0.5 * k0;
+  scr[64 + q4 * 8 + 2 * m4 + 1] = -0.5 * k1;
+  vi_warp_sync();
+  const double kb0 = scr[64 + m4 * 8 + q4], kb1 = scr[64 + (m4 + 4) * 8 + q4];
+  // tg = T^T ug: lane k (< 8) holds row k of T and ug[k]; sum over k of T[k][c] ug[k] per column c
+  double tg[8];
+  {
+    const double u = (lane < 8) ? ugs : 0.0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 8; ++c) tg[c] = vi_oct_allsum((lane < 8) ? tr[c] * u : 0.0);
+    // lanes 0..7 now hold the totals; broadcast to the warp
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 8; ++c) tg[c] = vi_shfl(tg[c], 0);
+  }
+  const int m = npad - 8 * (p + 1);
+  double* vgp = Vg ? Vg + vi_bnd_voff(npad, p) : nullptr;
+  if (vgp && warp == 0) {                                        // T row-major
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 8; ++j)
+      if (lane < 8) vgp[lane * 8 + j] = tr[j];
+  }
+  for (int I = p + 1 + warp; I < nbk; I += nw) {
+    const int ro = 8 * I - 8;
+    // U_I = Y_I + V_I K
+    const double* wi = S.W + ro + q4;
+    double u0 = wi[(2 * m4) * ldv], u1 = wi[(2 * m4 + 1) * ldv];
+    const double* vi = S.V + ro + q4;                            // A operand of V_I: (row q4, col m4 + 4 t)
+    vi_mma884(u0, u1, vi[m4 * ldv], kb0);
+    vi_mma884(u0, u1, vi[(m4 + 4) * ldv], kb1);
+    // W_I = U_I T
+    double ua0, ua1;
+    vi_bnd_c_to_a(u0, u1, &ua0, &ua1);
+    double w0 = 0.0, w1 = 0.0;
+    vi_mma884(w0, w1, ua0, tb0);
+    vi_mma884(w0, w1, ua1, tb1);
+    vi_warp_sync();                                              // every lane has read Y_I
+    double* wo = S.W + ro + q4;
+    wo[(2 * m4) * ldv] = w0;
+    wo[(2 * m4 + 1) * ldv] = w1;
+    // g_I -= V_I tg; V_I to global
+    if (lane < 8) {
+      double acc = 0.0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int c = 0; c < 8; ++c) acc = fma(S.V[c * ldv + ro + lane], tg[c], acc);
+      S.g[8 * I + lane] -= acc;
+    }
+    if (vgp) {
+      for (int e = lane; e < 64; e += 32) {
+        const int c = e >> 3, r = e & 7;
+        vgp[64 + c * m + (8 * I + r - 8 * (p + 1))] = S.V[c * ldv + ro + r];
+      }
+    }
+  }
+}
+
+// ---- P4: A_IJ -= V_I W_J^T + W_I V_J^T over the lower triangle of the trailing matrix ---------------------------
+VI_DEV void vi_bnd_update_row(const vi_bnd_ws& S, int p, int I) {
+  const int lane = vi_tid() & 31, q4 = lane >> 2, m4 = lane & 3;
+  const int nbk = S.nbk, ldv = S.ldv;
+  const int ro = 8 * I - 8 + q4;
+  // A operands (row q4, column m4 + 4 t), negated so that the MMA subtracts
+  const double nv0 = -S.V[m4 * ldv + ro], nv1 = -S.V[(m4 + 4) * ldv + ro];
+  const double nw0 = -S.W[m4 * ldv + ro], nw1 = -S.W[(m4 + 4) * ldv + ro];
+  const int ec = vi_bnd_el(q4, 2 * m4);                              // accumulator pair (16-byte aligned)
+  for (int J = p + 1; J <= I; ++J) {
+    double* blk = S.X + vi_bnd_blk(nbk, I, J) * 64 + ec;
+    double c0 = blk[0], c1 = blk[1];
+    // B operands: (W_J^T)[k][n] = W[8 J + n][k]  ->  W[k * ldv + 8 J - 8 + n], k = m4 + 4 t, n = q4
+    const int bo = 8 * J - 8 + q4;
+    vi_mma884(c0, c1, nv0, S.W[m4 * ldv + bo]);
+    vi_mma884(c0, c1, nv1, S.W[(m4 + 4) * ldv + bo]);
+    vi_mma884(c0, c1, nw0, S.V[m4 * ldv + bo]);
+    vi_mma884(c0, c1, nw1, S.V[(m4 + 4) * ldv + bo]);
+    blk[0] = c0; blk[1] = c1;
+  }
+}
+
+VI_DEV void vi_bnd_update(const vi_bnd_ws& S, int p) {
+  const int warp = vi_tid() >> 5, nw = S.nw, nbk = S.nbk;
+  const int mb = nbk - (p + 1);
+  // rows paired short + long (row p+1+q has q+1 blocks, row nbk-1-q has mb-q): equal work per pair
+  for (int q = warp; 2 * q < mb; q += nw) {
+    const int Ia = p + 1 + q, Ib = nbk - 1 - q;
+    vi_bnd_update_row(S, p, Ia);
+    if (Ib > Ia) vi_bnd_update_row(S, p, Ib);
+  }
+}
+
+// Whole reduction.  After the call the band (half-width 8) sits in the diagonal and first sub-diagonal blocks,
+// S.g = Q1^T y, and Vg (global, may be null) holds T and V of every panel.
+VI_DEV void vi_bnd_reduce(const vi_bnd_ws& S, double* Vg) {
+  const int warp = vi_tid() >> 5;
+  for (int p = 0; p + 1 < S.nbk; ++p) {
+    if (warp == 0) vi_bnd_panel_qr(S, p);
+    vi_cta_sync();
+    vi_bnd_symm(S, p);
+    vi_cta_sync();
+    vi_bnd_wpanel(S, p, Vg);
+    vi_cta_sync();
+    vi_bnd_update(S, p);
+    vi_cta_sync();
+  }
+}
+
+// band[j * 9 + d] = X[j + d][j] (d = 0..8, zero beyond the matrix), then g
+VI_DEV void vi_bnd_store_band(const vi_bnd_ws& S, double* band) {
+  const int n = S.n, npad = S.npad, nbk = S.nbk, tid = vi_tid(), nt = vi_nthreads();
+  for (int e = tid; e < 9 * npad; e += nt) {
+    const int j = e / 9, d = e - 9 * j;
+    const int i = j + d;
+    double x = 0.0;
+    if (i < n && j < n) x = S.X[vi_bnd_blk(nbk, i >> 3, j >> 3) * 64 + vi_bnd_el(i & 7, j & 7)];
+    band[e] = x;
+  }
+  for (int i = tid; i < npad; i += nt) band[9 * npad + i] = S.g[i];
+}
+
+// u <- Q1 u by one warp: block reflectors I - V T V^T in reverse panel order (u: shared memory, n entries valid,
+// padded to npad with zeros by the caller or simply not read: rows >= n of V are zero).
+VI_DEV void vi_bnd_apply_q(double* u, int n, const double* Vg) {
+  const int lane = vi_tid() & 31;
+  const int npad = vi_bnd_npad(n), nbk = npad >> 3;
+  for (int p = nbk - 2; p >= 0; --p) {
+    const int r0 = 8 * (p + 1), m = npad - r0;
+    const double* T = Vg + vi_bnd_voff(npad, p);
+    const double* V = T + 64;
+    double t[8];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 8; ++c) t[c] = 0.0;
+    for (int i = lane; i < m; i += 32) {
+      const double ui = (r0 + i < n) ? u[r0 + i] : 0.0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int c = 0; c < 8; ++c) t[c] = fma(V[c * m + i], ui, t[c]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int c = 0; c < 8; ++c) t[c] += vi_shfl_xor(t[c], o);
+    }
+    double t2[8];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int a = 0; a < 8; ++a) {
+      double acc = 0.0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int c = a; c < 8; ++c) acc = fma(T[a * 8 + c], t[c], acc);
+      t2[a] = acc;
+    }
+    for (int i = lane; i < m; i += 32) {
+      if (r0 + i < n) {
+        double acc = 0.0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int c = 0; c < 8; ++c) acc = fma(V[c * m + i], t2[c], acc);
+        u[r0 + i] -= acc;
+      }
+    }
+    vi_warp_sync();
+  }
+}
+
+#endif  // device / emulator

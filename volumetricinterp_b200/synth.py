@@ -89,6 +89,23 @@ def true_coeffs(nbasis, maxl=None, seed=1, n_terms=5, scale=1e11):
     return c
 
 
+def structured_coeffs(nbasis, maxl, n_terms=10, amp=0.3, seed=1, scale=1e11):
+    """Like true_coeffs, with horizontal structure beyond the first five terms (degrees l <= 2 of the first radial
+    order, a few terms of the next two) at `amp` of their amplitude.  With the curvature regulariser this puts
+    chi2(lambda = 1) well above the gate count while the unregularised chi2 stays near noise_scale^2 of it, so the
+    reference's chi2 = nu search (interpolate.py:173-218) finds a root for (almost) every record instead of ending
+    "too smooth" (lambda = 0) or without a bracket (NaN record)."""
+    rng = np.random.default_rng(seed)
+    L2 = maxl * maxl
+    order = [0, L2, 1, 2, 3, 4, 5, 6, 7, 8, L2 + 1, L2 + 2, L2 + 3, 2 * L2, 2 * L2 + 1]
+    idx = np.array(order[:n_terms]) % nbasis
+    c = np.zeros(nbasis)
+    c[idx] = scale * rng.uniform(0.5, 1.5, idx.size) * rng.choice([-1.0, 1.0], idx.size)
+    c[idx[5:]] *= amp
+    c[idx[0]] = abs(c[idx[0]]) * 3.0
+    return c
+
+
 def make_records(A, nrecords, seed=2, c_true=None, bad_frac=0.10, drift=0.05,
                  maxl=None, noise_scale=1.0):
     """Records generated from the model itself: d = A c + sigma N(0,1) with
