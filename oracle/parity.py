@@ -21,17 +21,19 @@ ST_OK, ST_TOO_SMOOTH, ST_NO_ROOT = 0, 1, 2
 
 def oracle_record(A_all, value_r, error_r, omega, name='curvature', order='einsum'):
     """Reference algorithm on one record.  order='einsum': the reference's own normal equations (bit for bit the
-    reference's fit); 'blas': same algorithm, A^T W A formed by BLAS -- the envelope run."""
+    reference's fit); 'blas': same algorithm, A^T W A formed by BLAS -- the envelope run; 'gelss': the reference's
+    normal equations, lstsq through LAPACK gelss instead of gelsd (same rcond) -- the second envelope."""
     ok = np.isfinite(value_r)
     A = np.asfortranarray(A_all[ok])
     b = value_r[ok]
     W = np.array(error_r[ok] ** (-2))
-    if order == 'einsum':
+    if order in ('einsum', 'gelss'):
         G, y = rp.normal_equations(A, W, b)
     else:
         AW = A * W[:, None]
         G, y = AW.T @ A, AW.T @ b
-    out = rp.fit_record_given_normal_equations(A, b, W, G, y, {name: omega}, [name])
+    out = rp.fit_record_given_normal_equations(A, b, W, G, y, {name: omega}, [name],
+                                               lapack_driver='gelss' if order == 'gelss' else None)
     lam = out['lam'][name]
     out['status'] = ST_NO_ROOT if np.isnan(lam) else (ST_TOO_SMOOTH if lam == 0 else ST_OK)
     out['lam'] = float(lam)
@@ -94,30 +96,41 @@ def summarize(rows):
             'chi2_rel_diff': stats('chi2_rel'), 'table_rel_diff': stats('table_rel')}
 
 
-def compare(gpu_rows, ref_rows, env_rows, A_all, value):
-    """gpu_rows / ref_rows / env_rows: per-record dicts (same records, same order)."""
-    g, e, per = [], [], []
+def _pair(a, b, A_all, value_r):
+    d = _cmp(a, b, A_all, value_r)
+    if 'rank_diff' in d:
+        d['rank_diff_abs'] = abs(d['rank_diff'])
+    if a.get('table') is not None and b.get('table') is not None:
+        t, nt = table_agreement(a['table'], b['table'])
+        if t is not None:
+            d['table_rel'] = t
+            d['table_decades_compared'] = nt
+    return d
+
+
+def compare(gpu_rows, ref_rows, env_rows, A_all, value, alt_rows=None):
+    """gpu_rows / ref_rows / env_rows / alt_rows: per-record dicts (same records, same order).  ref = the reference's
+    algorithm as shipped (einsum normal equations, gelsd); env = the same with BLAS-order normal equations; alt = the
+    same with LAPACK gelss instead of gelsd (both envelopes: equally valid executions of the reference)."""
+    keys = ('status', 'sf', 'k_lo', 'lam', 'rank')
+    g, e, al, ga, per = [], [], [], [], []
     for r, (a, b, c) in enumerate(zip(gpu_rows, ref_rows, env_rows)):
         if a.get('sf') is None and a.get('nu') is not None and b.get('npts'):
             a['sf'] = a['nu'] / b['npts']
-        dg = _cmp(a, b, A_all, value[r])
-        if 'rank_diff' in dg:
-            dg['rank_diff_abs'] = abs(dg['rank_diff'])
-        if a.get('table') is not None and b.get('table') is not None:
-            t, nt = table_agreement(a['table'], b['table'])
-            if t is not None:
-                dg['table_rel'] = t
-                dg['table_decades_compared'] = nt
-        de = _cmp(c, b, A_all, value[r]) if c is not None else {}
-        if 'rank_diff' in de:
-            de['rank_diff_abs'] = abs(de['rank_diff'])
-        if c is not None and c.get('table') is not None and b.get('table') is not None:
-            t, nt = table_agreement(c['table'], b['table'])
-            if t is not None:
-                de['table_rel'] = t
+        dg = _pair(a, b, A_all, value[r])
+        de = _pair(c, b, A_all, value[r]) if c is not None else {}
+        row = {'record': r, 'ref': {k: b.get(k) for k in keys}, 'gpu': {k: a.get(k) for k in keys},
+               'env_blas': {k: c.get(k) for k in keys} if c is not None else None,
+               'gpu_vs_ref': dg, 'env_blas_vs_ref': de}
         g.append(dg); e.append(de)
-        per.append({'record': r, 'ref': {k: b.get(k) for k in ('status', 'sf', 'k_lo', 'lam', 'rank')},
-                    'gpu': {k: a.get(k) for k in ('status', 'sf', 'k_lo', 'lam', 'rank')},
-                    'env': {k: c.get(k) for k in ('status', 'sf', 'k_lo', 'lam', 'rank')} if c is not None else None,
-                    'gpu_vs_ref': dg, 'env_vs_ref': de})
-    return {'gpu_vs_reference': summarize(g), 'reference_vs_itself_blas_order': summarize(e), 'per_record': per}
+        if alt_rows is not None:
+            x = alt_rows[r]
+            da, dga = _pair(x, b, A_all, value[r]), _pair(a, x, A_all, value[r])
+            al.append(da); ga.append(dga)
+            row.update(env_gelss={k: x.get(k) for k in keys}, env_gelss_vs_ref=da, gpu_vs_env_gelss=dga)
+        per.append(row)
+    out = {'gpu_vs_reference': summarize(g), 'reference_vs_itself_blas_order': summarize(e), 'per_record': per}
+    if alt_rows is not None:
+        out['reference_vs_itself_gelss_driver'] = summarize(al)
+        out['gpu_vs_reference_with_gelss_driver'] = summarize(ga)
+    return out

@@ -1,0 +1,203 @@
+"""Tier-3 parity of the CUDA fit at the rank-deficient orders, N = 27 and the benchmarked
+N = 144, asserted against the reference's own trace and reproducibility envelope; plus the operator-seam, Estimate
+and large-model cases added in round 2.
+
+What "inside the envelope" means: tests/golden/envelope_<case>.json (oracle/make_golden_envelope.py) holds three
+equally valid executions of the reference's algorithm on every golden record -- as shipped (gelsd), with BLAS-order
+normal equations, with LAPACK gelss instead of gelsd.  They agree with each other on the scale factor and the
+bracket decade but NOT on lambda or the fitted densities (up to 0.13 in log10 lambda and 0.7 in A.C at N = 144).
+The CUDA path is required to agree where they agree and to lie no farther from the nearest of them than they lie
+from each other where they do not."""
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden, oracle_model, product_model
+import ref_port as rp
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(float).eps
+DRIVERS = ("gelsd", "blas", "gelss")
+
+
+def _envelope(name):
+    with open(os.path.join(GOLDEN, f"envelope_{name}.json")) as f:
+        return json.load(f)["records"]
+
+
+def _fit(cuda, g, **kw):
+    from volumetricinterp_b200 import fit
+    return fit.fit_records(product_model(g), g["lat"], g["lon"], g["alt"], g["value"], g["error"], g["regs"], "chi2",
+                           device=cuda, **kw)
+
+
+@pytest.mark.parametrize("name", ["mid27", "c1_144"])
+def test_search_agrees_with_reference_trace_and_envelope(cuda, name):
+    """(a) record status, scale factor and bracket decade identical to the reference (interpolate.py:173-211);
+    (b) the chi2(10^-k) table equals the unmodified reference's trace decade by decade while the regulariser
+    dominates (k <= 20: both solve a well-posed system there), 1e-5 relative;
+    (c) lambda, chi2 and the fitted densities A.C inside the envelope of the reference against itself."""
+    g = load_golden(name)
+    env = _envelope(name)
+    res = _fit(cuda, g, want_trace=True)
+    for r, e in enumerate(env):
+        ref = e["gelsd"]
+        assert int(res.status[r]) == ref["status"], (r, res.status[r], ref["status"])
+        ok = np.isfinite(g["value"][r])
+        # (b) decade by decade against the golden trace of the unmodified reference
+        tr = g["trace"][r]
+        tr = tr[np.isfinite(tr[:, 0])]
+        tab_ref = rp._decade_table([tuple(x) for x in tr])
+        tab_gpu = np.asarray(res.trace["table"][r])
+        both = np.isfinite(tab_ref) & np.isfinite(tab_gpu)
+        assert both[:21].all()
+        rel = np.abs(tab_gpu[:21] - tab_ref[:21]) / np.abs(tab_ref[:21])
+        assert rel.max() <= 1e-5, (r, rel.max())
+        if ref["status"] != 0:
+            continue
+        # (a)
+        assert abs(res.trace["nu"][r] / ref["npts"] - ref["sf"]) < 1e-9, (r, res.trace["nu"][r] / ref["npts"], ref["sf"])
+        klos = {e[d]["k_lo"] for d in DRIVERS}
+        assert int(res.trace["k_lo"][r]) in klos, (r, int(res.trace["k_lo"][r]), klos)
+        # (c)
+        ll = {d: np.log10(e[d]["lam"]) for d in DRIVERS}
+        spread = max(ll.values()) - min(ll.values())
+        near = min(DRIVERS, key=lambda d: abs(np.log10(res.reg_params[r, 0]) - ll[d]))
+        assert abs(np.log10(res.reg_params[r, 0]) - ll[near]) <= max(3 * spread, 1e-4), (r, res.reg_params[r, 0], e)
+        ac = {d: np.array(e[d]["AC"]) for d in DRIVERS}
+        ac_gpu = g["A"][ok] @ res.Coeffs[r]
+        dist = lambda x, y: np.max(np.abs(x - y)) / np.max(np.abs(y))
+        ac_spread = max(dist(ac[a], ac[b]) for a in DRIVERS for b in DRIVERS)
+        assert min(dist(ac_gpu, ac[d]) for d in DRIVERS) <= max(3 * ac_spread, 1e-6), (r, ac_spread)
+        c2 = [e[d]["chi2"] for d in DRIVERS]
+        c2_spread = (max(c2) - min(c2)) / ref["chi2"]
+        assert min(abs(res.chi_sq[r] - x) for x in c2) / ref["chi2"] <= max(3 * c2_spread, 1e-7), (r, c2_spread)
+        ranks = [e[d]["rank"] for d in DRIVERS]
+        assert min(ranks) - 2 <= int(res.rank[r]) <= max(ranks) + 2
+
+
+def test_covariance_at_rank_deficient_order_vs_reference(cuda):
+    """N = 27 (rank 24-27): dC = pinv(X) A^T W A pinv(X) (interpolate.py:464-467) against the golden covariance,
+    relative to its largest entry, inside what the reference itself reproduces under a BLAS-order change of X."""
+    g = load_golden("mid27")
+    res = _fit(cuda, g, want_cov=True)
+    for r in range(g["value"].shape[0]):
+        ref = g["Covariance"][r] if "Covariance" in g else None
+        if np.isnan(g["Coeffs"][r]).all():
+            assert np.isnan(res.Covariance[r]).all()
+            continue
+        ok = np.isfinite(g["value"][r])
+        A, W, b = np.asfortranarray(g["A"][ok]), g["error"][r][ok] ** -2, g["value"][r][ok]
+        lam = {g["reglist"][0]: g["lam"][r, 0]}
+        regs = {g["reglist"][0]: g["regs"][0]}
+        _, dref = rp.solve_coeffs(A, b, W, regs, lam, g["reglist"], cov=True)
+        # the reference against itself: same lambda, BLAS-order normal equations
+        AW = A * W[:, None]
+        X2 = AW.T @ A + g["lam"][r, 0] * g["regs"][0]
+        H2 = __import__("scipy.linalg").linalg.pinv(X2)
+        d2 = H2 @ (AW.T @ A) @ H2
+        envelope = np.max(np.abs(d2 - dref)) / np.max(np.abs(dref))
+        # GPU at its own lambda (within 1e-5 of the reference's): compare on the diagonal block structure
+        got = np.max(np.abs(res.Covariance[r] - dref)) / np.max(np.abs(dref))
+        assert got <= max(10 * envelope, 1e-3), (r, got, envelope)
+        assert np.allclose(res.Covariance[r], res.Covariance[r].T, rtol=0, atol=1e-9 * np.abs(dref).max())
+
+
+def test_eval_C_with_covariance_through_the_operator_seam(cuda, tmp_path):
+    """Interpolate.eval_C(..., calccov=True) -> (C, dC) like the reference (interpolate.py:464-469)."""
+    from volumetricinterp_b200 import Interpolate
+    g = load_golden("lo12")
+    cfg = tmp_path / "config.ini"
+    cfg.write_text(g["config_text"])
+    it = Interpolate(str(cfg))
+    r = 0
+    ok = np.isfinite(g["value"][r])
+    A, b, W = g["A"][ok], g["value"][r][ok], g["error"][r][ok] ** -2
+    regs = dict(zip(g["reglist"], g["regs"]))
+    lam = {"curvature": g["lam"][r, 0]}
+    Cc, dC = it.eval_C(A, b, W, regs, lam, calccov=True)
+    Cref, dref = rp.solve_coeffs(np.asfortranarray(A), b, W, regs, lam, g["reglist"], cov=True)
+    X = rp.normal_equations(A, W, b)[0] + g["lam"][r, 0] * g["regs"][0]
+    s = np.linalg.svd(X, compute_uv=False)
+    assert np.max(np.abs(Cc - Cref)) <= max(1e-9, 200 * EPS * s[0] / s[-1]) * np.abs(Cref).max()
+    assert np.max(np.abs(dC - dref)) <= max(1e-8, 2000 * EPS * s[0] / s[-1]) * np.abs(dref).max()
+
+
+def test_estimate_time_interpolation(cuda):
+    """timeinterp=True: coefficients blended linearly between the neighbouring record mid-times
+    (estimate.py:202-209), then the same kernel."""
+    from volumetricinterp_b200 import Estimate
+    from run_reference_time import unix2datetime
+    g = load_golden("lo12")
+    good = [r for r in range(g["Coeffs"].shape[0] - 1) if np.isfinite(g["Coeffs"][r]).all() and np.isfinite(g["Coeffs"][r + 1]).all()]
+    r = good[0]
+    mt = g["utime"].mean(axis=1)
+    t0 = 0.3 * mt[r] + 0.7 * mt[r + 1]
+    est = Estimate.from_arrays(g["config_text"], g["utime"], g["Coeffs"], g["hull_vert"], timeinterp=True)
+    out = est(unix2datetime(float(t0)), g["q_lat"], g["q_lon"], g["q_alt"])
+    Cb = rp.select_coeffs(g["utime"], g["Coeffs"], t0, timeinterp=True)
+    ref = rp.estimate(oracle_model(g), Cb, g["hull_vert"], g["q_lat"], g["q_lon"], g["q_alt"])
+    assert np.array_equal(np.isnan(out), np.isnan(ref))
+    m = np.isfinite(ref)
+    assert np.all(np.abs(out[m] - ref[m]) <= 1e-8 * np.abs(ref[m]))
+    with pytest.raises(ValueError):
+        est(unix2datetime(float(mt[-1]) + 1.0), g["q_lat"], g["q_lon"], g["q_alt"])
+
+
+def test_hull_mask_on_the_hull_itself(cuda):
+    """Gates that lie ON the hull (on its facets) are inside for the reference: Qhull does not turn a point within
+    its roundoff of a facet into a new vertex (estimate.py:167-177), whereas a bare half-space test decides them by
+    rounding noise.  Every gate of the geometry evaluated as a query point: masks identical to the reference's
+    re-hull decision, except at gates that ARE hull vertices, where the reference's answer depends on which of the
+    two coincident points Qhull keeps (tests/test_oracle.py::test_hull_tolerance_matches_the_rehull_decision) and
+    this implementation always answers inside."""
+    from volumetricinterp_b200 import Estimate
+    from volumetricinterp_b200.geo import geodetic2ecef
+    from run_reference_time import unix2datetime
+    for name in ("lo12", "c1_144"):
+        g = load_golden(name)
+        est = Estimate.from_arrays(g["config_text"], g["utime"], g["Coeffs"], g["hull_vert"])
+        out = est(unix2datetime(float(g["q_time"])), g["lat"], g["lon"], g["alt"])
+        ref_in = rp.inside_hull_rehull(g["hull_vert"], g["lat"], g["lon"], g["alt"])
+        pts = np.array(geodetic2ecef(g["lat"], g["lon"], g["alt"])).T
+        is_vertex = (np.abs(pts[:, None, :] - g["hull_vert"][None, :, :]).max(axis=2) == 0).any(axis=1)
+        assert is_vertex.sum() == g["hull_vert"].shape[0]
+        assert ref_in[~is_vertex].all()                       # the hull was built from these very points
+        assert np.isfinite(out).all(), (name, int((~np.isfinite(out)).sum()))
+
+
+def test_radbasfun_default_grid_end_to_end(cuda):
+    """The reference's own example radbasfun grid (NUMGRIDPNT = 7 -> N = 343 > VI_NMAX_SMEM): normal equations fall
+    back to the tiled strict kernel, the solver to the global-memory paths, covariance included -- no size limit
+    surfaces in the API (interpolate.py:456-467 has none).  Checked against the oracle on the fitted densities."""
+    from volumetricinterp_b200 import fit, synth
+    from volumetricinterp_b200.models import radbasfun
+    cfg = ("[DEFAULT]\nPARAM = dens\nFILENAME = x.h5\nOUTPUTFILENAME = y.h5\nREGULARIZATION_LIST =\n"
+           "REGULARIZATION_METHOD = chi2\nERRLIM = 1e10,1e13\nGOODFITCODE = 1,2,3,4\nCHI2LIM = 0.1,10\n\n[MODEL]\n"
+           "NAME = radbasfun\nLATCP = 78\nLONCP = 262\nEPS = 2.5e5\nLATRANGE = 72,78\nLONRANGE = 255,275\n"
+           "ALTRANGE = 100,700\nNUMGRIDPNT = 7\n")
+    model = radbasfun.Model(io.StringIO(cfg))
+    assert model.nbasis == 343
+    lat2, lon2, alt2 = synth.make_geometry(11, 70, seed=5)
+    lat, lon, alt, _ = synth.flatten_valid(lat2, lon2, alt2)
+    import configparser
+    cp = configparser.ConfigParser()
+    cp.read_file(io.StringIO(cfg))
+    om = rp.model_from_config(cp)
+    A = om.basis(lat, lon, alt)
+    rng = np.random.default_rng(3)
+    c = np.zeros(343)
+    c[rng.choice(343, 12, replace=False)] = 1e11 * rng.uniform(0.5, 1.5, 12)
+    value, error, _ = synth.make_records(A, 3, seed=9, c_true=c)
+    res = fit.fit_records(model, lat, lon, alt, value, error, None, "chi2", device=cuda, want_cov=True)
+    assert res.Coeffs.shape == (3, 343) and res.Covariance.shape == (3, 343, 343)
+    assert np.isfinite(res.Coeffs).all() and np.isfinite(res.Covariance).all()
+    Cref, _, c2ref, _ = rp.fit_records(om, lat, lon, alt, value, error, {}, [])
+    for r in range(3):
+        ok = np.isfinite(value[r])
+        d, dref = A[ok] @ res.Coeffs[r], A[ok] @ Cref[r]
+        assert np.max(np.abs(d - dref)) <= 1e-4 * np.abs(dref).max(), r
+        assert abs(res.chi_sq[r] - c2ref[r]) <= 1e-4 * c2ref[r]

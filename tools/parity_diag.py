@@ -21,7 +21,8 @@ for name in sys.argv[1:] or ["mid27", "c1_144"]:
     gpu = [parity.gpu_record(res, r, res.trace) for r in range(R)]
     ref = [parity.oracle_record(g["A"], g["value"][r], g["error"][r], g["regs"][0], g["reglist"][0]) for r in range(R)]
     env = [parity.oracle_record(g["A"], g["value"][r], g["error"][r], g["regs"][0], g["reglist"][0], "blas") for r in range(R)]
-    out = parity.compare(gpu, ref, env, g["A"], g["value"])
+    alt = [parity.oracle_record(g["A"], g["value"][r], g["error"][r], g["regs"][0], g["reglist"][0], "gelss") for r in range(R)]
+    out = parity.compare(gpu, ref, env, g["A"], g["value"], alt)
     out["golden_C_bit_identical_to_oracle"] = [bool(np.array_equal(ref[r]["C"], g["Coeffs"][r], equal_nan=True)) for r in range(R)]
     # decade by decade: GPU table vs the golden trace of the UNMODIFIED reference
     if "trace" in g:
@@ -45,6 +46,8 @@ for name in sys.argv[1:] or ["mid27", "c1_144"]:
                                      np.nanmax(np.abs(g["Covariance_diag"][r]))) if np.isfinite(g["Covariance_diag"][r]).all() else None
                                for r in range(R)]
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"parity_{name}.json"), "w"), indent=1, default=float)
-    print(name, json.dumps(out["gpu_vs_reference"]), "\n   envelope", json.dumps(out["reference_vs_itself_blas_order"]))
+    for k in ("gpu_vs_reference", "reference_vs_itself_blas_order", "reference_vs_itself_gelss_driver",
+              "gpu_vs_reference_with_gelss_driver"):
+        print(name, k, json.dumps(out[k]))
     for p in out["per_record"]:
-        print("  ", json.dumps({k: p[k] for k in ("record", "ref", "gpu", "env")}, default=float))
+        print("  ", json.dumps({k: p[k] for k in ("record", "ref", "gpu", "env_blas", "env_gelss")}, default=float))

@@ -34,5 +34,6 @@ for it in range(2):
                                        ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream))
     torch.cuda.synchronize()
 ms, cnt = _native.profile_read()
-print({k: round(v, 2) for k, v in ms.items() if cnt[k]}, "us/system tridiag:", round(1e3 * ms["tridiag"] / S, 3),
-      "ok:", int((status == 0).sum().item()))
+print({k: round(v, 2) for k, v in ms.items() if cnt[k]}, "us/system tridiag(+chase):",
+      round(1e3 * (ms["tridiag"] + ms.get("chase", 0.0)) / S, 3), "ok:", int((status == 0).sum().item()),
+      "rank mean", float(rank.double().mean().item()))
