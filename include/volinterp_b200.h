@@ -151,6 +151,21 @@ int vi_estimate_radbasfun(const double* lat, const double* lon, const double* al
                           const double* centers, int32_t N, double eps, const double* C, int32_t Rsel,
                           const double* hull_eq, int32_t F, double* out, void* stream);
 
+/* estimate.py:113-121 for MANY records of one coefficient file (BASELINE configs[3]: 1 k records): the points are
+ * tested against the hull and compacted first, the basis rows of the in-hull points are evaluated once (one thread
+ * per point) and out = rows . C^T runs as an FP64 tensor-core GEMM; points outside the hull cost one NaN store per
+ * record and nothing else.  Same outputs as vi_estimate_* (which stay the entry points for a few records).
+ * workspace: vi_estimate_workspace_bytes(npts, N, Rsel) bytes of device scratch; npts < 2^31 per call. */
+int vi_estimate_workspace_bytes(int64_t npts, int32_t N, int32_t Rsel, int64_t* bytes);
+int vi_estimate_sphharmlag_many(const double* lat, const double* lon, const double* alt, int64_t npts,
+                                const vi_shl_params* params, const double* C, int32_t Rsel,
+                                const double* hull_eq, int32_t F, double* out,
+                                void* workspace, int64_t workspace_bytes, void* stream);
+int vi_estimate_radbasfun_many(const double* lat, const double* lon, const double* alt, int64_t npts,
+                               const double* centers, int32_t N, double eps, const double* C, int32_t Rsel,
+                               const double* hull_eq, int32_t F, double* out,
+                               void* workspace, int64_t workspace_bytes, void* stream);
+
 /* End-to-end convenience entry points on HOST buffers (the calls the Python `Interpolate` /
  * `Estimate` classes make when handed numpy arrays): H2D, kernels, D2H, synchronous. */
 int vi_fit_host(const double* A /*P x N*/, const double* value, const double* error, const double* weight,
@@ -173,6 +188,9 @@ int vi_fp64_peak_probe(int32_t mode, int32_t iters, double* tflops, void* stream
 int vi_profile_enable(int32_t on);
 int vi_profile_reset(void);
 int vi_profile_read(double* ms_by_kind, int64_t* launches_by_kind, int32_t nkinds);
+/* Givens rotations generated by the tridiagonal eigen-solves (= entries of the rotation tapes written; each is read
+ * twice by the replay) and eigen-systems solved by vi_fit_batched since the last vi_profile_reset. */
+int vi_profile_counters(int64_t* rotations, int64_t* systems);
 
 #ifdef __cplusplus
 }

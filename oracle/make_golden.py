@@ -41,6 +41,9 @@ CASES = {
     # gcv method (interpolate.py:263-351): leave-one-gate-out objective, Nelder-Mead; small on purpose
     # (the reference solves len(b) systems per objective evaluation)
     "lo8_gcv": (dict(NAME="sphharmlag", MAXK=2, MAXL=2, CAP_LIM=10), dict(REGULARIZATION_METHOD="gcv"), 5, 16, 3, True),
+    # C3 order (BASELINE configs[2]): N = 500 (MAXK 5 x MAXL 10; CAP_LIM 11 keeps Gamma(nu + m + 1) finite),
+    # the reference's real curvature matrix (9 minutes of QUADPACK), few gates and records to keep the run offline
+    "c3_500": (dict(NAME="sphharmlag", MAXK=5, MAXL=10, CAP_LIM=11), {}, 9, 40, 2, False),
     # radbasfun: no regulariser exists (radbasfun.py:62) -> plain lstsq per record
     "rbf27": (dict(NAME="radbasfun", NUMGRIDPNT=3, EPS=300000.0, LATRANGE="74,80", LONRANGE="255,280",
                    ALTRANGE="100,600"), dict(REGULARIZATION_LIST=""), 9, 40, 4, True),

@@ -34,6 +34,8 @@ struct Warp {
   double boxa[32], boxb[32];
 };
 
+inline uint64_t& progress() { static uint64_t p = 0; return p; }    // bumped whenever any barrier completes
+
 struct Cta {
   std::vector<Fiber> fibers;
   std::vector<Warp> warps;
@@ -55,7 +57,7 @@ inline void yield() {
 
 inline void wait(Barrier& b, int count) {
   const uint64_t g = b.gen;
-  if (++b.arrived == count) { b.arrived = 0; ++b.gen; return; }
+  if (++b.arrived == count) { b.arrived = 0; ++b.gen; ++progress(); return; }
   while (b.gen == g) yield();
 }
 
@@ -86,18 +88,23 @@ inline void run_cta(unsigned block, int nthreads, const std::function<void()>& b
     makecontext(&f.ctx, (void (*)())trampoline, 0);
   }
   int live = nthreads;
-  long spins = 0;
+  int idle_passes = 0;
   while (live > 0) {
-    int progressed = 0;
+    const uint64_t before = progress();
+    const int live_before = live;
     for (int t = 0; t < nthreads; ++t) {
       if (c.fibers[t].done) continue;
       c.cur = t;
       swapcontext(&c.sched, &c.fibers[t].ctx);
       if (c.fibers[t].done) { --live; }
-      ++progressed;
     }
-    if (!progressed) break;
-    if (++spins > 200000000L) { fprintf(stderr, "cuda_emu: deadlock suspected\n"); abort(); }
+    // a pass over all fibers in which no barrier completed and no fiber finished: nobody can ever move again
+    // (e.g. a warp-wide shuffle reached by only part of the warp -- a divergent __shfl_sync on the GPU)
+    if (progress() == before && live == live_before) {
+      if (++idle_passes > 4) { fprintf(stderr, "cuda_emu: DEADLOCK (divergent synchronisation?)\n"); abort(); }
+    } else {
+      idle_passes = 0;
+    }
   }
   cta() = nullptr;
 }

@@ -17,7 +17,9 @@ VI_NALPHA = 102
 ST_OK, ST_TOO_SMOOTH, ST_NO_ROOT, ST_NONFINITE, ST_NOCONV, ST_EMPTY = range(6)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvolinterp_b200.so")
+# VI_LIB_VARIANT selects an A/B build made by `VI_LIB_VARIANT=<tag> python -m volumetricinterp_b200.build` (tuning only)
+LIB_PATH = os.path.join(_HERE, "libvolinterp_b200%s.so" % (("_" + os.environ["VI_LIB_VARIANT"])
+                                                          if os.environ.get("VI_LIB_VARIANT") else ""))
 
 
 class ShlParams(C.Structure):
@@ -57,12 +59,16 @@ SIGNATURES = {
     "vi_fit_search_trace": [_ptr, _i64, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr],
     "vi_estimate_sphharmlag": [_ptr, _ptr, _ptr, _i64, _shl, _ptr, _i32, _ptr, _i32, _ptr, _ptr],
     "vi_estimate_radbasfun": [_ptr, _ptr, _ptr, _i64, _ptr, _i32, _dbl, _ptr, _i32, _ptr, _i32, _ptr, _ptr],
+    "vi_estimate_workspace_bytes": [_i64, _i32, _i32, C.POINTER(_i64)],
+    "vi_estimate_sphharmlag_many": [_ptr, _ptr, _ptr, _i64, _shl, _ptr, _i32, _ptr, _i32, _ptr, _ptr, _i64, _ptr],
+    "vi_estimate_radbasfun_many": [_ptr, _ptr, _ptr, _i64, _ptr, _i32, _dbl, _ptr, _i32, _ptr, _i32, _ptr, _ptr, _i64, _ptr],
     "vi_fit_host": [_ptr, _ptr, _ptr, _ptr, _i32, _i32, _i32, _ptr, _i32, _i32, _i32, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "vi_estimate_sphharmlag_host": [_ptr, _ptr, _ptr, _i64, _shl, _ptr, _i32, _ptr, _i32, _ptr],
     "vi_fp64_peak_probe": [_i32, _i32, C.POINTER(_dbl), _ptr],
     "vi_profile_enable": [_i32],
     "vi_profile_reset": [],
     "vi_profile_read": [_ptr, _ptr, _i32],
+    "vi_profile_counters": [C.POINTER(_i64), C.POINTER(_i64)],
 }
 PROFILE_KINDS = ("basis", "normal_eq", "tridiag", "tql", "apply", "chi2", "covariance", "estimate", "misc", "chase")
 
@@ -123,3 +129,20 @@ def fill_shl_params(maxk, maxl, ct0, st0, kx, ky, nu, kvm, g1, g2):
             p.g1[l][m] = float(g1[l][m])
             p.g2[l][m] = float(g2[l][m])
     return p
+
+
+_est_ws = {}
+
+
+def estimate_workspace(device, npts, N, Rsel):
+    """Device scratch of vi_estimate_*_many (cached per device, grown on demand)."""
+    import torch
+    need = C.c_int64(0)
+    check(lib().vi_estimate_workspace_bytes(int(npts), int(N), int(Rsel), C.byref(need)))
+    key = str(device)
+    ws = _est_ws.get(key)
+    if ws is None or ws.numel() < need.value:
+        _est_ws.pop(key, None)
+        ws = torch.empty((need.value,), dtype=torch.uint8, device=device)
+        _est_ws[key] = ws
+    return ws

@@ -14,8 +14,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 INC = os.path.join(ROOT, "include")
-OUT = os.path.join(HERE, "libvolinterp_b200.so")
-OBJ = os.path.join(HERE, "build")
+# VI_LIB_VARIANT=<tag> (with VI_EXTRA_NVCC=-D...) builds an A/B variant next to the product library
+_TAG = os.environ.get("VI_LIB_VARIANT", "")
+OUT = os.path.join(HERE, "libvolinterp_b200%s.so" % (("_" + _TAG) if _TAG else ""))
+OBJ = os.path.join(HERE, "build" + (("_" + _TAG) if _TAG else ""))
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INC, "-I", CSRC, "--expt-relaxed-constexpr"]
@@ -24,6 +26,7 @@ UNITS = {          # file -> extra flags
     "abi.cu": [],
     "basis.cu": ["-fmad=false"],
     "normal_eq.cu": [],
+    "estimate_gemm.cu": [],
     "fit.cu": [],
     "probe.cu": [],
 }
@@ -66,8 +69,10 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or _stale(OUT, objs):
-        cmd = [_nvcc()] + ARCH + ["-shared", "-o", OUT] + objs + ["-lcudart"]
+        tmp = OUT + ".tmp"                 # link aside, then rename: the library is never seen half-written
+        cmd = [_nvcc()] + ARCH + ["-shared", "-o", tmp] + objs + ["-lcudart"]
         subprocess.check_call(cmd)
+        os.replace(tmp, OUT)
     return OUT
 
 

@@ -23,7 +23,16 @@ int64_t g_launches[VI_K_COUNT] = {0};
 double g_ms[VI_K_COUNT] = {0};
 std::vector<Span> g_spans;
 cudaEvent_t g_cur;
+int64_t g_rotations = 0, g_systems = 0;
 }  // namespace
+
+void vi_prof_count_rotations(int64_t rotations, int64_t systems) { g_rotations += rotations; g_systems += systems; }
+
+extern "C" int vi_profile_counters(int64_t* rotations, int64_t* systems) {
+  if (rotations) *rotations = g_rotations;
+  if (systems) *systems = g_systems;
+  return VI_OK;
+}
 
 void vi_prof_launch_begin(int kind, cudaStream_t s) {
   g_launches[kind] += 1;
@@ -51,6 +60,7 @@ extern "C" int vi_profile_reset(void) {
   for (auto& sp : g_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   g_spans.clear();
   for (int k = 0; k < VI_K_COUNT; ++k) { g_launches[k] = 0; g_ms[k] = 0.0; }
+  g_rotations = 0; g_systems = 0;
   return VI_OK;
 }
 

@@ -272,6 +272,60 @@ k_est_rbf(const double* __restrict__ lat, const double* __restrict__ lon, const 
   }
 }
 
+// ---- many-record Estimate, first half (estimate_gemm.cu has the second): hull compaction + basis rows ----------
+__device__ __forceinline__ int k_slot16(int k) { return (k & ~15) | ((k & 3) << 2) | ((k >> 2) & 3); }
+
+// idx[0 .. *count) = points inside the hull (order arbitrary: every point's result is independent of it)
+__global__ void __launch_bounds__(256)
+k_hull_compact(const double* __restrict__ lat, const double* __restrict__ lon, const double* __restrict__ alt,
+               int64_t npts, const double* __restrict__ eq, int F, int32_t* __restrict__ idx, int32_t* __restrict__ count) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool in = false;
+  if (p < npts) {
+    in = true;
+    if (F > 0) {
+      double x, y, z;
+      vi_geodetic2ecef(lat[p], lon[p], alt[p], &x, &y, &z);
+      in = inside_hull(eq, F, x, y, z);
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, in);
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0 && m) base = atomicAdd(count, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (in) idx[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)p;
+}
+
+// basis row of compacted point j in slot order (k -> 4 (k % 4) + k / 4 inside each group of 16), zero padded to KP
+__global__ void __launch_bounds__(kThreads)
+k_rows_shl_idx(const double* __restrict__ lat, const double* __restrict__ lon, const double* __restrict__ alt,
+               const int32_t* __restrict__ idx, const int32_t* __restrict__ count, const __grid_constant__ vi_shl_params P,
+               int KP, double* __restrict__ Arows) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= *count) return;
+  const int N = P.maxk * P.maxl * P.maxl;
+  const int32_t p = idx[j];
+  double* row = Arows + j * (int64_t)KP;
+  for (int k = N; k < KP; ++k) row[k_slot16(k)] = 0.0;
+  vi_shl_row(P, lat[p], lon[p], alt[p], [&](int n, double v) { row[k_slot16(n)] = v; });
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_rows_rbf_idx(const double* __restrict__ lat, const double* __restrict__ lon, const double* __restrict__ alt,
+               const int32_t* __restrict__ idx, const int32_t* __restrict__ count, const double* __restrict__ centers,
+               int N, double eps, int KP, double* __restrict__ Arows) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= *count) return;
+  const int32_t p = idx[j];
+  double x, y, z;
+  vi_geodetic2ecef(lat[p], lon[p], alt[p], &x, &y, &z);
+  double* row = Arows + j * (int64_t)KP;
+  for (int k = N; k < KP; ++k) row[k_slot16(k)] = 0.0;
+  for (int n = 0; n < N; ++n)
+    row[k_slot16(n)] = vi_rbf_value(x, y, z, centers[3 * n], centers[3 * n + 1], centers[3 * n + 2], eps);
+}
+
 int check_shl(const vi_shl_params* P) {
   VI_REQUIRE(P != nullptr, "params is NULL");
   VI_REQUIRE(P->maxk >= 1 && P->maxk <= VI_MAXK_MAX && P->maxl >= 1 && P->maxl <= VI_MAXL_MAX,
@@ -374,6 +428,66 @@ extern "C" int vi_estimate_radbasfun(const double* lat, const double* lon, const
   return VI_OK;
 }
 
+// second half, estimate_gemm.cu
+int vi_estimate_gemm_launch(const int32_t* count, const int32_t* idx, const double* Arows, double* Cs, const double* C,
+                            int32_t Rsel, int32_t N, int64_t npts, double* out, cudaStream_t s);
+
+namespace {
+struct EstWs { int32_t* count; int32_t* idx; double* Arows; double* Cs; };
+int est_carve(void* workspace, int64_t workspace_bytes, int64_t npts, int32_t N, int32_t Rsel, EstWs* w) {
+  int64_t need = 0;
+  if (int rc = vi_estimate_workspace_bytes(npts, N, Rsel, &need)) return rc;
+  if (workspace == nullptr || workspace_bytes < need) {
+    vi_set_error("estimate workspace too small: %lld < %lld bytes", (long long)workspace_bytes, (long long)need);
+    return VI_EWORKSPACE;
+  }
+  VI_REQUIRE(npts < ((int64_t)1 << 31), "at most 2^31 - 1 points per call (tile the grid)");
+  const int64_t KP = (N + 15) / 16 * 16;
+  char* b = reinterpret_cast<char*>(workspace);
+  w->count = reinterpret_cast<int32_t*>(b); b += 256;
+  w->idx = reinterpret_cast<int32_t*>(b); b += vi_align_up(npts * 4, 256);
+  w->Arows = reinterpret_cast<double*>(b); b += npts * KP * 8;
+  w->Cs = reinterpret_cast<double*>(b);
+  return VI_OK;
+}
+}  // namespace
+
+extern "C" int vi_estimate_sphharmlag_many(const double* lat, const double* lon, const double* alt, int64_t npts,
+                                           const vi_shl_params* params, const double* C, int32_t Rsel,
+                                           const double* hull_eq, int32_t F, double* out,
+                                           void* workspace, int64_t workspace_bytes, void* stream) {
+  if (int rc = check_shl(params)) return rc;
+  VI_REQUIRE(npts >= 0 && Rsel >= 1 && C != nullptr && out != nullptr, "bad arguments");
+  if (npts == 0) return VI_OK;
+  if (hull_eq == nullptr) F = 0;
+  const int N = params->maxk * params->maxl * params->maxl;
+  const int KP = (N + 15) / 16 * 16;
+  EstWs w;
+  if (int rc = est_carve(workspace, workspace_bytes, npts, N, Rsel, &w)) return rc;
+  cudaStream_t s = vi_stream(stream);
+  VI_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int32_t), s));
+  VI_KERNEL(VI_K_ESTIMATE, s, k_hull_compact<<<(unsigned)((npts + 255) / 256), 256, 0, s>>>(lat, lon, alt, npts, hull_eq, F, w.idx, w.count));
+  VI_KERNEL(VI_K_ESTIMATE, s, k_rows_shl_idx<<<(unsigned)((npts + kThreads - 1) / kThreads), kThreads, 0, s>>>(lat, lon, alt, w.idx, w.count, *params, KP, w.Arows));
+  return vi_estimate_gemm_launch(w.count, w.idx, w.Arows, w.Cs, C, Rsel, N, npts, out, s);
+}
+
+extern "C" int vi_estimate_radbasfun_many(const double* lat, const double* lon, const double* alt, int64_t npts,
+                                          const double* centers, int32_t N, double eps, const double* C, int32_t Rsel,
+                                          const double* hull_eq, int32_t F, double* out,
+                                          void* workspace, int64_t workspace_bytes, void* stream) {
+  VI_REQUIRE(npts >= 0 && Rsel >= 1 && N >= 1 && C != nullptr && out != nullptr && centers != nullptr, "bad arguments");
+  if (npts == 0) return VI_OK;
+  if (hull_eq == nullptr) F = 0;
+  const int KP = (N + 15) / 16 * 16;
+  EstWs w;
+  if (int rc = est_carve(workspace, workspace_bytes, npts, N, Rsel, &w)) return rc;
+  cudaStream_t s = vi_stream(stream);
+  VI_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int32_t), s));
+  VI_KERNEL(VI_K_ESTIMATE, s, k_hull_compact<<<(unsigned)((npts + 255) / 256), 256, 0, s>>>(lat, lon, alt, npts, hull_eq, F, w.idx, w.count));
+  VI_KERNEL(VI_K_ESTIMATE, s, k_rows_rbf_idx<<<(unsigned)((npts + kThreads - 1) / kThreads), kThreads, 0, s>>>(lat, lon, alt, w.idx, w.count, centers, N, eps, KP, w.Arows));
+  return vi_estimate_gemm_launch(w.count, w.idx, w.Arows, w.Cs, C, Rsel, N, npts, out, s);
+}
+
 extern "C" int vi_estimate_sphharmlag_host(const double* lat, const double* lon, const double* alt, int64_t npts,
                                            const vi_shl_params* params, const double* C, int32_t Rsel,
                                            const double* hull_eq, int32_t F, double* out) {
@@ -386,20 +500,24 @@ extern "C" int vi_estimate_sphharmlag_host(const double* lat, const double* lon,
   int rc = VI_OK;
   size_t nb = (size_t)npts * sizeof(double);
   if (hull_eq == nullptr) F = 0;
-  VI_CUDA(cudaMalloc(&d_in, 3 * nb));
-  VI_CUDA(cudaMalloc(&d_C, (size_t)Rsel * N * sizeof(double)));
-  VI_CUDA(cudaMalloc(&d_out, (size_t)Rsel * nb));
-  if (F > 0) VI_CUDA(cudaMalloc(&d_eq, (size_t)F * 4 * sizeof(double)));
-  VI_CUDA(cudaMemcpyAsync(d_in, lat, nb, cudaMemcpyHostToDevice, s));
-  VI_CUDA(cudaMemcpyAsync(d_in + npts, lon, nb, cudaMemcpyHostToDevice, s));
-  VI_CUDA(cudaMemcpyAsync(d_in + 2 * npts, alt, nb, cudaMemcpyHostToDevice, s));
-  VI_CUDA(cudaMemcpyAsync(d_C, C, (size_t)Rsel * N * sizeof(double), cudaMemcpyHostToDevice, s));
-  if (F > 0) VI_CUDA(cudaMemcpyAsync(d_eq, hull_eq, (size_t)F * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
-  rc = vi_estimate_sphharmlag(d_in, d_in + npts, d_in + 2 * npts, npts, params, d_C, Rsel, d_eq, F, d_out, s);
-  if (rc == VI_OK) {
-    VI_CUDA(cudaMemcpyAsync(out, d_out, (size_t)Rsel * nb, cudaMemcpyDeviceToHost, s));
-    VI_CUDA(cudaStreamSynchronize(s));
-  }
-  cudaFree(d_in); cudaFree(d_C); cudaFree(d_out); if (d_eq) cudaFree(d_eq);
+  // (no early returns between the allocations and the frees: a failed call must not leak device memory)
+#define VI_TRY(x) do { if (rc == VI_OK) { cudaError_t _e = (x); if (_e != cudaSuccess) { vi_set_error("%s -> %s", #x, cudaGetErrorString(_e)); rc = VI_ECUDA; } } } while (0)
+  VI_TRY(cudaMalloc(&d_in, 3 * nb));
+  VI_TRY(cudaMalloc(&d_C, (size_t)Rsel * N * sizeof(double)));
+  VI_TRY(cudaMalloc(&d_out, (size_t)Rsel * nb));
+  if (F > 0) VI_TRY(cudaMalloc(&d_eq, (size_t)F * 4 * sizeof(double)));
+  VI_TRY(cudaMemcpyAsync(d_in, lat, nb, cudaMemcpyHostToDevice, s));
+  VI_TRY(cudaMemcpyAsync(d_in + npts, lon, nb, cudaMemcpyHostToDevice, s));
+  VI_TRY(cudaMemcpyAsync(d_in + 2 * npts, alt, nb, cudaMemcpyHostToDevice, s));
+  VI_TRY(cudaMemcpyAsync(d_C, C, (size_t)Rsel * N * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (F > 0) VI_TRY(cudaMemcpyAsync(d_eq, hull_eq, (size_t)F * 4 * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (rc == VI_OK) rc = vi_estimate_sphharmlag(d_in, d_in + npts, d_in + 2 * npts, npts, params, d_C, Rsel, d_eq, F, d_out, s);
+  VI_TRY(cudaMemcpyAsync(out, d_out, (size_t)Rsel * nb, cudaMemcpyDeviceToHost, s));
+  VI_TRY(cudaStreamSynchronize(s));
+#undef VI_TRY
+  if (d_in) cudaFree(d_in);
+  if (d_C) cudaFree(d_C);
+  if (d_out) cudaFree(d_out);
+  if (d_eq) cudaFree(d_eq);
   return rc;
 }

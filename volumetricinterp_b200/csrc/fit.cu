@@ -61,6 +61,7 @@ struct SysBuf {
   size_t smem;
   double *V, *d, *e, *g, *tau, *scl, *tcs, *lam, *Csys, *chi2, *chi2p, *Xg, *band;
   int32_t *tix, *st, *rec, *rank, *nrot, *unit, *kidx, *gate;
+  unsigned long long* rot_total;   // rotations of all eigen-solves since the call started (profiling; may be null)
 };
 
 // leave-one-gate-out systems (GCV): system s is built from G - w a a^T, y - w b a with a = A[gate[s]]
@@ -122,6 +123,7 @@ void sysbuf_carve(Bump& b, SysBuf& S, int64_t cap, int n, int nreg, int P) {
   S.kidx = b.take<int32_t>(cap);
   S.gate = b.take<int32_t>(cap);
   S.Xg = S.use_gx ? b.take<double>(cap * n * S.ld) : nullptr;
+  S.rot_total = b.take<unsigned long long>(4);
 }
 
 constexpr int kCovChunk = 512;     // records whose eigenvector / H / T scratch is held at once
@@ -535,6 +537,7 @@ __global__ void k_tql_smem(int64_t nsys, SysBuf B, int L, int iter_batch) {
   if (!act) return;
   if (q != 0) { B.st[s] = VI_ST_NOCONV; return; }
   B.nrot[s] = nrot;
+  if (B.rot_total) atomicAdd(B.rot_total, (unsigned long long)nrot);
   for (int i = 0; i < n; ++i) B.d[base + (int64_t)i * 32] = d[i];
 }
 
@@ -557,6 +560,7 @@ __global__ void k_tql_single(int64_t nsys, SysBuf B) {
   const int q = vi_tql_values(n, d, e, tape_of(B, s), &nrot);
   if (q != 0) { B.st[s] = VI_ST_NOCONV; return; }
   B.nrot[s] = nrot;
+  if (B.rot_total) atomicAdd(B.rot_total, (unsigned long long)nrot);
   for (int i = 0; i < n; ++i) B.d[base + (int64_t)i * 32] = d[i];
 }
 
@@ -1446,9 +1450,9 @@ int run_tridiag(int64_t cnt, const double* G, const double* y, const double* reg
   if (B.two_stage) {
     const size_t smem1 = (size_t)vi_bnd_doubles(B.n) * sizeof(double);
     const int nt = vi_bnd_threads(B.n);
-    if (nt == 256) {
-      VI_CUDA(cudaFuncSetAttribute(k_band<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-      VI_KERNEL(VI_K_TRIDIAG, s, (k_band<256, 2><<<(unsigned)cnt, nt, smem1, s>>>(G, y, regs, B, dd)));
+    if (nt == 32 * VI_BND_NW) {
+      VI_CUDA(cudaFuncSetAttribute(k_band<32 * VI_BND_NW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      VI_KERNEL(VI_K_TRIDIAG, s, (k_band<32 * VI_BND_NW, 2><<<(unsigned)cnt, nt, smem1, s>>>(G, y, regs, B, dd)));
     } else {
       VI_CUDA(cudaFuncSetAttribute(k_band<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
       VI_KERNEL(VI_K_TRIDIAG, s, (k_band<128, 1><<<(unsigned)cnt, nt, smem1, s>>>(G, y, regs, B, dd)));
@@ -1662,6 +1666,7 @@ extern "C" int vi_solve_cov_batched(const double* G, const double* y, const int3
   }
   SysBuf B;
   sysbuf_carve(b, B, cap, N, nreg, 1);
+  VI_CUDA(cudaMemsetAsync(B.rot_total, 0, 4 * sizeof(unsigned long long), st));
   for (int64_t s0 = 0; s0 < S; s0 += cap) {
     int64_t cnt = (S - s0 < cap) ? S - s0 : cap;
     VI_KERNEL(VI_K_MISC, st, k_setup_solve<<<blocks(cap, 256), 256, 0, st>>>(s0, cnt, nreg, rec, lam, B));
@@ -1725,6 +1730,7 @@ extern "C" int vi_fit_batched(const double* At, const double* A, const double* W
   SysBuf B;
   sysbuf_carve(b, B, cap, N, nreg, P);
   int64_t solved = 0;
+  VI_CUDA(cudaMemsetAsync(B.rot_total, 0, 4 * sizeof(unsigned long long), st));
 
   if (method == VI_METHOD_CHI2) {
     double h_tab[VI_NALPHA];
@@ -1864,6 +1870,12 @@ extern "C" int vi_fit_batched(const double* At, const double* A, const double* W
     VI_KERNEL(VI_K_MISC, st, k_finalize<<<(unsigned)cnt, 64, 0, st>>>(r0, cnt, N, B, C, chi2, rank, status));
     VI_LAUNCH_CHECK();
     solved += cnt;
+  }
+  {
+    unsigned long long rot = 0;
+    VI_CUDA(cudaMemcpyAsync(&rot, B.rot_total, sizeof(rot), cudaMemcpyDeviceToHost, st));
+    VI_CUDA(cudaStreamSynchronize(st));
+    vi_prof_count_rotations((int64_t)rot, solved);
   }
   if (cov_to_host) {        // the caller's stream order covers the copies: `st` waits for both slots
     for (int slot = 0; slot < 2 && slot < cov_chunk; ++slot) VI_CUDA(cudaStreamWaitEvent(st, sink.drained[slot], 0));

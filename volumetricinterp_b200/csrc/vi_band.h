@@ -30,8 +30,10 @@
 #endif
 #endif
 
-#define VI_BND_MAXT 5            // panel rows per lane in the QR warp: n <= 32 * 5 + 8 = 168
 #define VI_BND_NMAX 168
+#ifndef VI_BND_NW
+#define VI_BND_NW 8              // warps per CTA at production orders (two CTAs per SM)
+#endif
 #define VI_BND_PART 136          // doubles per warp of partial Gram data: 64 (V^T Y) + 64 (V^T V) + 8 (V^T g)
 
 VI_HD int vi_bnd_npad(int n) { return (n + 7) & ~7; }
@@ -41,7 +43,7 @@ VI_HD int vi_bnd_nblk(int n) { const int b = vi_bnd_nbk(n); return b * (b + 1) /
 VI_HD int vi_bnd_el(int r, int c) { return ((c >> 2) << 5) + (((r << 2) + (c & 3)) ^ ((c >> 2) << 3)); }
 VI_HD int vi_bnd_ldv(int n) { const int np = vi_bnd_npad(n); return (np > 8 ? np - 8 : 0) + 4; }
 // warps of the CTA: 8 (two CTAs of 256 threads per SM at n = 144), fewer for tiny systems
-VI_HD int vi_bnd_nwarp(int n) { const int b = vi_bnd_nbk(n); return b >= 9 ? 8 : (b >= 5 ? 4 : (b >= 3 ? 2 : 1)); }
+VI_HD int vi_bnd_nwarp(int n) { const int b = vi_bnd_nbk(n); return b >= 9 ? VI_BND_NW : (b >= 5 ? 4 : (b >= 3 ? 2 : 1)); }
 VI_HD int vi_bnd_threads(int n) { return 32 * vi_bnd_nwarp(n); }
 // shared-memory doubles of one CTA
 VI_HD int vi_bnd_doubles(int n) {
@@ -86,75 +88,94 @@ VI_HD void vi_bnd_carve(vi_bnd_ws& S, double* mem, int n) {
 
 // X <- scl (0.5 (G + G^T) + sum_r lam[r] Reg_r [- wj a a^T]) in block layout, zero padding, scl = 2^-exponent(max|X|);
 // g <- y [- wj bj a].  Same arithmetic per element as vi_trp_load (GCV downdate: interpolate.py:332-349).
+// Blocks of block column J are dealt to the warps round robin; a lane covers 2 of the 64 elements of a block
+// ((row lane/8 + 4 h, column lane%8): 64-byte segments of row-major G), 32-bit index arithmetic throughout.
 VI_DEV void vi_bnd_load(const vi_bnd_ws& S, const double* G, const double* y, const double* regs, const double* lam,
                         int nreg, const double* arow, double wj, double bj) {
   const int n = S.n, nbk = S.nbk, tid = vi_tid(), nt = vi_nthreads();
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-  double mx = 0.0, bad = 0.0;
-  const int nblk = nbk * (nbk + 1) / 2;
-  // one block per warp and trip: lanes cover 4 rows x 8 columns twice (row-major G: 64-byte segments)
-  int I = 0, J = 0;                      // block index b -> (I, J): column-block-major
-  for (int b = 0; b < nblk; ++b) {
-    if ((b % nw) == warp) {
-      double* blk = S.X + b * 64;
+  const double big = 1.79769313486231570e308;
+  double mx = 0.0;                       // +inf marks a non-finite entry
+  const int r = lane >> 3, c = lane & 7;
+  const int e0 = vi_bnd_el(r, c), e1 = vi_bnd_el(r + 4, c);
+  double l0 = 0.0, l1 = 0.0;             // (two regularisers cover every configuration of the reference)
+  if (nreg > 0) l0 = lam[0];
+  if (nreg > 1) l1 = lam[1];
+  const int nn = n * n;
+  for (int J = 0; J < nbk; ++J) {
+    const int k = 8 * J + c;
+    double* blk = S.X + vi_bnd_blk(nbk, J + warp, J) * 64;
+    for (int I = J + warp; I < nbk; I += nw, blk += 64 * nw) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
       for (int h = 0; h < 2; ++h) {
-        const int r = (lane >> 3) + 4 * h, c = lane & 7;
-        const int i = 8 * I + r, k = 8 * J + c;
+        const int i = 8 * I + r + 4 * h;
         double x = 0.0;
         if (i < n && k < n) {
-          x = 0.5 * (G[(int64_t)i * n + k] + G[(int64_t)k * n + i]);
-          for (int q = 0; q < nreg; ++q) {
+          const int ik = i * n + k, ki = k * n + i;
+          x = 0.5 * (G[ik] + G[ki]);
+          if (l0 != 0.0) x = fma(l0, regs[ik], x);
+          if (l1 != 0.0) x = fma(l1, regs[nn + ik], x);
+          for (int q = 2; q < nreg; ++q) {
             const double l = lam[q];
-            if (l != 0.0) x = fma(l, regs[((int64_t)q * n + i) * n + k], x);
+            if (l != 0.0) x = fma(l, regs[q * nn + ik], x);
           }
           if (arow) x = x - wj * (arow[i] * arow[k]);
-          if (!(fabs(x) <= 1.79769313486231570e308)) bad = 1.0;
-          mx = fmax(mx, fabs(x));
+          mx = (fabs(x) <= big) ? fmax(mx, fabs(x)) : INFINITY;
         }
-        blk[vi_bnd_el(r, c)] = x;
+        blk[h ? e1 : e0] = x;
       }
     }
-    if (++I == nbk) { ++J; I = J; }
   }
   for (int i = tid; i < S.npad; i += nt) {
     double t = 0.0;
     if (i < n) {
       t = y[i];
       if (arow) t = t - (wj * bj) * arow[i];
-      if (!(fabs(t) <= 1.79769313486231570e308)) bad = 1.0;
+      if (!(fabs(t) <= big)) mx = INFINITY;
     }
     S.g[i] = t;
   }
-  S.part[tid] = (bad != 0.0) ? -1.0 : mx;
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, vi_shfl_xor(mx, o));
+  if (lane == 0) S.part[warp] = mx;
   vi_cta_sync();
-  if (tid == 0) {
-    double m = 0.0, bd = 0.0;
-    for (int t = 0; t < nt; ++t) { const double r = S.part[t]; if (r < 0.0) bd = 1.0; else m = fmax(m, r); }
-    int ex = 0;
-    double scl = 1.0;
-    if (bd == 0.0 && m > 0.0) { frexp(m, &ex); scl = ldexp(1.0, -ex); }
-    S.sc[0] = scl; S.sc[1] = bd;
+  double m = 0.0;
+  for (int w = 0; w < nw; ++w) m = fmax(m, S.part[w]);
+  const bool bad = !(m <= big);
+  int ex = 0;
+  double scl = 1.0;
+  if (!bad && m > 0.0) { frexp(m, &ex); scl = ldexp(1.0, -ex); }
+  if (tid == 0) { S.sc[0] = scl; S.sc[1] = bad ? 1.0 : 0.0; }
+  if (scl != 1.0) {
+    const int tot = vi_bnd_nblk(n) * 64;
+    for (int idx = tid; idx < tot; idx += nt) S.X[idx] *= scl;
   }
-  vi_cta_sync();
-  const double scl = S.sc[0];
-  if (scl != 1.0)
-    for (int idx = tid; idx < nblk * 64; idx += nt) S.X[idx] *= scl;
   vi_cta_sync();
 }
 
-// ---- P1: Householder QR of panel p by warp 0 -----------------------------------------------------------------
-// Lane l owns the panel rows r0 + l + 32 t (r0 = 8 (p + 1)), all 8 columns, in registers.  Column j: one shuffle
-// round gives every lane s_c = sum_{i > pivot} a_j[i] a_c[i] for c = j..7 (c = j: the squared norm); then
-// v = (1, a_j scale), beta, tau and the update a_c -= tau (v^T a_c) v are local except for the pivot-row elements.
-// Leaves V (unit lower trapezoidal, zeros above) in S.V, tau in S.tau, R in block (p + 1, p).
-VI_DEV void vi_bnd_panel_qr(const vi_bnd_ws& S, int p) {
+// ---- P1: Householder QR of panel p by ONE warp, panel in registers ---------------------------------------------
+// Lane l owns the panel rows r0 + l + 32 t, t < 4 (r0 = 8 (p + 1)), all 8 columns, in registers; a panel of more than
+// 128 rows keeps its rows r0 + 128 + l in shared memory (their final place in S.V), one per lane: at n = 144 that is
+// the first panel only.  Column j: one shuffle round gives every lane s_c = sum_{i > pivot} a_j[i] a_c[i] for
+// c = j..7 (c = j: the squared norm); then v = (1, a_j scale), beta, tau and the update a_c -= tau (v^T a_c) v are
+// local except for the pivot-row elements.  The factorisation (vi_bnd_qr_compute) touches nothing but block column
+// p, tau and block (p + 1, p) -- and S.V for a tall panel -- so for panels of at most 128 rows it can run beside the
+// trailing update of the previous panel; the write-back of V (vi_bnd_qr_store) comes after that update is done with V.
+#define VI_BND_QT 4
+struct vi_bnd_panel { double a[8][VI_BND_QT]; };
+
+VI_DEV void vi_bnd_qr_compute(const vi_bnd_ws& S, int p, vi_bnd_panel& P) {
   const int lane = vi_tid() & 31;
   const int r0 = 8 * (p + 1), npad = S.npad, nbk = S.nbk, ldv = S.ldv;
-  double a[8][VI_BND_MAXT];
+  double (&a)[8][VI_BND_QT] = P.a;
+  const int i4 = r0 + 32 * VI_BND_QT + lane;                    // this lane's tail row (tall panels)
+  const bool tail = i4 < npad;
+  double* vt = S.V + (i4 - 8);                                  // column c of the tail row at vt[c * ldv]
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-  for (int t = 0; t < VI_BND_MAXT; ++t) {
+  for (int t = 0; t < VI_BND_QT; ++t) {
     const int i = r0 + lane + 32 * t;
     const bool in = i < npad;
     const double* blk = S.X + vi_bnd_blk(nbk, in ? (i >> 3) : p + 1, p) * 64;
@@ -163,12 +184,23 @@ VI_DEV void vi_bnd_panel_qr(const vi_bnd_ws& S, int p) {
 #endif
     for (int c = 0; c < 8; ++c) a[c][t] = in ? blk[vi_bnd_el(i & 7, c)] : 0.0;
   }
+  if (tail) {
+    const double* blk = S.X + vi_bnd_blk(nbk, i4 >> 3, p) * 64;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 8; ++c) vt[c * ldv] = blk[vi_bnd_el(i4 & 7, c)];
+  }
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
   for (int j = 0; j < 8; ++j) {
     // rows strictly below the pivot row r0 + j: t > 0, or t == 0 and lane > j
-    double s[8];
+    double s[8], x4[8];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int c = j; c < 8; ++c) x4[c] = tail ? vt[c * ldv] : 0.0;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
@@ -177,59 +209,46 @@ VI_DEV void vi_bnd_panel_qr(const vi_bnd_ws& S, int p) {
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-      for (int t = 1; t < VI_BND_MAXT; ++t) acc = fma(a[j][t], a[c][t], acc);
-      s[c] = acc;
+      for (int t = 1; t < VI_BND_QT; ++t) acc = fma(a[j][t], a[c][t], acc);
+      s[c] = fma(x4[j], x4[c], acc);
     }
+    const double alpha = vi_shfl(a[j][0], j);
     for (int o = 16; o > 0; o >>= 1) {
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
       for (int c = j; c < 8; ++c) s[c] += vi_shfl_xor(s[c], o);
     }
-    const double alpha = vi_shfl(a[j][0], j);
     double beta, tau, scale;
     vi_reflector_scalars(alpha, s[j], &beta, &tau, &scale);
     // v in place of column j (rows below the pivot); pivot element becomes beta (R's diagonal)
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-    for (int t = 0; t < VI_BND_MAXT; ++t) {
+    for (int t = 0; t < VI_BND_QT; ++t) {
       const bool below = (t > 0) || (lane > j);
-      if (below) a[j][t] = a[j][t] * scale;
+      a[j][t] = below ? a[j][t] * scale : a[j][t];
     }
+    const double v4 = x4[j] * scale;
+    if (tail) vt[j * ldv] = v4;
+    const double vpiv = (lane == j) ? 1.0 : ((lane > j) ? a[j][0] : 0.0);   // v on this lane's t = 0 row
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
     for (int c = j + 1; c < 8; ++c) {
-      const double apc = vi_shfl(a[c][0], j);                 // pivot-row element of column c
-      const double w = tau * (apc + scale * s[c]);            // tau v^T a_c
-      if (lane == j) a[c][0] = a[c][0] - w;
-      else if (lane > j) a[c][0] = fma(-w, a[j][0], a[c][0]);
+      const double apc = vi_shfl(a[c][0], j);                   // pivot-row element of column c
+      const double w = tau * (apc + scale * s[c]);              // tau v^T a_c
+      a[c][0] = fma(-w, vpiv, a[c][0]);
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-      for (int t = 1; t < VI_BND_MAXT; ++t) a[c][t] = fma(-w, a[j][t], a[c][t]);
+      for (int t = 1; t < VI_BND_QT; ++t) a[c][t] = fma(-w, a[j][t], a[c][t]);
+      if (tail) vt[c * ldv] = fma(-w, v4, x4[c]);
     }
     if (lane == j) a[j][0] = beta;
     if (lane == 0) S.tau[j] = tau;
   }
-  // write back: V to shared memory, R to block (p + 1, p)
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-  for (int t = 0; t < VI_BND_MAXT; ++t) {
-    const int i = r0 + lane + 32 * t;
-    if (i < npad) {
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-      for (int c = 0; c < 8; ++c) {
-        const int piv = r0 + c;
-        S.V[c * ldv + (i - 8)] = (i > piv) ? a[c][t] : (i == piv ? 1.0 : 0.0);
-      }
-    }
-  }
-  if (lane < 8) {
+  if (lane < 8) {                                              // R -> block (p + 1, p)
     double* blk = S.X + vi_bnd_blk(nbk, p + 1, p) * 64;
 #if defined(__CUDACC__)
 #pragma unroll
@@ -238,7 +257,27 @@ VI_DEV void vi_bnd_panel_qr(const vi_bnd_ws& S, int p) {
   }
 }
 
-// fragment conversions inside a warp ---------------------------------------------------------------------------
+// V (unit lower trapezoidal, zeros above) -> S.V  (the tail rows of a tall panel are there already)
+VI_DEV void vi_bnd_qr_store(const vi_bnd_ws& S, int p, const vi_bnd_panel& P) {
+  const int lane = vi_tid() & 31;
+  const int r0 = 8 * (p + 1), npad = S.npad, ldv = S.ldv;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int t = 0; t < VI_BND_QT; ++t) {
+    const int i = r0 + lane + 32 * t;
+    if (i < npad) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int c = 0; c < 8; ++c) {
+        const int piv = r0 + c;
+        S.V[c * ldv + (i - 8)] = (i > piv) ? P.a[c][t] : (i == piv ? 1.0 : 0.0);
+      }
+    }
+  }
+}
+
 // accumulator (row lane/4, columns 2 (lane%4) + {0,1}) -> A operand of k-step t (row lane/4, column lane%4 + 4 t)
 VI_DEV void vi_bnd_c_to_a(double c0, double c1, double* a0, double* a1) {
   const int lane = vi_tid() & 31;
@@ -249,17 +288,6 @@ VI_DEV void vi_bnd_c_to_a(double c0, double c1, double* a0, double* a1) {
   const double x1 = vi_shfl(c0, s1), y1 = vi_shfl(c1, s1);
   *a0 = (m & 1) ? y0 : x0;
   *a1 = (m & 1) ? y1 : x1;
-}
-// accumulator -> B operand of k-step t: element (row = lane%4 + 4 t, column = lane/4)
-VI_DEV void vi_bnd_c_to_b(double c0, double c1, double* b0, double* b1) {
-  const int lane = vi_tid() & 31;
-  const int n = lane >> 2;                       // wanted column
-  const int k0 = lane & 3, k1 = (lane & 3) + 4;  // wanted rows
-  const int s0 = 4 * k0 + (n >> 1), s1 = 4 * k1 + (n >> 1);
-  const double x0 = vi_shfl(c0, s0), y0 = vi_shfl(c1, s0);
-  const double x1 = vi_shfl(c0, s1), y1 = vi_shfl(c1, s1);
-  *b0 = (n & 1) ? y0 : x0;
-  *b1 = (n & 1) ? y1 : x1;
 }
 
 // ---- P2: Y_I = sum_J A_IJ V_J for this warp's block rows; partial Gram blocks ---------------------------------
@@ -273,20 +301,32 @@ VI_DEV void vi_bnd_symm(const vi_bnd_ws& S, int p) {
   const int ea0 = lane, ea1 = 32 + (lane ^ 8);           // A operand of a stored block, k-steps 0 and 1
   const int et0 = vi_bnd_el(m4, q4), et1 = vi_bnd_el(m4 + 4, q4);   // A operand of its transpose
   for (int I = p + 1 + warp; I < nbk; I += nw) {
-    double y0 = 0.0, y1 = 0.0;
-    for (int J = p + 1; J < nbk; ++J) {
-      const double* vj = S.V + vb + 8 * J - 8;
-      double a0, a1;
-      if (J <= I) {
-        const double* blk = S.X + vi_bnd_blk(nbk, I, J) * 64;
-        a0 = blk[ea0]; a1 = blk[ea1];
-      } else {
-        const double* blk = S.X + vi_bnd_blk(nbk, J, I) * 64;
-        a0 = blk[et0]; a1 = blk[et1];
+    // two accumulator pairs (k-steps 0 and 1 of every block): two independent DMMA chains instead of one
+    double y0 = 0.0, y1 = 0.0, z0 = 0.0, z1 = 0.0;
+    // J <= I: stored blocks (I, J), one block column apart: block index grows by nbk - J - 1 per step
+    {
+      int b = vi_bnd_blk(nbk, I, p + 1);
+      const double* vj = S.V + vb + 8 * (p + 1) - 8;
+      for (int J = p + 1; J <= I; ++J) {
+        const double* blk = S.X + b * 64;
+        vi_mma884(y0, y1, blk[ea0], vj[0]);
+        vi_mma884(z0, z1, blk[ea1], vj[4]);
+        b += nbk - J - 1;
+        vj += 8;
       }
-      vi_mma884(y0, y1, a0, vj[0]);
-      vi_mma884(y0, y1, a1, vj[4]);
     }
+    // J > I: transposes of the stored blocks (J, I), contiguous in block column I
+    {
+      const double* blk = S.X + (vi_bnd_blk(nbk, I, I) + 1) * 64;
+      const double* vj = S.V + vb + 8 * (I + 1) - 8;
+      for (int J = I + 1; J < nbk; ++J) {
+        vi_mma884(y0, y1, blk[et0], vj[0]);
+        vi_mma884(z0, z1, blk[et1], vj[4]);
+        blk += 64;
+        vj += 8;
+      }
+    }
+    y0 += z0; y1 += z1;
     // Y_I -> shared (W panel), accumulator layout: (row q4, columns 2 m4, 2 m4 + 1)
     double* wi = S.W + 8 * I - 8 + q4;
     wi[(2 * m4) * ldv] = y0;
@@ -304,6 +344,9 @@ VI_DEV void vi_bnd_symm(const vi_bnd_ws& S, int p) {
       const double* vc = S.V + lane * ldv + 8 * I - 8;
       const double* gi = S.g + 8 * I;
       double acc = 0.0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
       for (int r = 0; r < 8; ++r) acc = fma(vc[r], gi[r], acc);
       ug += acc;
     }
@@ -314,18 +357,10 @@ VI_DEV void vi_bnd_symm(const vi_bnd_ws& S, int p) {
   if (lane < 8) pw[128 + lane] = ug;
 }
 
-// 8-way select of x[idx], idx in 0..7 (registers cannot be indexed dynamically)
-VI_DEV double vi_sel8(const double (&x)[8], int idx) {
-  const double a = (idx & 1) ? x[1] : x[0], b = (idx & 1) ? x[3] : x[2];
-  const double c = (idx & 1) ? x[5] : x[4], d = (idx & 1) ? x[7] : x[6];
-  const double e = (idx & 2) ? b : a, f = (idx & 2) ? d : c;
-  return (idx & 4) ? f : e;
-}
-
-// ---- P3: T, K = -1/2 T^T (V^T Y), W_I = (Y_I + V_I K) T, g -= V T^T (V^T g); reflectors to global -------------
-VI_DEV void vi_bnd_wpanel(const vi_bnd_ws& S, int p, double* Vg) {
-  const int tid = vi_tid(), warp = tid >> 5, lane = tid & 31;
-  const int nbk = S.nbk, ldv = S.ldv, nw = S.nw, npad = S.npad;
+// ---- P3a (warp 0): T (compact WY), K = -1/2 T^T (V^T Y), tg = T^T (V^T g) -> slot 0 of S.part -------------------
+// layout of the slot afterwards: [0, 64) T row-major, [64, 128) K row-major, [128, 136) tg
+VI_DEV void vi_bnd_small(const vi_bnd_ws& S) {
+  const int lane = vi_tid() & 31, nw = S.nw;
   const int q4 = lane >> 2, m4 = lane & 3;
   // sums of the partial Gram blocks: lane holds elements e = lane and lane + 32 (row-major 8 x 8)
   double my[2] = {0.0, 0.0}, sv[2] = {0.0, 0.0}, ugs = 0.0;
@@ -335,6 +370,7 @@ VI_DEV void vi_bnd_wpanel(const vi_bnd_ws& S, int p, double* Vg) {
     sv[0] += pw[64 + lane]; sv[1] += pw[96 + lane];
     if (lane < 8) ugs += pw[128 + lane];
   }
+  vi_warp_sync();                                               // slot 0 is read by every lane before it is overwritten
   // T (upper triangular, LAPACK dlarft forward/columnwise): lane i (mod 8) builds row i,
   //   T[i][i] = tau_i,  T[i][j] = -tau_j sum_{k=i}^{j-1} T[i][k] S[k][j]  (i < j),  S = V^T V
   const int ti = lane & 7;
@@ -359,9 +395,7 @@ VI_DEV void vi_bnd_wpanel(const vi_bnd_ws& S, int p, double* Vg) {
     }
     tr[j] = (ti == j) ? tj : ((ti < j) ? -tj * acc : 0.0);
   }
-  // every warp has read all the partials: from here on a warp's own slot of S.part is its private scratch
-  vi_cta_sync();
-  double* scr = S.part + warp * VI_BND_PART;                     // [0, 64): T row-major, [64, 128): K row-major
+  double* scr = S.part;
   if (lane < 8) {
 #if defined(__CUDACC__)
 #pragma unroll
@@ -369,47 +403,47 @@ VI_DEV void vi_bnd_wpanel(const vi_bnd_ws& S, int p, double* Vg) {
     for (int j = 0; j < 8; ++j) scr[lane * 8 + j] = tr[j];
   }
   vi_warp_sync();
-  // B operand T[k][n] (k = lane%4 + 4 t, n = lane/4); the A operand of T^T, (T^T)[r][k] = T[k][r], is the same value
+  // K = -1/2 T^T My: A = T^T ((T^T)[r][k] = T[k][r]: the same values as the B operand of T), B = My[k][n]
   const double tb0 = scr[m4 * 8 + q4], tb1 = scr[(m4 + 4) * 8 + q4];
-  // K = -1/2 T^T My: B = My[k][n] = element 8 k + n of the row-major sum held as (lane, lane + 32)
   double k0 = 0.0, k1 = 0.0;
-  {
-    const double mb0 = vi_shfl(my[0], 8 * m4 + q4);            // k = m4     -> e = 8 m4 + q4 < 32
-    const double mb1 = vi_shfl(my[1], 8 * m4 + q4);            // k = m4 + 4 -> e - 32
-    vi_mma884(k0, k1, tb0, mb0);
-    vi_mma884(k0, k1, tb1, mb1);
-  }
+  vi_mma884(k0, k1, tb0, vi_shfl(my[0], 8 * m4 + q4));           // k = m4     -> element 8 m4 + q4 < 32
+  vi_mma884(k0, k1, tb1, vi_shfl(my[1], 8 * m4 + q4));           // k = m4 + 4 -> that element - 32
   scr[64 + q4 * 8 + 2 * m4] = -0.5 * k0;
   scr[64 + q4 * 8 + 2 * m4 + 1] = -0.5 * k1;
-  vi_warp_sync();
-  const double kb0 = scr[64 + m4 * 8 + q4], kb1 = scr[64 + (m4 + 4) * 8 + q4];
-  // tg = T^T ug: lane k (< 8) holds row k of T and ug[k]; sum over k of T[k][c] ug[k] per column c
-  double tg[8];
-  {
-    const double u = (lane < 8) ? ugs : 0.0;
+  // tg[c] = sum_k T[k][c] ug[k]: lane k (< 8) holds row k of T and ug[k]
+  const double u = (lane < 8) ? ugs : 0.0;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-    for (int c = 0; c < 8; ++c) tg[c] = vi_oct_allsum((lane < 8) ? tr[c] * u : 0.0);
-    // lanes 0..7 now hold the totals; broadcast to the warp
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-    for (int c = 0; c < 8; ++c) tg[c] = vi_shfl(tg[c], 0);
+  for (int c = 0; c < 8; ++c) {
+    const double t = vi_oct_allsum((lane < 8) ? tr[c] * u : 0.0);
+    if (lane == 0) scr[128 + c] = t;
   }
+}
+
+// ---- P3b (all warps): W_I = (Y_I + V_I K) T, g_I -= V_I tg; V and T to global --------------------------------------
+VI_DEV void vi_bnd_wpanel(const vi_bnd_ws& S, int p, double* Vg) {
+  const int tid = vi_tid(), warp = tid >> 5, lane = tid & 31;
+  const int nbk = S.nbk, ldv = S.ldv, nw = S.nw, npad = S.npad;
+  const int q4 = lane >> 2, m4 = lane & 3;
+  const double* scr = S.part;
+  const double tb0 = scr[m4 * 8 + q4], tb1 = scr[(m4 + 4) * 8 + q4];               // B operand of T
+  const double kb0 = scr[64 + m4 * 8 + q4], kb1 = scr[64 + (m4 + 4) * 8 + q4];     // B operand of K
+  double tg[8];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int c = 0; c < 8; ++c) tg[c] = scr[128 + c];
   const int m = npad - 8 * (p + 1);
   double* vgp = Vg ? Vg + vi_bnd_voff(npad, p) : nullptr;
   if (vgp && warp == 0) {                                        // T row-major
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-    for (int j = 0; j < 8; ++j)
-      if (lane < 8) vgp[lane * 8 + j] = tr[j];
+    vgp[lane] = scr[lane];
+    vgp[32 + lane] = scr[32 + lane];
   }
   for (int I = p + 1 + warp; I < nbk; I += nw) {
     const int ro = 8 * I - 8;
     // U_I = Y_I + V_I K
-    const double* wi = S.W + ro + q4;
+    double* wi = S.W + ro + q4;
     double u0 = wi[(2 * m4) * ldv], u1 = wi[(2 * m4 + 1) * ldv];
     const double* vi = S.V + ro + q4;                            // A operand of V_I: (row q4, col m4 + 4 t)
     vi_mma884(u0, u1, vi[m4 * ldv], kb0);
@@ -420,10 +454,8 @@ VI_DEV void vi_bnd_wpanel(const vi_bnd_ws& S, int p, double* Vg) {
     double w0 = 0.0, w1 = 0.0;
     vi_mma884(w0, w1, ua0, tb0);
     vi_mma884(w0, w1, ua1, tb1);
-    vi_warp_sync();                                              // every lane has read Y_I
-    double* wo = S.W + ro + q4;
-    wo[(2 * m4) * ldv] = w0;
-    wo[(2 * m4 + 1) * ldv] = w1;
+    wi[(2 * m4) * ldv] = w0;                                     // (each lane overwrites the two values it read)
+    wi[(2 * m4 + 1) * ldv] = w1;
     // g_I -= V_I tg; V_I to global
     if (lane < 8) {
       double acc = 0.0;
@@ -434,60 +466,94 @@ VI_DEV void vi_bnd_wpanel(const vi_bnd_ws& S, int p, double* Vg) {
       S.g[8 * I + lane] -= acc;
     }
     if (vgp) {
-      for (int e = lane; e < 64; e += 32) {
-        const int c = e >> 3, r = e & 7;
-        vgp[64 + c * m + (8 * I + r - 8 * (p + 1))] = S.V[c * ldv + ro + r];
-      }
+      const int c = lane >> 3, rr = lane & 7;
+      vgp[64 + c * m + (8 * I + rr - 8 * (p + 1))] = S.V[c * ldv + ro + rr];
+      vgp[64 + (c + 4) * m + (8 * I + rr - 8 * (p + 1))] = S.V[(c + 4) * ldv + ro + rr];
     }
   }
 }
 
 // ---- P4: A_IJ -= V_I W_J^T + W_I V_J^T over the lower triangle of the trailing matrix ---------------------------
-VI_DEV void vi_bnd_update_row(const vi_bnd_ws& S, int p, int I) {
+// blocks (I, J) of block row I for J = J0 .. J1
+VI_DEV void vi_bnd_update_row(const vi_bnd_ws& S, int I, int J0, int J1) {
   const int lane = vi_tid() & 31, q4 = lane >> 2, m4 = lane & 3;
   const int nbk = S.nbk, ldv = S.ldv;
   const int ro = 8 * I - 8 + q4;
   // A operands (row q4, column m4 + 4 t), negated so that the MMA subtracts
   const double nv0 = -S.V[m4 * ldv + ro], nv1 = -S.V[(m4 + 4) * ldv + ro];
   const double nw0 = -S.W[m4 * ldv + ro], nw1 = -S.W[(m4 + 4) * ldv + ro];
+  int b = vi_bnd_blk(nbk, I, J0);
+  // B operands: (W_J^T)[k][n] = W[8 J + n][k]  ->  W[k * ldv + 8 J - 8 + n], k = m4 + 4 t, n = q4
+  const double* wj = S.W + m4 * ldv + 8 * J0 - 8 + q4;
+  const double* vj = S.V + m4 * ldv + 8 * J0 - 8 + q4;
   const int ec = vi_bnd_el(q4, 2 * m4);                              // accumulator pair (16-byte aligned)
-  for (int J = p + 1; J <= I; ++J) {
-    double* blk = S.X + vi_bnd_blk(nbk, I, J) * 64 + ec;
-    double c0 = blk[0], c1 = blk[1];
-    // B operands: (W_J^T)[k][n] = W[8 J + n][k]  ->  W[k * ldv + 8 J - 8 + n], k = m4 + 4 t, n = q4
-    const int bo = 8 * J - 8 + q4;
-    vi_mma884(c0, c1, nv0, S.W[m4 * ldv + bo]);
-    vi_mma884(c0, c1, nv1, S.W[(m4 + 4) * ldv + bo]);
-    vi_mma884(c0, c1, nw0, S.V[m4 * ldv + bo]);
-    vi_mma884(c0, c1, nw1, S.V[(m4 + 4) * ldv + bo]);
-    blk[0] = c0; blk[1] = c1;
+  for (int J = J0; J <= J1; ++J) {
+    double* blk = S.X + b * 64 + ec;
+    double c0 = blk[0], c1 = blk[1], d0 = 0.0, d1 = 0.0;            // two independent DMMA chains per block
+    vi_mma884(c0, c1, nv0, wj[0]);
+    vi_mma884(d0, d1, nw0, vj[0]);
+    vi_mma884(c0, c1, nv1, wj[4 * ldv]);
+    vi_mma884(d0, d1, nw1, vj[4 * ldv]);
+    blk[0] = c0 + d0; blk[1] = c1 + d1;
+    b += nbk - J - 1;
+    wj += 8; vj += 8;
   }
 }
 
-VI_DEV void vi_bnd_update(const vi_bnd_ws& S, int p) {
+// block column p + 1 of the trailing matrix (what the next panel's QR reads), all warps
+VI_DEV void vi_bnd_update_col(const vi_bnd_ws& S, int p) {
   const int warp = vi_tid() >> 5, nw = S.nw, nbk = S.nbk;
-  const int mb = nbk - (p + 1);
-  // rows paired short + long (row p+1+q has q+1 blocks, row nbk-1-q has mb-q): equal work per pair
-  for (int q = warp; 2 * q < mb; q += nw) {
-    const int Ia = p + 1 + q, Ib = nbk - 1 - q;
-    vi_bnd_update_row(S, p, Ia);
-    if (Ib > Ia) vi_bnd_update_row(S, p, Ib);
+  for (int I = p + 1 + warp; I < nbk; I += nw) vi_bnd_update_row(S, I, p + 1, p + 1);
+}
+
+// the rest, block columns >= p + 2, by the warps wfirst .. nw - 1.  Rows paired short + long (row p+2+q has q+1
+// blocks, row nbk-1-q has mb-q): equal work per pair.
+VI_DEV void vi_bnd_update_rest(const vi_bnd_ws& S, int p, int wfirst) {
+  const int warp = (vi_tid() >> 5) - wfirst, nwk = S.nw - wfirst, nbk = S.nbk;
+  if (warp < 0 || nwk <= 0) return;
+  const int mb = nbk - (p + 2);
+  for (int q = warp; 2 * q < mb; q += nwk) {
+    const int Ia = p + 2 + q, Ib = nbk - 1 - q;
+    vi_bnd_update_row(S, Ia, p + 2, Ia);
+    if (Ib > Ia) vi_bnd_update_row(S, Ib, p + 2, Ib);
   }
 }
 
 // Whole reduction.  After the call the band (half-width 8) sits in the diagonal and first sub-diagonal blocks,
 // S.g = Q1^T y, and Vg (global, may be null) holds T and V of every panel.
+// Warp 0 factors panel p + 1 WHILE the other warps finish the trailing update of panel p (look-ahead): the serial
+// part of a panel step (8 dependent reflectors) is off the other warps' critical path as far as the data allow.
 VI_DEV void vi_bnd_reduce(const vi_bnd_ws& S, double* Vg) {
   const int warp = vi_tid() >> 5;
-  for (int p = 0; p + 1 < S.nbk; ++p) {
-    if (warp == 0) vi_bnd_panel_qr(S, p);
-    vi_cta_sync();
+  const int npan = S.nbk - 1;
+  if (npan <= 0) return;
+  // a panel of more than 128 rows keeps its tail rows in S.V while it is factored: no look-ahead for those
+  auto tall = [&](int p) { return S.npad - 8 * (p + 1) > 32 * VI_BND_QT; };
+  vi_bnd_panel P;
+  if (warp == 0) { vi_bnd_qr_compute(S, 0, P); vi_bnd_qr_store(S, 0, P); }
+  vi_cta_sync();
+  for (int p = 0; p < npan; ++p) {
     vi_bnd_symm(S, p);
+    vi_cta_sync();
+    if (warp == 0) vi_bnd_small(S);
     vi_cta_sync();
     vi_bnd_wpanel(S, p, Vg);
     vi_cta_sync();
-    vi_bnd_update(S, p);
+    vi_bnd_update_col(S, p);
     vi_cta_sync();
+    const bool more = p + 1 < npan;
+    const bool ahead = more && !tall(p + 1) && S.nw > 1;
+    // look-ahead: warp 0 factors panel p + 1 while the others finish the trailing update of panel p
+    if (ahead && warp == 0) vi_bnd_qr_compute(S, p + 1, P);
+    else vi_bnd_update_rest(S, p, ahead ? 1 : 0);
+    vi_cta_sync();
+    if (more) {
+      if (warp == 0) {
+        if (!ahead) vi_bnd_qr_compute(S, p + 1, P);
+        vi_bnd_qr_store(S, p + 1, P);
+      }
+      vi_cta_sync();
+    }
   }
 }
 

@@ -4,14 +4,12 @@
 // Sweep s annihilates column s below its sub-diagonal with a Householder reflector of length 8 acting on rows
 // s+1..s+8; applying it from both sides pushes a bulge 8 rows down, whose first column the next reflector of the
 // same sweep removes, and so on to the end of the matrix (step k of sweep s acts on rows s+1+8k .. s+8+8k).  The
-// remaining bulge columns stay: the working band has 15 sub-diagonals.  Step k of sweep s+1 touches rows that sweep
-// s has finished with once sweep s has completed its step k+2, so up to four consecutive sweeps are in flight at a
-// time, one per group of 8 lanes (lane = row of the 8 x 8 blocks), in lock step.
+// remaining bulge columns stay: the working band has 15 sub-diagonals.  A step only ever writes its own 8 rows
+// (the update of the block below is deferred into the next step of the same sweep), so step k of sweep s+1 is
+// safe once sweep s has completed its step k+1: up to four consecutive sweeps are in flight at a time, one per
+// group of 8 lanes (lane = row of the 8 x 8 blocks), in lock step, two steps apart.
 //
-// Per step a lane group: builds the reflector from the column it clears, applies it from the left to the other 7
-// columns of the bulge block (lane = column there, so the dot products are local), two-sided to the diagonal
-// block, from the right to the block below (lane = row), and to the right-hand side g; the reflector goes to
-// global memory for the back-transformation (vi_chase_apply_q).
+// The reflector of every step goes to global memory for the back-transformation (vi_chs_apply_q).
 //
 // Reference call being replaced: scipy.linalg.lstsq at interpolate.py:462 (see vi_band.h).
 #pragma once
@@ -25,7 +23,8 @@
 #endif
 #endif
 
-#define VI_CHS_LDB 17      // rows of the working band per column: diagonal + 15 sub-diagonals (+ 1: odd stride)
+#define VI_CHS_LDB 18      // rows of the working band per column: diagonal + 15 sub-diagonals, padded so that both a
+                           // column walk (stride 1) and a row walk (stride LDB - 1 = 17) are bank-conflict free
 
 VI_HD int vi_chs_nsweeps(int n) { return n > 2 ? n - 2 : 0; }
 // steps of sweep s: rows s+1 .. n-1 in groups of 8
@@ -56,59 +55,99 @@ VI_DEV void vi_chs_load(double* Bw, double* g, const double* band, int n) {
   vi_warp_sync();
 }
 
-// One chase step by the 8 lanes of a group (r = lane % 8); `on` = false: the group idles but takes part in the
-// shuffles.  refl: 8 doubles of this reflector in global memory.
-VI_DEV void vi_chs_step(double* Bw, double* g, int n, int s, int k, bool on, double* refl) {
+// One chase step by the 8 lanes of a group (r = lane % 8 = row of the 8 x 8 blocks); `on` = false: the group idles but
+// takes part in the shuffles.  Step k of sweep s works on rows r0 .. r0+7, r0 = s + 1 + 8 k, and on nothing else:
+//   (k >= 1) the block left of the diagonal block, G = A[rows, r0-8 .. r0-1], first receives the PREVIOUS step's
+//            reflector from the right (that update is deferred to here so that a step never writes below its own
+//            rows: consecutive sweeps can then follow each other two steps apart instead of three);
+//   the reflector is built from the column being cleared (column s for k = 0, the first column of G otherwise);
+//   it is applied from the left to the other 7 columns of G, from both sides to the diagonal block, and to g.
+// Every load of the step is issued before the reflector's scalar chain (rsqrt, reciprocal) starts.
+// vprev / tauprev: the previous step's reflector of this sweep (in: step k-1's, out: this step's).
+// refl: 8 doubles of this reflector in global memory (tau, v[1..7]).
+VI_DEV double vi_chs_dot8(const double (&a)[8], const double (&b)[8]) {
+  const double s0 = fma(a[1], b[1], a[0] * b[0]), s1 = fma(a[3], b[3], a[2] * b[2]);
+  const double s2 = fma(a[5], b[5], a[4] * b[4]), s3 = fma(a[7], b[7], a[6] * b[6]);
+  return (s0 + s1) + (s2 + s3);
+}
+
+VI_DEV void vi_chs_step(double* Bw, double* g, int n, int s, int k, bool on, double* refl, double (&vprev)[8],
+                        double& tauprev, const int (&doff)[8]) {
   const int lane = vi_tid() & 31, r = lane & 7, base = lane & ~7;
   const int r0 = s + 1 + 8 * k;                 // first row / column of the diagonal block
   const int L = on ? ((n - r0 < 8) ? n - r0 : 8) : 0;       // rows of this step
   const int colx = (k == 0) ? s : r0 - 8;       // column being cleared
-  // ---- reflector from x = Bw[(r0 + r, colx)] --------------------------------------------------------------
-  double x = 0.0;
-  if (r < L) x = Bw[colx * VI_CHS_LDB + (r0 + r - colx)];
+  const bool row = r < L;
+  // ---- loads ---------------------------------------------------------------------------------------------------
+  double G[8], d[8];
+  double* grow = Bw + colx * VI_CHS_LDB + (r0 + r - colx);      // element (r0 + r, colx + q) at grow[q (LDB - 1)]
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int q = 0; q < 8; ++q) G[q] = (row && (k >= 1 || q == 0)) ? grow[q * (VI_CHS_LDB - 1)] : 0.0;
+  const double* dblk = Bw + r0 * VI_CHS_LDB;                    // element (r0 + max(r,q), r0 + min(r,q)) at dblk[doff[q]]
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int q = 0; q < 8; ++q) d[q] = (row && q < L) ? dblk[doff[q]] : 0.0;
+  const double gi = row ? g[r0 + r] : 0.0;
+  // ---- deferred right-apply of the previous reflector of this sweep -------------------------------------------
+  if (k >= 1 && tauprev != 0.0) {
+    const double dot = tauprev * vi_chs_dot8(G, vprev);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 8; ++q) G[q] = fma(-dot, vprev[q], G[q]);
+  }
+  // ---- reflector from x = first column ----------------------------------------------------------------------------
+  const double x = G[0];
   const double xn2 = vi_oct_allsum((r >= 1) ? x * x : 0.0);
   const double alpha = vi_shfl(x, base);
   double beta, tau, scale;
   vi_reflector_scalars(alpha, xn2, &beta, &tau, &scale);
   const double v = (r == 0) ? 1.0 : x * scale;            // zero for r >= L (x = 0 there)
-  if (r < L) Bw[colx * VI_CHS_LDB + (r0 + r - colx)] = (r == 0) ? beta : 0.0;
   if (on) refl[r] = (r == 0) ? tau : v;
   double vv[8];
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
   for (int q = 0; q < 8; ++q) vv[q] = vi_shfl(v, base + q);
-  // ---- left: the other columns of the bulge block (k >= 1): lane = column colx + r, r = 1..7 -----------------
-  if (on && k >= 1 && r >= 1 && tau != 0.0) {
-    double* col = Bw + (colx + r) * VI_CHS_LDB + (r0 - colx - r);     // element (r0 + q, colx + r) at col[q]
-    double e[8], dot = 0.0;
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-    for (int q = 0; q < 8; ++q) { e[q] = (q < L) ? col[q] : 0.0; dot = fma(vv[q], e[q], dot); }
-    dot *= tau;
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-    for (int q = 0; q < 8; ++q)
-      if (q < L) col[q] = fma(-dot, vv[q], e[q]);
-  }
-  // ---- two-sided on the diagonal block: lane = row r0 + r ---------------------------------------------------
+  G[0] = (r == 0) ? beta : 0.0;
+  // ---- left-apply to the other columns of G: w_c = tau sum_r v_r G[r][c] across the group's lanes --------------
+  // (every lane of the warp takes part in the shuffles, whatever its group's step: a group at k = 0 carries zeros)
   {
-    double d[8], pr = 0.0;
+    double w[8];
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-    for (int q = 0; q < 8; ++q) {
-      double t = 0.0;
-      if (r < L && q < L) {
-        const int hi = (r > q) ? r : q, lo = (r > q) ? q : r;
-        t = Bw[(r0 + lo) * VI_CHS_LDB + (hi - lo)];
-      }
-      d[q] = t;
-      pr = fma(t, vv[q], pr);
+    for (int q = 1; q < 8; ++q) w[q] = v * G[q];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int o = 1; o < 8; o <<= 1) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int q = 1; q < 8; ++q) w[q] += vi_shfl_xor(w[q], o);
     }
-    pr *= tau;                                            // p = tau D v
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int q = 1; q < 8; ++q) G[q] = fma(-(tau * w[q]), v, G[q]);
+  }
+  if (row) {
+    if (k >= 1) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int q = 0; q < 8; ++q) grow[q * (VI_CHS_LDB - 1)] = G[q];
+    } else {
+      grow[0] = G[0];
+    }
+  }
+  // ---- two-sided on the diagonal block -------------------------------------------------------------------------------
+  {
+    const double pr = tau * vi_chs_dot8(d, vv);           // p = tau D v
     const double vp = vi_oct_allsum(v * pr);
     const double w = pr - (0.5 * tau * vp) * v;           // w = p - (tau/2)(v.p) v
     double ww[8];
@@ -117,39 +156,24 @@ VI_DEV void vi_chs_step(double* Bw, double* g, int n, int s, int k, bool on, dou
 #endif
     for (int q = 0; q < 8; ++q) ww[q] = vi_shfl(w, base + q);
     if (tau != 0.0) {
+      double* dst = Bw + r0 * VI_CHS_LDB;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
       for (int q = 0; q < 8; ++q)
-        if (r < L && q <= r) Bw[(r0 + q) * VI_CHS_LDB + (r - q)] = (d[q] - v * ww[q]) - w * vv[q];
-    }
-  }
-  // ---- right: the block below, rows r0 + 8 + r, columns r0 .. r0 + L - 1: lane = row ------------------------
-  {
-    const int i = r0 + 8 + r;
-    if (on && i < n && tau != 0.0) {
-      double e[8], dot = 0.0;
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-      for (int q = 0; q < 8; ++q) {
-        e[q] = (q < L) ? Bw[(r0 + q) * VI_CHS_LDB + (i - r0 - q)] : 0.0;
-        dot = fma(e[q], vv[q], dot);
-      }
-      dot *= tau;
-#if defined(__CUDACC__)
-#pragma unroll
-#endif
-      for (int q = 0; q < 8; ++q)
-        if (q < L) Bw[(r0 + q) * VI_CHS_LDB + (i - r0 - q)] = fma(-dot, vv[q], e[q]);
+        if (row && q <= r) dst[doff[q]] = (d[q] - v * ww[q]) - w * vv[q];
     }
   }
   // ---- right-hand side ---------------------------------------------------------------------------------------
   {
-    const double gi = (r < L) ? g[r0 + r] : 0.0;
     const double dot = vi_oct_allsum(v * gi);
-    if (r < L && tau != 0.0) g[r0 + r] = gi - (tau * dot) * v;
+    if (row && tau != 0.0) g[r0 + r] = gi - (tau * dot) * v;
   }
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int q = 0; q < 8; ++q) vprev[q] = vv[q];
+  tauprev = tau;
 }
 
 // Whole reduction by one warp.  refl: 8 * vi_chs_nrefl(n) doubles (global).  Leaves d = Bw[(j, j)], e = Bw[(j+1, j)].
@@ -158,6 +182,17 @@ VI_DEV void vi_chs_reduce(double* Bw, double* g, int n, double* refl) {
   const int nsw = vi_chs_nsweeps(n);
   int s = grp;                       // this group's current sweep (s, s + 4, ...)
   int kdone = 0;                     // completed steps of it
+  double vprev[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  double tauprev = 0.0;
+  int doff[8];                       // diagonal-block offsets of this lane's row: min(r, q) LDB + |r - q|
+  {
+    const int r = lane & 7;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 8; ++q) doff[q] = ((r < q) ? r : q) * VI_CHS_LDB + ((r < q) ? q - r : r - q);
+  }
+  int roff = vi_chs_off(n, s);       // reflectors generated before this group's current sweep
   for (;;) {
     const int K = (s < nsw) ? vi_chs_nsteps(n, s) : 0;
     // predecessor sweep s - 1 belongs to group (grp + 3) % 4
@@ -168,7 +203,7 @@ VI_DEV void vi_chs_reduce(double* Bw, double* g, int n, double* refl) {
       if (ps < s - 1) can = false;                                     // predecessor not started yet
       else if (ps == s - 1) {
         const int Kp = vi_chs_nsteps(n, s - 1);
-        const int need = (kdone + 3 < Kp) ? kdone + 3 : Kp;            // it must have finished step kdone + 2
+        const int need = (kdone + 2 < Kp) ? kdone + 2 : Kp;            // it must have finished step kdone + 1
         can = pk >= need;
       }
     }
@@ -177,10 +212,14 @@ VI_DEV void vi_chs_reduce(double* Bw, double* g, int n, double* refl) {
     alive |= vi_shfl_i(alive, (lane + 8) & 31);
     alive |= vi_shfl_i(alive, (lane + 16) & 31);
     if (!alive) break;
-    vi_chs_step(Bw, g, n, s, kdone, can, can ? refl + 8 * (vi_chs_off(n, s) + kdone) : refl);
+    vi_chs_step(Bw, g, n, s, kdone, can, can ? refl + 8 * (roff + kdone) : refl, vprev, tauprev, doff);
     vi_warp_sync();
     if (can) {
-      if (++kdone == K) { s += 4; kdone = 0; }
+      if (++kdone == K) {              // next sweep of this group: s + 4
+        roff += K + ((s + 1 < nsw) ? vi_chs_nsteps(n, s + 1) : 0) + ((s + 2 < nsw) ? vi_chs_nsteps(n, s + 2) : 0) +
+                ((s + 3 < nsw) ? vi_chs_nsteps(n, s + 3) : 0);
+        s += 4; kdone = 0;
+      }
     }
   }
 }

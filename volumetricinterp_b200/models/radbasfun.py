@@ -60,14 +60,22 @@ class Model(object):
         return out
 
     def estimate_device(self, lat, lon, alt, C, hull_eq, out, stream=None):
-        """out[r, p] = basis(p) . C[r], NaN outside the hull (estimate.py:113-121)."""
+        """out[r, p] = basis(p) . C[r], NaN outside the hull (estimate.py:113-121); 16 or more records go through the
+        compaction + FP64 tensor-core GEMM path (vi_estimate_radbasfun_many)."""
         import torch
         s = stream if stream is not None else torch.cuda.current_stream(lat.device).cuda_stream
         cen = self.centers_device(lat.device)
         F = 0 if hull_eq is None else hull_eq.shape[0]
+        npts, R = lat.numel(), C.shape[0]
+        if R >= 16 and npts > 0 and self.nbasis <= 144:      # the GEMM tile holds K = nbasis columns in shared memory
+            ws = _native.estimate_workspace(lat.device, npts, self.nbasis, R)
+            _native.check(_native.lib().vi_estimate_radbasfun_many(
+                lat.data_ptr(), lon.data_ptr(), alt.data_ptr(), npts, cen.data_ptr(), self.nbasis, self.eps,
+                C.data_ptr(), R, hull_eq.data_ptr() if F else None, F, out.data_ptr(), ws.data_ptr(), ws.numel(), s))
+            return out
         _native.check(_native.lib().vi_estimate_radbasfun(
-            lat.data_ptr(), lon.data_ptr(), alt.data_ptr(), lat.numel(), cen.data_ptr(), self.nbasis, self.eps,
-            C.data_ptr(), C.shape[0], hull_eq.data_ptr() if F else None, F, out.data_ptr(), s))
+            lat.data_ptr(), lon.data_ptr(), alt.data_ptr(), npts, cen.data_ptr(), self.nbasis, self.eps,
+            C.data_ptr(), R, hull_eq.data_ptr() if F else None, F, out.data_ptr(), s))
         return out
 
     def basis(self, gdlat, gdlon, gdalt):

@@ -92,13 +92,21 @@ class Model(object):
         return out
 
     def estimate_device(self, lat, lon, alt, Cf, hull_eq, out, stream=None):
-        """out[r, p] = basis(p) . Cf[r], NaN outside the hull (estimate.py:113-121)."""
+        """out[r, p] = basis(p) . Cf[r], NaN outside the hull (estimate.py:113-121).  With 16 or more records the
+        in-hull points are compacted and the contraction runs as an FP64 tensor-core GEMM (vi_estimate_*_many)."""
         import torch
         s = stream if stream is not None else torch.cuda.current_stream(lat.device).cuda_stream
         F = 0 if hull_eq is None else hull_eq.shape[0]
+        npts, R = lat.numel(), Cf.shape[0]
+        if R >= 16 and npts > 0 and self.nbasis <= 144:      # the GEMM tile holds K = nbasis columns in shared memory
+            ws = _native.estimate_workspace(lat.device, npts, self.nbasis, R)
+            _native.check(_native.lib().vi_estimate_sphharmlag_many(
+                lat.data_ptr(), lon.data_ptr(), alt.data_ptr(), npts, C.byref(self.params()),
+                Cf.data_ptr(), R, hull_eq.data_ptr() if F else None, F, out.data_ptr(), ws.data_ptr(), ws.numel(), s))
+            return out
         _native.check(_native.lib().vi_estimate_sphharmlag(
-            lat.data_ptr(), lon.data_ptr(), alt.data_ptr(), lat.numel(), C.byref(self.params()),
-            Cf.data_ptr(), Cf.shape[0], hull_eq.data_ptr() if F else None, F, out.data_ptr(), s))
+            lat.data_ptr(), lon.data_ptr(), alt.data_ptr(), npts, C.byref(self.params()),
+            Cf.data_ptr(), R, hull_eq.data_ptr() if F else None, F, out.data_ptr(), s))
         return out
 
     def basis(self, gdlat, gdlon, gdalt):
