@@ -296,7 +296,7 @@ int h_system_solve_two_stage(int n, const double* G, const double* y, const doub
   if (bandout) std::memcpy(bandout, band.data(), 9 * (size_t)np * sizeof(double));
   std::vector<double> work(vi_chs_doubles(n) + 2, 0.0);
   double* Bw = work.data();
-  double* gw = Bw + VI_CHS_LDB * (np + 8);
+  double* gw = Bw + VI_CHS_LDB * np;
   emu::run_cta(0, 32, [&]() {
     vi_chs_load(Bw, gw, band.data(), n);
     vi_chs_reduce(Bw, gw, n, refl.data());

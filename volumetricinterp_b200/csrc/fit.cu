@@ -371,7 +371,7 @@ k_band(const double* __restrict__ G, const double* __restrict__ y, const double*
 
 // Stage 2, one WARP per system: band -> tridiagonal by bulge chasing, four sweeps in flight (one per 8 lanes).
 // Leaves d, e, g = Q2^T Q1^T y in the interleaved layout the QL kernels read; reflectors behind stage 1's in B.V.
-constexpr int kChaseWarps = 4;
+constexpr int kChaseWarps = 5;     // 5 x 21.5 KB at n = 144: two CTAs = 10 systems per SM
 __global__ void __launch_bounds__(kChaseWarps * 32)
 k_chase(int64_t nsys, SysBuf B) {
   extern __shared__ __align__(16) double sm[];
@@ -380,7 +380,7 @@ k_chase(int64_t nsys, SysBuf B) {
   if (s >= nsys || B.st[s] != VI_ST_OK) return;
   const int np = vi_bnd_npad(n);
   double* Bw = sm + (size_t)warp * vi_chs_doubles(n);
-  double* g = Bw + VI_CHS_LDB * (np + 8);
+  double* g = Bw + VI_CHS_LDB * np;
   vi_chs_load(Bw, g, B.band + s * (int64_t)vi_bnd_band_doubles(n), n);
   vi_chs_reduce(Bw, g, n, B.V + s * B.vstride + vi_bnd_vdoubles(n));
   const int64_t base = ileave(s, n);

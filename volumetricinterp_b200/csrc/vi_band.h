@@ -32,7 +32,9 @@
 
 #define VI_BND_NMAX 168
 #ifndef VI_BND_NW
-#define VI_BND_NW 8              // warps per CTA at production orders (two CTAs per SM)
+#define VI_BND_NW 6              // warps per CTA at production orders: two CTAs per SM leave 168 registers per thread,
+                                 // what the register-resident panel QR needs without spilling (measured on B200 at
+                                 // n = 144: 8 warps 0.72, 6 warps 0.59, 4 warps 0.60 us per system)
 #endif
 #define VI_BND_PART 136          // doubles per warp of partial Gram data: 64 (V^T Y) + 64 (V^T V) + 8 (V^T g)
 

@@ -40,16 +40,16 @@ VI_HD int vi_chs_nrefl(int n) { return vi_chs_off(n, vi_chs_nsweeps(n)); }
 // doubles of global reflector storage (8 per reflector: tau, v[1..7])
 VI_HD int vi_chs_rdoubles(int n) { return 8 * vi_chs_nrefl(n); }
 // shared-memory doubles per system (warp): working band + g
-VI_HD int vi_chs_doubles(int n) { const int np = (n + 7) & ~7; return VI_CHS_LDB * (np + 8) + np + 8; }
+VI_HD int vi_chs_doubles(int n) { const int np = (n + 7) & ~7; return VI_CHS_LDB * np + np + 8; }
 
 #if defined(__CUDACC__) || defined(VI_EMU)
 
 // Bw[c * LDB + (i - c)], i >= c.  band: 9 doubles per column + g behind (vi_bnd_store_band).
 VI_DEV void vi_chs_load(double* Bw, double* g, const double* band, int n) {
   const int lane = vi_tid() & 31, np = (n + 7) & ~7;
-  for (int e = lane; e < VI_CHS_LDB * (np + 8); e += 32) {
+  for (int e = lane; e < VI_CHS_LDB * np; e += 32) {
     const int c = e / VI_CHS_LDB, d = e - c * VI_CHS_LDB;
-    Bw[e] = (c < np && d <= 8) ? band[c * 9 + d] : 0.0;
+    Bw[e] = (d <= 8) ? band[c * 9 + d] : 0.0;
   }
   for (int i = lane; i < np + 8; i += 32) g[i] = (i < np) ? band[9 * np + i] : 0.0;
   vi_warp_sync();
