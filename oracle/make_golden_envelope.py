@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE -- reproducibility envelope of the reference at the rank-deficient orders, as a fixture.
 
-For every record of the golden cases mid27 and c1_144 (tests/golden/*.npz, produced by the UNMODIFIED reference):
+For every record of the golden cases mid27, c1_144 and c3_500 (tests/golden/*.npz, produced by the UNMODIFIED reference):
 the reference's algorithm (oracle/ref_port.py, bit-identical to the reference on these cases) is re-run
   * as shipped                                    ('gelsd': scipy.linalg.lstsq default driver, einsum normal equations)
   * with BLAS-order normal equations              ('blas':  a 1e-16 relative change of X)
@@ -25,7 +25,7 @@ from conftest import load_golden   # noqa: E402
 
 
 def main():
-    for case in ("mid27", "c1_144"):
+    for case in (sys.argv[1:] or ("mid27", "c1_144", "c3_500")):
         g = load_golden(case)
         out = {"case": case, "records": []}
         for r in range(g["value"].shape[0]):
