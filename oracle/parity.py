@@ -112,7 +112,7 @@ def compare(gpu_rows, ref_rows, env_rows, A_all, value, alt_rows=None):
     """gpu_rows / ref_rows / env_rows / alt_rows: per-record dicts (same records, same order).  ref = the reference's
     algorithm as shipped (einsum normal equations, gelsd); env = the same with BLAS-order normal equations; alt = the
     same with LAPACK gelss instead of gelsd (both envelopes: equally valid executions of the reference)."""
-    keys = ('status', 'sf', 'k_lo', 'lam', 'rank')
+    keys = ('status', 'sf', 'k_lo', 'lam', 'rank', 'calls')
     g, e, al, ga, per = [], [], [], [], []
     for r, (a, b, c) in enumerate(zip(gpu_rows, ref_rows, env_rows)):
         if a.get('sf') is None and a.get('nu') is not None and b.get('npts'):

@@ -34,9 +34,10 @@ def _fit(cuda, g, **kw):
                            device=cuda, **kw)
 
 
-@pytest.mark.parametrize("name", ["mid27", "c1_144"])
+@pytest.mark.parametrize("name", ["mid27", "c1_144", "c3_500"])
 def test_search_agrees_with_reference_trace_and_envelope(cuda, name):
-    """(a) record status, scale factor and bracket decade identical to the reference (interpolate.py:173-211);
+    """c3_500 is the high-order configuration of BASELINE configs[2] (N = 500, the reference's real curvature matrix).
+    (a) record status, scale factor and bracket decade identical to the reference (interpolate.py:173-211);
     (b) the chi2(10^-k) table equals the unmodified reference's trace decade by decade while the regulariser
     dominates (k <= 20: both solve a well-posed system there), 1e-5 relative;
     (c) lambda, chi2 and the fitted densities A.C inside the envelope of the reference against itself."""

@@ -164,7 +164,7 @@ def test_envelope_fixture_matches_the_golden_reference_run():
     import json
     import os
     from conftest import GOLDEN
-    for name in ("mid27", "c1_144"):
+    for name in ("mid27", "c1_144", "c3_500"):
         g = load_golden(name)
         env = json.load(open(os.path.join(GOLDEN, f"envelope_{name}.json")))["records"]
         assert len(env) == g["value"].shape[0]
@@ -206,3 +206,17 @@ def test_hull_tolerance_matches_the_rehull_decision():
     at_vertices = [rehull(v) for v in hv]
     assert all(inside(v) for v in hv)
     assert 0 < sum(at_vertices) < len(hv)        # the reference itself is not consistent on its own vertices
+
+
+def test_high_order_golden_is_reproduced_by_the_oracle():
+    """c3_500 (N = 500: MAXK 5, MAXL 10, CAP_LIM 11; generated by the unmodified reference with its real curvature
+    matrix): the oracle's design matrix is bit-identical and its search lands on the golden lambda and coefficients."""
+    import parity
+    g = load_golden("c3_500")
+    m = oracle_model(g)
+    assert m.nbasis == 500
+    assert np.array_equal(m.basis(g["lat"], g["lon"], g["alt"]), g["A"])
+    r = 1                                                   # 53 eval_C calls in the reference's trace
+    o = parity.oracle_record(g["A"], g["value"][r], g["error"][r], g["regs"][0], g["reglist"][0])
+    assert o["lam"] == g["lam"][r, 0] and o["calls"] == int(g["n_eval"][r])
+    assert np.array_equal(o["C"], g["Coeffs"][r])
