@@ -16,6 +16,7 @@
 #include "../volumetricinterp_b200/csrc/vi_ne_split.h"
 #include "../volumetricinterp_b200/csrc/vi_band.h"
 #include "../volumetricinterp_b200/csrc/vi_chase.h"
+#include "../volumetricinterp_b200/csrc/vi_wave.h"
 
 extern "C" {
 
@@ -324,6 +325,40 @@ int h_system_solve_two_stage(int n, const double* G, const double* y, const doub
   std::memcpy(C, u.data(), n * sizeof(double));
   return 0;
 }
+// Wavefront tape replay (vi_wave.h) against the sequential replay (vi_tql.h): QL of the tridiagonal (d0, e0), then
+// Z^T g and Z g both ways.  Returns 0 if the results are BIT-IDENTICAL, a positive code otherwise; *nsweeps = sweeps found.
+int h_wave_replay_identical(int n, const double* d0, const double* e0, const double* g0, int* nsweeps, int* nrot_out) {
+  std::vector<double> d(d0, d0 + n), e(n, 0.0);
+  for (int i = 0; i + 1 < n; ++i) e[i] = e0[i];
+  int cap = 2 * n * n + 64;
+  std::vector<double> tcs(2 * (size_t)cap);
+  std::vector<int32_t> ti(cap);
+  vi_tape tape{{tcs.data(), 2}, {tcs.data() + 1, 2}, {ti.data(), 1}, cap};
+  int32_t nr = 0;
+  if (vi_tql_values(n, {d.data(), 1}, {e.data(), 1}, tape, &nr) != 0) return 9;
+  *nrot_out = nr;
+  std::vector<double> a(g0, g0 + n), b(g0, g0 + n), wa(g0, g0 + n), wb(g0, g0 + n);
+  vi_tape_apply_zt({a.data(), 1}, tape, nr);
+  vi_tape_apply_z({b.data(), 1}, tape, nr);
+  const int maxsw = vi_wav_maxsweeps(n);
+  std::vector<int32_t> tab(maxsw + 2);
+  int ns = 0, tnext = 0;
+  emu::run_cta(0, 32, [&]() {
+    int tn = 0;
+    const int k = vi_wav_scan(ti.data(), 0, nr, tab.data(), maxsw, &tn);
+    if (vi_tid() == 0) { ns = k; tnext = tn; }
+    if (tn == nr) {
+      vi_wav_pass<true>(wa.data(), tcs.data(), ti.data(), tab.data(), k);
+      vi_wav_pass<false>(wb.data(), tcs.data(), ti.data(), tab.data(), k);
+    }
+  });
+  *nsweeps = ns;
+  if (tnext != nr) return 8;            // table overflow (the kernel then replays sequentially)
+  if (std::memcmp(a.data(), wa.data(), n * sizeof(double)) != 0) return 1;
+  if (std::memcmp(b.data(), wb.data(), n * sizeof(double)) != 0) return 2;
+  return 0;
+}
+
 int h_bnd_threads(int n) { return vi_bnd_threads(n); }
 int h_bnd_smem_bytes(int n) { return vi_bnd_doubles(n) * 8; }
 int h_chs_nrefl(int n) { return vi_chs_nrefl(n); }

@@ -495,3 +495,30 @@ def test_flattened_ql_is_bit_identical_to_nested(harness):
         nrot = C.c_int(0)
         rc = harness.h_tql_flat_identical(n, dptr(np.ascontiguousarray(d)), dptr(np.append(e, 0.0)), C.byref(nrot))
         assert rc == 0, (n, rc)
+
+
+@pytest.mark.parametrize("n,kind", [(5, "rand"), (27, "rand"), (64, "graded"), (144, "graded"), (144, "rand"), (144, "split"),
+                                    (160, "graded")])
+def test_wavefront_tape_replay_is_bit_identical(harness, n, kind):
+    """vi_wave.h (one warp per system, QL sweeps pipelined across the lanes) against the sequential tape replay of
+    vi_tql.h, both directions: the same rotations on the same operands in a different interleaving -> identical bits.
+    'split': a tridiagonal with negligible off-diagonals in the middle (short sweeps on sub-blocks, non-nested ranges)."""
+    import ctypes as C
+    rng = np.random.default_rng(n * 7 + len(kind))
+    d = rng.standard_normal(n)
+    e = rng.standard_normal(n)
+    if kind == "graded":
+        d *= 10.0 ** rng.uniform(-12, 0, n)
+        e *= 10.0 ** rng.uniform(-12, 0, n)
+    if kind == "split":
+        e[n // 3] = 1e-300
+        e[n // 2] = 0.0
+        e[n // 2 + 5] = 1e-40
+    g = rng.standard_normal(n)
+    ns, nr = C.c_int(0), C.c_int(0)
+    fn = harness.h_wave_replay_identical
+    fn.restype = C.c_int
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    rc = fn(n, dp(d), dp(e), dp(g), C.byref(ns), C.byref(nr))
+    assert rc == 0, (rc, ns.value, nr.value)
+    assert 0 < ns.value <= 4 * n + 32 and nr.value >= n - 1

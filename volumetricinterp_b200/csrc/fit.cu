@@ -33,6 +33,7 @@
 #include "vi_tridiag_packed.h"
 #include "vi_band.h"
 #include "vi_chase.h"
+#include "vi_wave.h"
 
 namespace {
 
@@ -601,6 +602,85 @@ k_apply(int64_t nsys, SysBuf B, double* __restrict__ Cout, int32_t* __restrict__
   }
   for (int i = lane; i < n; i += 32) Cs[i] = w[i];
   if (lane == 0) rank_out[s] = B.rank[s];
+}
+
+// u = Z L^+ Z^T g and c = Q u in ONE kernel, one WARP per system: the rotation tape is replayed as a wavefront of
+// QL sweeps across the lanes (vi_wave.h: ~7 rotations per step on average at n = 144 instead of one), the spectral
+// cut-off (|l| > rcond max|l|: gelsd's rule) runs lane-parallel, and the back-transformation (two-stage: chase
+// reflectors then block reflectors; one-stage: Householder rows) follows on the vector still in shared memory.
+// Replaces k_replay + k_apply / k_apply_ts (kept behind VI_OLD_REPLAY for A/B measurements).
+constexpr int kWaveWarps = 8;
+__global__ void __launch_bounds__(kWaveWarps * 32)
+k_replay_wave(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, int32_t* __restrict__ rank_out) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int n = B.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t s = (int64_t)blockIdx.x * kWaveWarps + warp;
+  if (s >= nsys) return;
+  const int st = B.st[s];
+  if (st == kSkip) return;
+  double* Cs = Cout + s * (int64_t)n;
+  if (st != VI_ST_OK) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int i = lane; i < n; i += 32) Cs[i] = nan;
+    if (lane == 0) rank_out[s] = 0;
+    return;
+  }
+  const int np = (n + 7) & ~7;
+  unsigned char* mine = smraw + (size_t)warp * vi_wav_bytes(n);
+  double* w = reinterpret_cast<double*>(mine);
+  int32_t* tab = reinterpret_cast<int32_t*>(mine + np * 8 + 64);
+  const int64_t base = ileave(s, n);
+  for (int i = lane; i < np + 8; i += 32) w[i] = (i < n) ? B.g[base + (int64_t)i * 32] : 0.0;
+  const int32_t nrot = B.nrot[s];
+  const double* cs = B.tcs + s * (int64_t)B.tapecap * 2;
+  const int32_t* ix = B.tix + s * (int64_t)B.tapecap;
+  int tnext = 0;
+  const int ns = vi_wav_scan(ix, 0, nrot, tab, vi_wav_maxsweeps(n), &tnext);
+  const bool whole = tnext == nrot;            // the sweep table holds the whole tape (else: sequential replay, rare)
+  if (whole) vi_wav_pass<true>(w, cs, ix, tab, ns);
+  else if (lane == 0) vi_tape_apply_zt(vi_svec{w, 1}, vi_tape{{const_cast<double*>(cs), 2}, {const_cast<double*>(cs) + 1, 2}, {const_cast<int32_t*>(ix), 1}, B.tapecap}, nrot);
+  __syncwarp();
+  // spectral cut-off
+  double lmax = 0.0;
+  for (int i = lane; i < n; i += 32) lmax = fmax(lmax, fabs(B.d[base + (int64_t)i * 32]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  const double cut = rcond * lmax;
+  int rank = 0;
+  for (int i = lane; i < n; i += 32) {
+    const double l = B.d[base + (int64_t)i * 32];
+    if (fabs(l) > cut) { w[i] = w[i] / l; ++rank; }
+    else w[i] = 0.0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+  __syncwarp();
+  if (whole) vi_wav_pass<false>(w, cs, ix, tab, ns);
+  else if (lane == 0) vi_tape_apply_z(vi_svec{w, 1}, vi_tape{{const_cast<double*>(cs), 2}, {const_cast<double*>(cs) + 1, 2}, {const_cast<int32_t*>(ix), 1}, B.tapecap}, nrot);
+  __syncwarp();
+  const double scl = B.scl[s];
+  for (int i = lane; i < n; i += 32) w[i] *= scl;
+  __syncwarp();
+  const double* Vg = B.V + s * B.vstride;
+  if (B.two_stage) {
+    vi_chs_apply_q(w, n, Vg + vi_bnd_vdoubles(n));
+    vi_bnd_apply_q(w, n, Vg);
+  } else {
+    for (int j = n - 3; j >= 0; --j) {           // Householder rows of the one-stage reduction (as k_apply)
+      const double t = B.tau[base + (int64_t)j * 32];
+      if (t == 0.0) continue;
+      const double* vj = Vg + (int64_t)j * n;
+      double dot = 0.0;
+      for (int i = j + 1 + lane; i < n; i += 32) dot += vj[i] * w[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      dot *= t;
+      for (int i = j + 1 + lane; i < n; i += 32) w[i] -= dot * vj[i];
+      __syncwarp();
+    }
+  }
+  for (int i = lane; i < n; i += 32) Cs[i] = w[i];
+  if (lane == 0) { rank_out[s] = rank; B.rank[s] = rank; }
 }
 
 // ---- covariance: dC = H (A^T W A) H, H = pinv(X)  (interpolate.py:464-467) ---------------------
@@ -1534,6 +1614,13 @@ int run_ql(int64_t cnt, const SysBuf& B, cudaStream_t s, bool* split) {
 
 int run_apply(int64_t cnt, const SysBuf& B, double rcond, double* Cout, int32_t* rank_out, cudaStream_t s, bool split) {
   if (cnt <= 0) return VI_OK;
+  static const bool old_replay = getenv("VI_OLD_REPLAY") != nullptr;
+  if (split && !old_replay) {
+    const size_t smem = (size_t)kWaveWarps * vi_wav_bytes(B.n);
+    VI_CUDA(cudaFuncSetAttribute(k_replay_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VI_KERNEL(VI_K_APPLY, s, k_replay_wave<<<blocks(cnt, kWaveWarps), kWaveWarps * 32, smem, s>>>(cnt, B, rcond, Cout, rank_out));
+    return VI_OK;
+  }
   if (split) {
     const size_t per_sys = (size_t)B.n * sizeof(double);
     const int fit = (int)((227 * 1024) / per_sys);
