@@ -359,6 +359,7 @@ int h_wave_replay_identical(int n, const double* d0, const double* e0, const dou
   return 0;
 }
 
+int h_wav_bytes(int n) { return vi_wav_bytes(n); }
 int h_bnd_threads(int n) { return vi_bnd_threads(n); }
 int h_bnd_smem_bytes(int n) { return vi_bnd_doubles(n) * 8; }
 int h_chs_nrefl(int n) { return vi_chs_nrefl(n); }

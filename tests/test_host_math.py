@@ -522,3 +522,5 @@ def test_wavefront_tape_replay_is_bit_identical(harness, n, kind):
     rc = fn(n, dp(d), dp(e), dp(g), C.byref(ns), C.byref(nr))
     assert rc == 0, (rc, ns.value, nr.value)
     assert 0 < ns.value <= 4 * n + 32 and nr.value >= n - 1
+    # per-warp slices of the kernel's shared memory stay 16-byte aligned (the vector is read as doubles)
+    assert all(harness.h_wav_bytes(m) % 16 == 0 and harness.h_wav_bytes(m) >= 8 * m + 4 * (4 * m + 33) for m in range(1, 600))

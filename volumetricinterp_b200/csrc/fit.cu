@@ -238,15 +238,21 @@ int env_int(const char* name, int dflt) {
 
 // QL kernel geometry (k_tql_smem): one CTA per SM of W warps, at most Lmax lanes of each carry a system
 // (2n doubles of shared memory per system).  Returns 0 warps when not even 32 systems fit.
-int ql_lanes_max() { static const int L = env_int("VI_TQL_LANES", 12); return L > 32 ? 32 : L; }
+int ql_fit(int n) { return (int)((227 * 1024) / ((size_t)2 * n * sizeof(double))); }      // systems per SM
+int ql_lanes_max(int n = 0) {
+  static const int L0 = env_int("VI_TQL_LANES", 12);
+  int L = L0 > 32 ? 32 : L0;
+  if (n > 0 && L > ql_fit(n)) L = ql_fit(n);      // high orders (N = 500: 29 systems per SM): fewer lanes, never none
+  return L;
+}
 int ql_warps(int n) {
-  const int fit = (int)((227 * 1024) / ((size_t)2 * n * sizeof(double)));
-  if (fit < 32) return 0;
-  int W = fit / ql_lanes_max();
+  const int fit = ql_fit(n);
+  if (fit < 1) return 0;
+  int W = fit / ql_lanes_max(n);
   if (W > 24) W = 24;
   return W < 1 ? 1 : W;
 }
-int64_t ql_wave(int n) { return (int64_t)sm_count() * ql_warps(n) * ql_lanes_max(); }
+int64_t ql_wave(int n) { return (int64_t)sm_count() * ql_warps(n) * ql_lanes_max(n); }
 
 int64_t default_system_cap(int64_t wanted, int n, int nreg, int P) {
   int64_t per = per_system_bytes(n, nreg, P);
@@ -1584,7 +1590,7 @@ int sparse_lanes(int64_t cnt, int sys_per_sm_max, int warps_per_sm, int Lmax) {
 
 int run_ql(int64_t cnt, const SysBuf& B, cudaStream_t s, bool* split) {
   const size_t per_sys = (size_t)2 * B.n * sizeof(double);
-  const int W = ql_warps(B.n), Lmax = ql_lanes_max();
+  const int W = ql_warps(B.n), Lmax = ql_lanes_max(B.n);
   *split = W > 0;
   if (cnt <= 0 || !*split) return VI_OK;
   const int L = sparse_lanes(cnt, W * Lmax, W, Lmax);
@@ -1602,6 +1608,7 @@ int run_ql(int64_t cnt, const SysBuf& B, cudaStream_t s, bool* split) {
   if (per_sm <= single_max) {
     int W1 = (int)per_sm;
     if (W1 > 24) W1 = 24;      // 78 registers per thread
+    if (W1 > ql_fit(B.n)) W1 = ql_fit(B.n);
     if (W1 < 1) W1 = 1;
     const size_t smem1 = (size_t)W1 * per_sys;
     VI_CUDA(cudaFuncSetAttribute(k_tql_single, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));

@@ -29,7 +29,7 @@
 // budget is 30 n -- a tape with more sweeps than this is replayed in several table loads)
 VI_HD int vi_wav_maxsweeps(int n) { return 4 * n + 32; }
 // shared-memory bytes per warp: vector (n doubles, padded) + sweep table
-VI_HD int vi_wav_bytes(int n) { return ((n + 7) & ~7) * 8 + 64 + (vi_wav_maxsweeps(n) + 1) * 4; }
+VI_HD int vi_wav_bytes(int n) { return (((n + 7) & ~7) * 8 + 64 + (vi_wav_maxsweeps(n) + 1) * 4 + 15) & ~15; }   // warps stay 16-byte aligned
 
 #if defined(__CUDACC__) || defined(VI_EMU)
 
