@@ -140,7 +140,7 @@ k_est_shl_tile(const double* __restrict__ lat, const double* __restrict__ lon, c
 // memory, then streams the coefficient vectors through in chunks of 32 records (double buffered) and
 // contracts with mma.sync.m16n8k16.f64.  Both operands are stored with the k index permuted inside each
 // group of 16 (k -> 4 (k % 4) + k / 4) and a row stride = 2 (mod 16) doubles, so that every fragment is
-// two conflict-free 128-bit shared loads (same scheme as k_ne_dmma2).
+// two conflict-free 128-bit shared loads (same scheme as k_ne_dmma3).
 constexpr int kMmaRC = 32;          // records per chunk
 
 __device__ __forceinline__ int k_slot(int k) { return (k & ~15) | ((k & 3) << 2) | ((k >> 2) & 3); }

@@ -11,11 +11,10 @@
 // Two kernels:
 //   k_ne_strict  VI_NE_STRICT: acc = (A[j,i]*w[j])*A[j,k] + acc, sequential in j, two
 //                roundings per term, never fused — reproduces np.einsum bit for bit.
-//   k_ne_dmma    VI_NE_FAST: per record a symmetric rank-P update G = (A.w)^T A on the FP64
-//                tensor-core path (mma.sync m16n8k4 f64), lower-triangular 16x8 tiles only, the
-//                right-hand side y = A^T (w.b) rides along as one extra tile column.  A is
-//                staged through shared memory by cp.async double buffering; the weights are
-//                applied to the A-fragment in registers.
+//   k_ne_dmma3   VI_NE_FAST: per record a symmetric rank-P update G = (A.w)^T A on the FP64
+//                tensor-core path (mma.sync m16n8k16 / m8n8k4 f64), lower triangle only, the
+//                right-hand side y = A^T (w.b) on the FP64 ALUs from the fragments the diagonal
+//                units hold.  A is staged through shared memory by cp.async double buffering.
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -150,18 +149,6 @@ k_ne_strict(const double* __restrict__ A, const double* __restrict__ value, cons
 // ---------------------------------------------------------------------------------------------
 // fast: FP64 tensor-core (DMMA) symmetric rank-P update, one record per CTA
 // ---------------------------------------------------------------------------------------------
-constexpr int kDW = 12;          // warps per CTA
-constexpr int kDT = 12;          // max 16x8 tiles per warp
-constexpr int kDJ = 32;          // gates per stage
-constexpr int kDStages = 2;
-
-__device__ __forceinline__ void dmma_16x8x4(double (&d)[4], double a0, double a1, double b0) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
-      : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3])
-      : "d"(a0), "d"(a1), "d"(b0));
-}
-
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc));
@@ -170,132 +157,12 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// leading dimension (doubles) of a staged row: >= cols, 2*ld mod 32 in {8, 24} (conflict-free fragments)
-__host__ __device__ inline int dmma_ld(int cols) {
-  int ld = cols;
-  while (((2 * ld) % 32) != 8 && ((2 * ld) % 32) != 24) ++ld;
-  return ld;
-}
-
-__global__ void __launch_bounds__(kDW * 32)
-k_ne_dmma(const double* __restrict__ A, const double* __restrict__ value, const double* __restrict__ error,
-          const double* __restrict__ weight, int P, int N, int mt, int nt, int ld, int ntiles, int tpw,
-          double* __restrict__ G, double* __restrict__ y) {
-  extern __shared__ double sm[];
-  double* As = sm;                                     // kDStages x kDJ x ld
-  double* sw = sm + (size_t)kDStages * kDJ * ld;       // kDStages x kDJ
-  unsigned char* tmi = reinterpret_cast<unsigned char*>(sw + kDStages * kDJ);   // ntiles
-  unsigned char* tni = tmi + 256;
-  const int r = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
-
-  // tile table: lower-triangular 16x8 tiles (8*ni <= 16*mi + 15), then the rhs column tiles (ni = nt-1)
-  if (tid == 0) {
-    int c = 0;
-    for (int mi = 0; mi < mt; ++mi) {
-      for (int ni = 0; ni < nt - 1; ++ni)
-        if (8 * ni <= 16 * mi + 15 && 8 * ni < N) { tmi[c] = (unsigned char)mi; tni[c] = (unsigned char)ni; ++c; }
-      tmi[c] = (unsigned char)mi; tni[c] = (unsigned char)(nt - 1); ++c;
-    }
-  }
-  // zero both stages once (padding columns stay zero; cp.async only overwrites columns < N)
-  for (int e = tid; e < kDStages * kDJ * ld; e += blockDim.x) As[e] = 0.0;
-  __syncthreads();
-
-  const int t0 = warp * tpw;
-  const int t1 = min(ntiles, t0 + tpw);
-  double acc[kDT][4];
-#pragma unroll
-  for (int q = 0; q < kDT; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0; }
-
-  // (mi, ni) of the tiles this warp owns, packed in registers (-1 = none)
-  int tinfo[kDT];
-#pragma unroll
-  for (int q = 0; q < kDT; ++q) {
-    const int tt = t0 + q;
-    tinfo[q] = (tt < t1) ? ((int)tmi[tt] | ((int)tni[tt] << 8)) : -1;
-  }
-
-  const int bcol = 8 * (nt - 1);      // the rhs lives in column bcol of the staged rows
-  const int nchunk = (P + kDJ - 1) / kDJ;
-  auto stage_load = [&](int chunk, int st) {
-    double* dst = As + (size_t)st * kDJ * ld;
-    const int j0 = chunk * kDJ;
-    for (int e = tid; e < kDJ * N; e += blockDim.x) {
-      int jj = e / N, c = e - jj * N;
-      int j = j0 + jj;
-      if (j < P) cp_async8(dst + jj * ld + c, A + (int64_t)j * N + c);
-      else dst[jj * ld + c] = 0.0;
-    }
-    if (tid < kDJ) {
-      int j = j0 + tid;
-      double w = 0.0, b = 0.0;
-      if (j < P) load_wb(value, error, weight, (int64_t)r * P + j, w, b);
-      sw[st * kDJ + tid] = w;
-      dst[tid * ld + bcol] = b;
-    }
-    cp_async_commit();
-  };
-
-  stage_load(0, 0);
-  for (int ch = 0; ch < nchunk; ++ch) {
-    const int st = ch & 1;
-    if (ch + 1 < nchunk) { stage_load(ch + 1, st ^ 1); cp_async_wait<1>(); }
-    else cp_async_wait<0>();
-    __syncthreads();
-    const double* S = As + (size_t)st * kDJ * ld;
-    const double* W = sw + st * kDJ;
-#pragma unroll 2
-    for (int ks = 0; ks < kDJ / 4; ++ks) {
-      const int jj = 4 * ks + t;
-      const double w = W[jj];
-      const double* row = S + jj * ld;
-      int cur_mi = -1;
-      double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-      for (int q = 0; q < kDT; ++q) {
-        if (tinfo[q] >= 0) {
-          const int mi = tinfo[q] & 255, ni = tinfo[q] >> 8;
-          if (mi != cur_mi) {
-            cur_mi = mi;
-            a0 = row[16 * mi + g] * w;
-            a1 = row[16 * mi + g + 8] * w;
-          }
-          const double b0 = row[8 * ni + g];
-          dmma_16x8x4(acc[q], a0, a1, b0);
-        }
-      }
-    }
-    __syncthreads();
-  }
-
-  // epilogue: c0 (g, 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1)
-#pragma unroll
-  for (int q = 0; q < kDT; ++q) {
-    if (tinfo[q] < 0) continue;
-    const int mi = tinfo[q] & 255, ni = tinfo[q] >> 8;
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      const int i = 16 * mi + g + ((v & 2) ? 8 : 0);
-      const int k = 8 * ni + 2 * t + (v & 1);
-      if (i >= N) continue;
-      const double val = acc[q][v];
-      if (ni == nt - 1) {
-        if (k == bcol) y[(int64_t)r * N + i] = val;
-      } else if (k <= i) {
-        G[((int64_t)r * N + i) * N + k] = val;
-        if (k != i) G[((int64_t)r * N + k) * N + i] = val;
-      }
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
-// fast, version 2: m16n8k16 DMMA, operands staged TRANSPOSED (column-major over the gates of a
+// fast: FP64 tensor-core (DMMA) symmetric rank-P update, one record per CTA (k_ne_dmma3 below).
+// Staging shared by the kernel: A transposed in shared memory (kELD doubles per basis function and
 // stage, gate index permuted so that the four k-values a lane feeds to one instruction are adjacent:
 // every fragment is two 128-bit shared loads), masked weights / data streamed by cp.async from the
-// arrays k_prep wrote (no division in the pipeline), 3 stages, one CTA barrier per 32 gates.
+// arrays k_prep wrote (no division in the pipeline), one CTA barrier per stage.
 // ---------------------------------------------------------------------------------------------
 constexpr int kEJ = 80;          // gates per stage (five k16 steps)
 constexpr int kELD = 82;         // doubles per staged column: 82 = 2 (mod 16) -> conflict-free 128-bit fragment loads
@@ -313,133 +180,8 @@ __device__ __forceinline__ void dmma_16x8x16(double (&d)[4], const double (&a)[8
 // position of gate jj (0..kEJ-1) inside a staged column: within each block of 16 gates, k -> 4 (k % 4) + k / 4
 __device__ __forceinline__ int gate_slot(int jj) { return (jj & ~15) | ((jj & 3) << 2) | ((jj >> 2) & 3); }
 
-template <int DT>
-__global__ void __launch_bounds__(kDW * 32)
-k_ne_dmma2(const double* __restrict__ A, const double* __restrict__ Wm, const double* __restrict__ bm,
-           int P, int N, int mt, int nt, int cols, int ntiles, int tpw, double* __restrict__ G, double* __restrict__ y) {
-  extern __shared__ __align__(16) double sm[];
-  double* S = sm;                                              // kEStages x cols x kELD
-  double* sw = sm + (size_t)kEStages * cols * kELD;            // kEStages x kEJ (slot order)
-  unsigned char* tmi = reinterpret_cast<unsigned char*>(sw + kEStages * kEJ);
-  unsigned char* tni = tmi + 256;
-  const int r = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
-  if (tid == 0) {
-    int c = 0;
-    for (int mi = 0; mi < mt; ++mi) {
-      for (int ni = 0; ni < nt - 1; ++ni)
-        if (8 * ni <= 16 * mi + 15 && 8 * ni < N) { tmi[c] = (unsigned char)mi; tni[c] = (unsigned char)ni; ++c; }
-      tmi[c] = (unsigned char)mi; tni[c] = (unsigned char)(nt - 1); ++c;
-    }
-  }
-  for (int e = tid; e < kEStages * cols * kELD + kEStages * kEJ; e += blockDim.x) sm[e] = 0.0;
-  __syncthreads();
-  // balanced split: ntiles / 12 tiles per warp, the remainder one each to the first warps (warps w, w+4, w+8
-  // share a tensor pipe, so the extras land on different sub-partitions)
-  (void)tpw;
-  const int tbase = ntiles / kDW, textra = ntiles % kDW;
-  const int t0 = warp * tbase + min(warp, textra);
-  const int t1 = t0 + tbase + (warp < textra ? 1 : 0);
-  int tinfo[DT];
-  double acc[DT][4];
-#pragma unroll
-  for (int q = 0; q < DT; ++q) {
-    const int tt = t0 + q;
-    tinfo[q] = (tt < t1) ? ((int)tmi[tt] | ((int)tni[tt] << 8)) : -1;
-    acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0;
-  }
-  const int bcol = 8 * (nt - 1);
-  const int nchunk = (P + kEJ - 1) / kEJ;
-  const int rj = tid / 48, cc = tid - 48 * rj;      // kDW * 32 = 384 threads = 8 x 48
-  const double* Wr = Wm + (int64_t)r * P;
-  const double* br = bm + (int64_t)r * P;
-
-  auto stage_load = [&](int chunk) {
-    const int st = chunk % kEStages;
-    double* dst = S + (size_t)st * cols * kELD;
-    const int j0 = chunk * kEJ;
-    // thread (rj, cc): gates rj, rj+8, rj+16, rj+24 x columns cc, cc+48, ... (no division in the loop;
-    // 48 consecutive lanes read 384 contiguous bytes of one row of A)
-#pragma unroll
-    for (int q = 0; q < kEJ / 8; ++q) {
-      const int jj = rj + 8 * q;
-      const int j = j0 + jj;
-      const int sl = gate_slot(jj);
-      if (j < P) {
-        const double* src = A + (int64_t)j * N;
-        for (int c = cc; c < N; c += 48) cp_async8(dst + c * kELD + sl, src + c);
-      } else {
-        for (int c = cc; c < N; c += 48) dst[c * kELD + sl] = 0.0;
-      }
-    }
-    if (tid < kEJ) {
-      const int j = j0 + tid, sl = gate_slot(tid);
-      if (j < P) { cp_async8(sw + st * kEJ + sl, Wr + j); cp_async8(dst + bcol * kELD + sl, br + j); }
-      else { sw[st * kEJ + sl] = 0.0; dst[bcol * kELD + sl] = 0.0; }
-    }
-    cp_async_commit();
-  };
-
-  // kEStages - 1 chunks in flight ahead of the one being consumed
-  for (int c = 0; c < kEStages - 1 && c < nchunk; ++c) stage_load(c);
-  for (int ch = 0; ch < nchunk; ++ch) {
-    if (kEStages >= 3 && ch + 1 < nchunk) cp_async_wait<kEStages - 2>(); else cp_async_wait<0>();
-    __syncthreads();       // chunk ch visible to all; everybody is done with the stage chunk ch + kEStages - 1 reuses
-    if (ch + kEStages - 1 < nchunk) stage_load(ch + kEStages - 1);
-    const int st = ch % kEStages;
-    const double* Sst = S + (size_t)st * cols * kELD;
-    const double* Wst = sw + st * kEJ;
-#pragma unroll
-    for (int ks = 0; ks < kEJ / 16; ++ks) {
-      const int kb = 16 * ks + 4 * t;
-      const double2 w01 = *reinterpret_cast<const double2*>(Wst + kb);
-      const double2 w23 = *reinterpret_cast<const double2*>(Wst + kb + 2);
-      int cur_mi = -1;
-      double a[8];
-#pragma unroll
-      for (int q = 0; q < DT; ++q) {
-        if (tinfo[q] >= 0) {
-          const int mi = tinfo[q] & 255, ni = tinfo[q] >> 8;
-          if (mi != cur_mi) {
-            cur_mi = mi;
-            const double* p0 = Sst + (16 * mi + g) * kELD + kb;
-            const double* p1 = p0 + 8 * kELD;
-            const double2 x01 = *reinterpret_cast<const double2*>(p0), x23 = *reinterpret_cast<const double2*>(p0 + 2);
-            const double2 z01 = *reinterpret_cast<const double2*>(p1), z23 = *reinterpret_cast<const double2*>(p1 + 2);
-            a[0] = x01.x * w01.x; a[2] = x01.y * w01.y; a[4] = x23.x * w23.x; a[6] = x23.y * w23.y;
-            a[1] = z01.x * w01.x; a[3] = z01.y * w01.y; a[5] = z23.x * w23.x; a[7] = z23.y * w23.y;
-          }
-          const double* pb = Sst + (8 * ni + g) * kELD + kb;
-          const double2 b01 = *reinterpret_cast<const double2*>(pb), b23 = *reinterpret_cast<const double2*>(pb + 2);
-          const double b[4] = {b01.x, b01.y, b23.x, b23.y};
-          dmma_16x8x16(acc[q], a, b);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < DT; ++q) {
-    if (tinfo[q] < 0) continue;
-    const int mi = tinfo[q] & 255, ni = tinfo[q] >> 8;
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {
-      const int i = 16 * mi + g + ((v & 2) ? 8 : 0);
-      const int k = 8 * ni + 2 * t + (v & 1);
-      if (i >= N) continue;
-      const double val = acc[q][v];
-      if (ni == nt - 1) {
-        if (k == bcol) y[(int64_t)r * N + i] = val;
-      } else if (k <= i) {
-        G[((int64_t)r * N + i) * N + k] = val;
-        if (k != i) G[((int64_t)r * N + k) * N + i] = val;
-      }
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
-// fast, version 3: version 2 without the work that is not part of the lower triangle.
+// the kernel: only the work that is part of the lower triangle.
 //   * the right-hand side y = A^T W b no longer occupies a 16x8 tile per row block (one useful column
 //     of eight): it is accumulated with plain DFMAs from the A fragments the diagonal unit holds anyway;
 //   * the tile right of the diagonal block's first half, (mi, 2 mi + 1), only has its lower 8 rows
@@ -620,49 +362,34 @@ extern "C" int vi_normal_eq_batched(const double* A, const double* value, const 
   };
   if (mode == VI_NE_STRICT) return strict();
   if (mode != VI_NE_FAST) { vi_set_error("unknown normal-equation mode %d", mode); return VI_EINVAL; }
+  // the tensor-core kernel keeps one record's whole lower triangle of 16 x 8 tiles in one CTA (N <= 160); larger
+  // models (the reference has no limit: radbasfun NUMGRIDPNT = 7 is N = 343, interpolate.py:456) run the tiled
+  // strict kernel
   const int mt = (N + 15) / 16;
-  const int nt = (N + 7) / 8 + 1;             // + rhs column tile
-  int ntiles = 0;
-  for (int mi = 0; mi < mt; ++mi) {
-    for (int ni = 0; ni < nt - 1; ++ni)
-      if (8 * ni <= 16 * mi + 15 && 8 * ni < N) ++ntiles;
-    ++ntiles;
-  }
-  // the tensor-core kernels keep one record's whole tile set in one CTA (nbasis <= VI_NMAX_SMEM); larger models
-  // (the reference has no limit: radbasfun NUMGRIDPNT=7 is N = 343, interpolate.py:456) run the tiled strict kernel
-  if (ntiles > kDW * kDT || ntiles > 255) return strict();
-  const int cols = (16 * mt > 8 * nt) ? 16 * mt : 8 * nt;
-  const int tpw = (ntiles + kDW - 1) / kDW;
-  if (Wm && bm && !getenv("VI_NE_V2")) {
-    // version 3: lower-triangle work only (half tiles on the diagonal, rhs on the FP64 ALUs)
-    const int cols3 = 16 * mt;
-    size_t smem3 = ((size_t)kEStages * cols3 * kELD + 2 * kEStages * kEJ) * sizeof(double) + 64;
-    NeSplit sp;
-    if (smem3 <= 227 * 1024 && ne3_split(N, mt, 7, sp)) {
-      VI_CUDA(cudaFuncSetAttribute(k_ne_dmma3<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-      VI_KERNEL(VI_K_NORMAL_EQ, s, k_ne_dmma3<7><<<(unsigned)R, kW3 * 32, smem3, s>>>(A, Wm, bm, P, N, mt, cols3, sp, G, y));
-      VI_LAUNCH_CHECK();
-      return VI_OK;
+  const int cols3 = 16 * mt;
+  const size_t smem3 = ((size_t)kEStages * cols3 * kELD + 2 * kEStages * kEJ) * sizeof(double) + 64;
+  NeSplit sp;
+  if (smem3 > 227 * 1024 || !ne3_split(N, mt, 7, sp)) return strict();
+  // masked weights / data: the caller's arrays, else a stream-ordered temporary
+  double *Wt = nullptr, *bt = nullptr;
+  if (!Wm || !bm) {
+    VI_CUDA(cudaMallocAsync(&Wt, (size_t)R * P * sizeof(double), s));
+    if (cudaMallocAsync(&bt, (size_t)R * P * sizeof(double), s) != cudaSuccess) {
+      cudaFreeAsync(Wt, s);
+      vi_set_error("out of device memory for the masked weights (%lld bytes)", (long long)R * P * 8);
+      return VI_ECUDA;
     }
+    VI_KERNEL(VI_K_NORMAL_EQ, s, k_prep<<<R, 256, 0, s>>>(value, error, weight, P, nullptr, nullptr, Wt, bt));
+    Wm = Wt; bm = bt;
   }
-  if (Wm && bm) {
-    // masked weights / data already materialised by k_prep: streaming variant
-    size_t smem2 = ((size_t)kEStages * cols * kELD + kEStages * kEJ) * sizeof(double) + 512;
-    if (smem2 <= 227 * 1024) {
-      if (tpw <= 9) {
-        VI_CUDA(cudaFuncSetAttribute(k_ne_dmma2<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        VI_KERNEL(VI_K_NORMAL_EQ, s, k_ne_dmma2<9><<<(unsigned)R, kDW * 32, smem2, s>>>(A, Wm, bm, P, N, mt, nt, cols, ntiles, tpw, G, y));
-      } else {
-        VI_CUDA(cudaFuncSetAttribute(k_ne_dmma2<kDT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        VI_KERNEL(VI_K_NORMAL_EQ, s, k_ne_dmma2<kDT><<<(unsigned)R, kDW * 32, smem2, s>>>(A, Wm, bm, P, N, mt, nt, cols, ntiles, tpw, G, y));
-      }
-      return VI_OK;
-    }
+  cudaError_t e = cudaFuncSetAttribute(k_ne_dmma3<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+  if (e == cudaSuccess) {
+    vi_prof_launch_begin(VI_K_NORMAL_EQ, s);
+    k_ne_dmma3<7><<<(unsigned)R, kW3 * 32, smem3, s>>>(A, Wm, bm, P, N, mt, cols3, sp, G, y);
+    vi_prof_launch_end(VI_K_NORMAL_EQ, s);
+    e = cudaGetLastError();
   }
-  const int ld = dmma_ld(cols);
-  size_t smem = ((size_t)kDStages * kDJ * ld + kDStages * kDJ) * sizeof(double) + 512;
-  VI_CUDA(cudaFuncSetAttribute(k_ne_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  VI_KERNEL(VI_K_NORMAL_EQ, s, k_ne_dmma<<<(unsigned)R, kDW * 32, smem, s>>>(A, value, error, weight, P, N, mt, nt, ld, ntiles, tpw, G, y));
-  VI_LAUNCH_CHECK();
+  if (Wt) { cudaFreeAsync(Wt, s); cudaFreeAsync(bt, s); }
+  if (e != cudaSuccess) { vi_set_error("k_ne_dmma3: %s", cudaGetErrorString(e)); return VI_ECUDA; }
   return VI_OK;
 }
