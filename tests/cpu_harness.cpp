@@ -272,6 +272,9 @@ int h_trp_octet_of(int n, int warp, int slot, int a) {
   return vi_trp_octet_of(W, warp, slot, a);
 }
 
+static int g_split_p1 = 0, g_split_nw = 0, g_split_qt = 4;
+void h_bnd_set_split(int p1, int nw2, int qt) { g_split_p1 = p1; g_split_nw = nw2; g_split_qt = qt; }
+
 // Two-stage pipeline of kernels k_band + k_chase + QL + back-transformation (csrc/vi_band.h, vi_chase.h), the device
 // code itself executed by the CUDA-on-CPU model of tests/cuda_emu.h (one fiber per CUDA thread):
 //   X -> band (one CTA) -> tridiagonal (one warp) -> QL with tape -> truncated solve -> C = Q1 Q2 c~.
@@ -284,14 +287,40 @@ int h_system_solve_two_stage(int n, const double* G, const double* y, const doub
   double* base = smem.data();
   if (reinterpret_cast<uintptr_t>(base) & 15) base += 1;
   double scl = 1.0, badf = 0.0;
+  const int p1 = (g_split_p1 > 0 && g_split_p1 < vi_bnd_nbk(n) - 1) ? g_split_p1 : 0;      // split reduction (k_band + k_band_tail)
+  std::vector<double> Xt(p1 ? vi_bnd_trailing_doubles(n, p1) + 2 : 2, 0.0);
   emu::run_cta(0, nt, [&]() {
     vi_bnd_ws S;
     vi_bnd_carve(S, base, n);
     vi_bnd_load(S, G, y, regs, lam, nreg, nullptr, 0.0, 0.0);
     const bool isbad = S.sc[1] != 0.0;
-    if (!isbad) { vi_bnd_reduce(S, Vg.data()); vi_bnd_store_band(S, band.data()); }
+    if (!isbad) {
+      if (p1) {
+        vi_bnd_reduce(S, Vg.data(), p1);
+        vi_bnd_store_band(S, band.data(), band.data() + 9 * np, 8 * p1);
+        vi_bnd_store_trailing(S, p1, Xt.data());
+      } else {
+        vi_bnd_reduce(S, Vg.data());
+        vi_bnd_store_band(S, band.data());
+      }
+    }
     if (vi_tid() == 0) { scl = S.sc[0]; badf = S.sc[1]; }
   });
+  if (p1 && badf == 0.0) {
+    const int n2 = n - 8 * p1, nw2 = g_split_nw > 0 ? g_split_nw : vi_bnd_nwarp(n2);
+    std::vector<double> smem2(vi_bnd_doubles(n2, nw2) + 2);
+    double* base2 = smem2.data();
+    if (reinterpret_cast<uintptr_t>(base2) & 15) base2 += 1;
+    emu::run_cta(0, 32 * nw2, [&]() {
+      vi_bnd_ws S;
+      vi_bnd_carve(S, base2, n2, nw2);
+      vi_bnd_load_trailing(S, Xt.data());
+      double* Vg2 = Vg.data() + vi_bnd_voff(np, p1);
+      if (g_split_qt == 3 && S.npad - 8 <= 96) vi_bnd_reduce<3>(S, Vg2);
+      else vi_bnd_reduce<4>(S, Vg2);
+      vi_bnd_store_band(S, band.data() + 9 * 8 * p1, band.data() + 9 * np + 8 * p1, S.npad);
+    });
+  }
   *bad = badf != 0.0;
   if (*bad) return 0;
   if (bandout) std::memcpy(bandout, band.data(), 9 * (size_t)np * sizeof(double));

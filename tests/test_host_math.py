@@ -211,6 +211,49 @@ def test_two_stage_band_is_orthogonally_similar(harness):
     assert np.abs(band.reshape(npad, 9)[n:]).max(initial=0.0) == 0.0
 
 
+def _band_of(harness, X, y, split):
+    n = X.shape[0]
+    npad = (n + 7) // 8 * 8
+    band = np.zeros(9 * npad)
+    Cq, dd, ee = np.zeros(n), np.zeros(n), np.zeros(n)
+    rank, bad = C.c_int(0), C.c_int(0)
+    regs, lam = np.zeros((1, n, n)), np.zeros(1)
+    harness.h_bnd_set_split(*split)
+    try:
+        st = harness.h_system_solve_two_stage(n, dptr(X), dptr(y), dptr(regs), dptr(lam), 1, C.c_double(EPS), dptr(Cq),
+                                              C.byref(rank), dptr(dd), dptr(ee), C.byref(bad), dptr(band))
+    finally:
+        harness.h_bnd_set_split(0, 0, 4)
+    assert st == 0 and bad.value == 0
+    return band, Cq, dd, ee, rank.value
+
+
+@pytest.mark.parametrize("n,p1", [(144, 7), (144, 1), (100, 5), (27, 1), (168, 10)])
+def test_two_stage_split_reduction(harness, n, p1):
+    """k_band + k_band_tail: the panels [0, p1) in one kernel, the trailing matrix (order n - 8 p1, a quarter of the
+    shared memory at n = 144: four CTAs per SM instead of two) in a second one.  With the same warp count and panel
+    register rows the hand-over changes nothing: band, tridiagonal and solution are BIT-IDENTICAL to the unsplit
+    reduction.  The production geometry of the tail (4 warps, 3 register rows per lane) only re-orders sums."""
+    rng = np.random.default_rng(900 + n + p1)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    ev = rng.standard_normal(n) * 10.0 ** rng.uniform(-10, 0, n)
+    X = (Q * ev) @ Q.T
+    X = np.ascontiguousarray(0.5 * (X + X.T))
+    y = rng.standard_normal(n)
+    b0, c0, d0, e0, r0 = _band_of(harness, X, y, (0, 0, 4))
+    nw_full = harness.h_bnd_threads(n) // 32
+    b1, c1, d1, e1, r1 = _band_of(harness, X, y, (p1, nw_full, 4))
+    if harness.h_bnd_threads(n - 8 * p1) // 32 == nw_full:      # (a smaller trailing order may get fewer warps by default)
+        pass
+    assert np.array_equal(b0, b1) and np.array_equal(d0, d1) and np.array_equal(e0, e1) and np.array_equal(c0, c1)
+    b2, c2, d2, e2, r2 = _band_of(harness, X, y, (p1, 4, 3))
+    scale = np.abs(b0).max()
+    assert np.allclose(b2, b0, rtol=0, atol=2e-14 * scale)
+    T0 = np.diag(d0) + np.diag(e0[:-1], 1) + np.diag(e0[:-1], -1)
+    T2 = np.diag(d2) + np.diag(e2[:-1], 1) + np.diag(e2[:-1], -1)
+    assert np.allclose(np.linalg.eigvalsh(T2), np.linalg.eigvalsh(T0), rtol=0, atol=1e-13 * np.abs(d0).max())
+
+
 def test_two_stage_layout(harness):
     """Block layout of vi_band.h: the element map of a block is a bijection, and each of the three fragment access
     patterns touches 16 distinct 8-byte bank pairs per half warp (64-bit accesses) / 8 distinct 16-byte slots per

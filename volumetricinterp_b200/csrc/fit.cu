@@ -58,6 +58,7 @@ struct SysBuf {
   int64_t cap;         // systems held at once (multiple of 32)
   int n, nreg, tapecap, nt, use_gx, ld, nchunk;
   int two_stage;       // tridiagonalisation by band reduction + bulge chasing (vi_band.h, vi_chase.h)
+  int split_p1;        // > 0: stage 1 in two kernels, the panels [0, split_p1) in k_band, the rest in k_band_tail
   int64_t vstride;     // doubles of reflector storage per system
   size_t smem;
   double *V, *d, *e, *g, *tau, *scl, *tcs, *lam, *Csys, *chi2, *chi2p, *Xg, *band;
@@ -74,6 +75,26 @@ constexpr int kChiGates = 1024;    // gates per CTA in k_chi2 (partial sums comb
 bool two_stage_ok(int n) {
   static const bool off = getenv("VI_ONE_STAGE") != nullptr;
   return !off && n <= VI_BND_NMAX && (size_t)vi_bnd_doubles(n) * sizeof(double) <= 227 * 1024;
+}
+
+// Split of stage 1 (k_band + k_band_tail).  The reduction is a chain of panel steps whose latency barely depends on
+// the size of the trailing matrix, while its shared-memory footprint (two CTAs per SM at n = 144) is set by the FIRST
+// panel.  From the panel on at which the trailing matrix fits four CTAs per SM (order 88: 50 KB with 4 warps), a
+// second kernel with that footprint takes over: twice as many systems in flight for the remaining panels.
+constexpr int kTailWarps = 4;
+int band_split(int n) {
+  static const int env = getenv("VI_BAND_SPLIT") ? atoi(getenv("VI_BAND_SPLIT")) : -1;       // 0: off, > 0: that panel
+  if (!two_stage_ok(n) || env == 0) return 0;
+  const int nbk = vi_bnd_nbk(n);
+  if (vi_bnd_nwarp(n) != VI_BND_NW) return 0;                // small orders: one kernel
+  int p1 = 0;
+  if (env > 0) p1 = env;
+  else
+    for (int p = 1; p < nbk - 2; ++p)
+      if ((size_t)vi_bnd_doubles(n - 8 * p, kTailWarps) * sizeof(double) + 1024 <= (227 * 1024) / 4) { p1 = p; break; }
+  if (p1 < 1 || p1 > nbk - 3) return 0;
+  if (vi_bnd_npad(n - 8 * p1) - 8 > 96) return 0;            // the tail's panel QR holds 3 x 32 rows in registers
+  return p1;
 }
 
 int tri_threads(int n) {
@@ -98,6 +119,7 @@ void sysbuf_carve(Bump& b, SysBuf& S, int64_t cap, int n, int nreg, int P) {
   S.use_gx = (smem_x + smem_aux > 227 * 1024) ? 1 : 0;
   S.smem = S.use_gx ? smem_aux : smem_x + smem_aux;
   S.two_stage = two_stage_ok(n) ? 1 : 0;
+  S.split_p1 = band_split(n);
   S.vstride = (int64_t)n * n;
   if (S.two_stage) {
     const int64_t need = (int64_t)vi_bnd_vdoubles(n) + vi_chs_rdoubles(n) + 8;
@@ -370,10 +392,34 @@ k_band(const double* __restrict__ G, const double* __restrict__ y, const double*
   vi_bnd_load(W, G + (int64_t)r * n * n, y + (int64_t)r * n, regs, B.lam + s * (B.nreg > 0 ? B.nreg : 1), B.nreg, arow, wj, bj);
   const bool bad = W.sc[1] != 0.0;
   if (!bad) {
-    vi_bnd_reduce(W, B.V + s * B.vstride);
-    vi_bnd_store_band(W, B.band + s * (int64_t)vi_bnd_band_doubles(n));
+    double* band = B.band + s * (int64_t)vi_bnd_band_doubles(n);
+    if (B.split_p1 > 0) {
+      // first kernel of the split reduction: the trailing matrix goes to the (still unused) tape area of the system
+      vi_bnd_reduce(W, B.V + s * B.vstride, B.split_p1);
+      vi_bnd_store_band(W, band, band + 9 * W.npad, 8 * B.split_p1);
+      vi_bnd_store_trailing(W, B.split_p1, B.tcs + s * (int64_t)B.tapecap * 2);
+    } else {
+      vi_bnd_reduce(W, B.V + s * B.vstride);
+      vi_bnd_store_band(W, band);
+    }
   }
   if (threadIdx.x == 0) { B.scl[s] = W.sc[0]; B.st[s] = bad ? VI_ST_NONFINITE : VI_ST_OK; }
+}
+
+// Second kernel of the split stage 1: the trailing matrix of order n - 8 p1 as an independent band reduction
+// (panel q of it = panel p1 + q of the system), four CTAs of four warps per SM.
+__global__ void __launch_bounds__(kTailWarps * 32, 4)
+k_band_tail(SysBuf B) {
+  extern __shared__ __align__(16) double sm[];
+  const int64_t s = blockIdx.x;
+  if (B.st[s] != VI_ST_OK) return;
+  const int n = B.n, p1 = B.split_p1, np = vi_bnd_npad(n);
+  vi_bnd_ws W;
+  vi_bnd_carve(W, sm, n - 8 * p1, kTailWarps);
+  vi_bnd_load_trailing(W, B.tcs + s * (int64_t)B.tapecap * 2);
+  vi_bnd_reduce<3>(W, B.V + s * B.vstride + vi_bnd_voff(np, p1));
+  double* band = B.band + s * (int64_t)vi_bnd_band_doubles(n);
+  vi_bnd_store_band(W, band + 9 * 8 * p1, band + 9 * np + 8 * p1, W.npad);
 }
 
 // Stage 2, one WARP per system: band -> tridiagonal by bulge chasing, four sweeps in flight (one per 8 lanes).
@@ -1542,6 +1588,11 @@ int run_tridiag(int64_t cnt, const double* G, const double* y, const double* reg
     } else {
       VI_CUDA(cudaFuncSetAttribute(k_band<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
       VI_KERNEL(VI_K_TRIDIAG, s, (k_band<128, 1><<<(unsigned)cnt, nt, smem1, s>>>(G, y, regs, B, dd)));
+    }
+    if (B.split_p1 > 0) {
+      const size_t smemt = (size_t)vi_bnd_doubles(B.n - 8 * B.split_p1, kTailWarps) * sizeof(double);
+      VI_CUDA(cudaFuncSetAttribute(k_band_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemt));
+      VI_KERNEL(VI_K_TRIDIAG, s, k_band_tail<<<(unsigned)cnt, kTailWarps * 32, smemt, s>>>(B));
     }
     const size_t smem2 = (size_t)kChaseWarps * vi_chs_doubles(B.n) * sizeof(double);
     VI_CUDA(cudaFuncSetAttribute(k_chase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));

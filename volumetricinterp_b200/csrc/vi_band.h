@@ -48,9 +48,10 @@ VI_HD int vi_bnd_ldv(int n) { const int np = vi_bnd_npad(n); return (np > 8 ? np
 VI_HD int vi_bnd_nwarp(int n) { const int b = vi_bnd_nbk(n); return b >= 9 ? VI_BND_NW : (b >= 5 ? 4 : (b >= 3 ? 2 : 1)); }
 VI_HD int vi_bnd_threads(int n) { return 32 * vi_bnd_nwarp(n); }
 // shared-memory doubles of one CTA
-VI_HD int vi_bnd_doubles(int n) {
-  const int nt = vi_bnd_threads(n);
-  int part = vi_bnd_nwarp(n) * VI_BND_PART;
+VI_HD int vi_bnd_doubles(int n, int nw = 0) {
+  if (nw <= 0) nw = vi_bnd_nwarp(n);
+  const int nt = 32 * nw;
+  int part = nw * VI_BND_PART;
   if (part < nt) part = nt;
   return vi_bnd_nblk(n) * 64 + 2 * 8 * vi_bnd_ldv(n) + vi_bnd_npad(n) + part + 16;
 }
@@ -72,8 +73,8 @@ struct vi_bnd_ws {
   int n, npad, nbk, ldv, nw;
 };
 
-VI_HD void vi_bnd_carve(vi_bnd_ws& S, double* mem, int n) {
-  S.n = n; S.npad = vi_bnd_npad(n); S.nbk = S.npad >> 3; S.ldv = vi_bnd_ldv(n); S.nw = vi_bnd_nwarp(n);
+VI_HD void vi_bnd_carve(vi_bnd_ws& S, double* mem, int n, int nw = 0) {
+  S.n = n; S.npad = vi_bnd_npad(n); S.nbk = S.npad >> 3; S.ldv = vi_bnd_ldv(n); S.nw = nw > 0 ? nw : vi_bnd_nwarp(n);
   const int nt = 32 * S.nw;
   int part = S.nw * VI_BND_PART;
   if (part < nt) part = nt;
@@ -164,20 +165,22 @@ VI_DEV void vi_bnd_load(const vi_bnd_ws& S, const double* G, const double* y, co
 // local except for the pivot-row elements.  The factorisation (vi_bnd_qr_compute) touches nothing but block column
 // p, tau and block (p + 1, p) -- and S.V for a tall panel -- so for panels of at most 128 rows it can run beside the
 // trailing update of the previous panel; the write-back of V (vi_bnd_qr_store) comes after that update is done with V.
-#define VI_BND_QT 4
-struct vi_bnd_panel { double a[8][VI_BND_QT]; };
+#define VI_BND_QT 4               // register rows per lane (template default): panels of up to 128 rows without a tail
+template <int QT>
+struct vi_bnd_panel { double a[8][QT]; };
 
-VI_DEV void vi_bnd_qr_compute(const vi_bnd_ws& S, int p, vi_bnd_panel& P) {
+template <int QT>
+VI_DEV void vi_bnd_qr_compute(const vi_bnd_ws& S, int p, vi_bnd_panel<QT>& P) {
   const int lane = vi_tid() & 31;
   const int r0 = 8 * (p + 1), npad = S.npad, nbk = S.nbk, ldv = S.ldv;
-  double (&a)[8][VI_BND_QT] = P.a;
-  const int i4 = r0 + 32 * VI_BND_QT + lane;                    // this lane's tail row (tall panels)
+  double (&a)[8][QT] = P.a;
+  const int i4 = r0 + 32 * QT + lane;                    // this lane's tail row (tall panels)
   const bool tail = i4 < npad;
   double* vt = S.V + (i4 - 8);                                  // column c of the tail row at vt[c * ldv]
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-  for (int t = 0; t < VI_BND_QT; ++t) {
+  for (int t = 0; t < QT; ++t) {
     const int i = r0 + lane + 32 * t;
     const bool in = i < npad;
     const double* blk = S.X + vi_bnd_blk(nbk, in ? (i >> 3) : p + 1, p) * 64;
@@ -211,7 +214,7 @@ VI_DEV void vi_bnd_qr_compute(const vi_bnd_ws& S, int p, vi_bnd_panel& P) {
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-      for (int t = 1; t < VI_BND_QT; ++t) acc = fma(a[j][t], a[c][t], acc);
+      for (int t = 1; t < QT; ++t) acc = fma(a[j][t], a[c][t], acc);
       s[c] = fma(x4[j], x4[c], acc);
     }
     const double alpha = vi_shfl(a[j][0], j);
@@ -227,7 +230,7 @@ VI_DEV void vi_bnd_qr_compute(const vi_bnd_ws& S, int p, vi_bnd_panel& P) {
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-    for (int t = 0; t < VI_BND_QT; ++t) {
+    for (int t = 0; t < QT; ++t) {
       const bool below = (t > 0) || (lane > j);
       a[j][t] = below ? a[j][t] * scale : a[j][t];
     }
@@ -244,7 +247,7 @@ VI_DEV void vi_bnd_qr_compute(const vi_bnd_ws& S, int p, vi_bnd_panel& P) {
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-      for (int t = 1; t < VI_BND_QT; ++t) a[c][t] = fma(-w, a[j][t], a[c][t]);
+      for (int t = 1; t < QT; ++t) a[c][t] = fma(-w, a[j][t], a[c][t]);
       if (tail) vt[c * ldv] = fma(-w, v4, x4[c]);
     }
     if (lane == j) a[j][0] = beta;
@@ -260,13 +263,14 @@ VI_DEV void vi_bnd_qr_compute(const vi_bnd_ws& S, int p, vi_bnd_panel& P) {
 }
 
 // V (unit lower trapezoidal, zeros above) -> S.V  (the tail rows of a tall panel are there already)
-VI_DEV void vi_bnd_qr_store(const vi_bnd_ws& S, int p, const vi_bnd_panel& P) {
+template <int QT>
+VI_DEV void vi_bnd_qr_store(const vi_bnd_ws& S, int p, const vi_bnd_panel<QT>& P) {
   const int lane = vi_tid() & 31;
   const int r0 = 8 * (p + 1), npad = S.npad, ldv = S.ldv;
 #if defined(__CUDACC__)
 #pragma unroll
 #endif
-  for (int t = 0; t < VI_BND_QT; ++t) {
+  for (int t = 0; t < QT; ++t) {
     const int i = r0 + lane + 32 * t;
     if (i < npad) {
 #if defined(__CUDACC__)
@@ -525,14 +529,18 @@ VI_DEV void vi_bnd_update_rest(const vi_bnd_ws& S, int p, int wfirst) {
 // S.g = Q1^T y, and Vg (global, may be null) holds T and V of every panel.
 // Warp 0 factors panel p + 1 WHILE the other warps finish the trailing update of panel p (look-ahead): the serial
 // part of a panel step (8 dependent reflectors) is off the other warps' critical path as far as the data allow.
-VI_DEV void vi_bnd_reduce(const vi_bnd_ws& S, double* Vg) {
+// pstop >= 0: only the panels [0, pstop) (the trailing matrix is then fully updated and handed to a second kernel with
+// a smaller footprint, vi_bnd_store_trailing / vi_bnd_load_trailing).  QT: register rows per lane of the panel QR.
+template <int QT = VI_BND_QT>
+VI_DEV void vi_bnd_reduce(const vi_bnd_ws& S, double* Vg, int pstop = -1) {
   const int warp = vi_tid() >> 5;
-  const int npan = S.nbk - 1;
+  int npan = S.nbk - 1;
+  if (pstop >= 0 && pstop < npan) npan = pstop;
   if (npan <= 0) return;
-  // a panel of more than 128 rows keeps its tail rows in S.V while it is factored: no look-ahead for those
-  auto tall = [&](int p) { return S.npad - 8 * (p + 1) > 32 * VI_BND_QT; };
-  vi_bnd_panel P;
-  if (warp == 0) { vi_bnd_qr_compute(S, 0, P); vi_bnd_qr_store(S, 0, P); }
+  // a panel of more than 32 QT rows keeps its tail rows in S.V while it is factored: no look-ahead for those
+  auto tall = [&](int p) { return S.npad - 8 * (p + 1) > 32 * QT; };
+  vi_bnd_panel<QT> P;
+  if (warp == 0) { vi_bnd_qr_compute<QT>(S, 0, P); vi_bnd_qr_store<QT>(S, 0, P); }
   vi_cta_sync();
   for (int p = 0; p < npan; ++p) {
     vi_bnd_symm(S, p);
@@ -546,30 +554,64 @@ VI_DEV void vi_bnd_reduce(const vi_bnd_ws& S, double* Vg) {
     const bool more = p + 1 < npan;
     const bool ahead = more && !tall(p + 1) && S.nw > 1;
     // look-ahead: warp 0 factors panel p + 1 while the others finish the trailing update of panel p
-    if (ahead && warp == 0) vi_bnd_qr_compute(S, p + 1, P);
+    if (ahead && warp == 0) vi_bnd_qr_compute<QT>(S, p + 1, P);
     else vi_bnd_update_rest(S, p, ahead ? 1 : 0);
     vi_cta_sync();
     if (more) {
       if (warp == 0) {
-        if (!ahead) vi_bnd_qr_compute(S, p + 1, P);
-        vi_bnd_qr_store(S, p + 1, P);
+        if (!ahead) vi_bnd_qr_compute<QT>(S, p + 1, P);
+        vi_bnd_qr_store<QT>(S, p + 1, P);
       }
       vi_cta_sync();
     }
   }
 }
 
-// band[j * 9 + d] = X[j + d][j] (d = 0..8, zero beyond the matrix), then g
-VI_DEV void vi_bnd_store_band(const vi_bnd_ws& S, double* band) {
-  const int n = S.n, npad = S.npad, nbk = S.nbk, tid = vi_tid(), nt = vi_nthreads();
-  for (int e = tid; e < 9 * npad; e += nt) {
+// band[j * 9 + d] = X[j + d][j] (d = 0..8, zero beyond the matrix) for the columns j < ncols, g[i] for i < ncols to
+// gout.  The whole system: ncols = npad, gout = band + 9 npad.
+VI_DEV void vi_bnd_store_band(const vi_bnd_ws& S, double* band, double* gout, int ncols) {
+  const int n = S.n, nbk = S.nbk, tid = vi_tid(), nt = vi_nthreads();
+  for (int e = tid; e < 9 * ncols; e += nt) {
     const int j = e / 9, d = e - 9 * j;
     const int i = j + d;
     double x = 0.0;
     if (i < n && j < n) x = S.X[vi_bnd_blk(nbk, i >> 3, j >> 3) * 64 + vi_bnd_el(i & 7, j & 7)];
     band[e] = x;
   }
-  for (int i = tid; i < npad; i += nt) band[9 * npad + i] = S.g[i];
+  for (int i = tid; i < ncols; i += nt) gout[i] = S.g[i];
+}
+VI_DEV void vi_bnd_store_band(const vi_bnd_ws& S, double* band) {
+  vi_bnd_store_band(S, band, band + 9 * S.npad, S.npad);
+}
+
+// Hand-over between the two kernels of a split reduction: after the panels [0, p1) the trailing matrix
+// X[8 p1 .., 8 p1 ..] is an independent problem of order n - 8 p1 (panel p1 + q of the whole = panel q of it: the
+// global reflector storage continues at vi_bnd_voff(npad, p1), the band at column 8 p1).  Blocks keep their element
+// layout; Xt: vi_bnd_trailing_doubles(n, p1) doubles (blocks of the sub-problem in its own packed order, then g).
+VI_HD int vi_bnd_trailing_doubles(int n, int p1) { const int m = vi_bnd_npad(n) - 8 * p1; return vi_bnd_nblk(m) * 64 + m; }
+VI_DEV void vi_bnd_store_trailing(const vi_bnd_ws& S, int p1, double* Xt) {
+  const int nbk = S.nbk, nb2 = nbk - p1, tid = vi_tid(), nt = vi_nthreads();
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  int c = 0;
+  for (int J = p1; J < nbk; ++J)
+    for (int I = J; I < nbk; ++I, ++c) {
+      if (c % nw != warp) continue;
+      const double* src = S.X + vi_bnd_blk(nbk, I, J) * 64;
+      double* dst = Xt + vi_bnd_blk(nb2, I - p1, J - p1) * 64;
+      dst[lane] = src[lane];
+      dst[lane + 32] = src[lane + 32];
+    }
+  double* gt = Xt + vi_bnd_nblk(8 * nb2) * 64;
+  for (int i = tid; i < 8 * nb2; i += nt) gt[i] = S.g[8 * p1 + i];
+}
+// S carved for the trailing order n - 8 p1
+VI_DEV void vi_bnd_load_trailing(const vi_bnd_ws& S, const double* Xt) {
+  const int tid = vi_tid(), nt = vi_nthreads();
+  const int tot = vi_bnd_nblk(S.n) * 64;
+  for (int i = tid; i < tot; i += nt) S.X[i] = Xt[i];
+  for (int i = tid; i < S.npad; i += nt) S.g[i] = Xt[tot + i];
+  if (tid == 0) { S.sc[0] = 1.0; S.sc[1] = 0.0; }
+  vi_cta_sync();
 }
 
 // u <- Q1 u by one warp: block reflectors I - V T V^T in reverse panel order (u: shared memory, n entries valid,
