@@ -70,7 +70,7 @@ SIGNATURES = {
     "vi_profile_read": [_ptr, _ptr, _i32],
     "vi_profile_counters": [C.POINTER(_i64), C.POINTER(_i64)],
 }
-PROFILE_KINDS = ("basis", "normal_eq", "tridiag", "tql", "apply", "chi2", "covariance", "estimate", "misc", "chase")
+PROFILE_KINDS = ("basis", "normal_eq", "tridiag", "tql", "apply", "chi2", "covariance", "estimate", "misc", "chase", "est_gemm")
 
 
 def profile_read():
@@ -134,12 +134,13 @@ def fill_shl_params(maxk, maxl, ct0, st0, kx, ky, nu, kvm, g1, g2):
 _est_ws = {}
 
 
-def estimate_workspace(device, npts, N, Rsel):
-    """Device scratch of vi_estimate_*_many (cached per device, grown on demand)."""
+def estimate_workspace(device, npts, N, Rsel, slot=0):
+    """Device scratch of vi_estimate_*_many (cached per device and slot, grown on demand; callers that keep two
+    tiles in flight on two streams use two slots)."""
     import torch
     need = C.c_int64(0)
     check(lib().vi_estimate_workspace_bytes(int(npts), int(N), int(Rsel), C.byref(need)))
-    key = str(device)
+    key = (str(device), int(slot))
     ws = _est_ws.get(key)
     if ws is None or ws.numel() < need.value:
         _est_ws.pop(key, None)

@@ -428,7 +428,8 @@ extern "C" int vi_estimate_radbasfun(const double* lat, const double* lon, const
   return VI_OK;
 }
 
-// second half, estimate_gemm.cu
+// estimate_gemm.cu: NaN fill of the output on a side stream (first), coefficient slots + GEMM (last)
+int vi_estimate_fill_begin(double* out, int32_t Rsel, int64_t npts, cudaStream_t s);
 int vi_estimate_gemm_launch(const int32_t* count, const int32_t* idx, const double* Arows, double* Cs, const double* C,
                             int32_t Rsel, int32_t N, int64_t npts, double* out, cudaStream_t s);
 
@@ -465,6 +466,7 @@ extern "C" int vi_estimate_sphharmlag_many(const double* lat, const double* lon,
   EstWs w;
   if (int rc = est_carve(workspace, workspace_bytes, npts, N, Rsel, &w)) return rc;
   cudaStream_t s = vi_stream(stream);
+  if (int rc = vi_estimate_fill_begin(out, Rsel, npts, s)) return rc;
   VI_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int32_t), s));
   VI_KERNEL(VI_K_ESTIMATE, s, k_hull_compact<<<(unsigned)((npts + 255) / 256), 256, 0, s>>>(lat, lon, alt, npts, hull_eq, F, w.idx, w.count));
   VI_KERNEL(VI_K_ESTIMATE, s, k_rows_shl_idx<<<(unsigned)((npts + kThreads - 1) / kThreads), kThreads, 0, s>>>(lat, lon, alt, w.idx, w.count, *params, KP, w.Arows));
@@ -482,6 +484,7 @@ extern "C" int vi_estimate_radbasfun_many(const double* lat, const double* lon, 
   EstWs w;
   if (int rc = est_carve(workspace, workspace_bytes, npts, N, Rsel, &w)) return rc;
   cudaStream_t s = vi_stream(stream);
+  if (int rc = vi_estimate_fill_begin(out, Rsel, npts, s)) return rc;
   VI_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int32_t), s));
   VI_KERNEL(VI_K_ESTIMATE, s, k_hull_compact<<<(unsigned)((npts + 255) / 256), 256, 0, s>>>(lat, lon, alt, npts, hull_eq, F, w.idx, w.count));
   VI_KERNEL(VI_K_ESTIMATE, s, k_rows_rbf_idx<<<(unsigned)((npts + kThreads - 1) / kThreads), kThreads, 0, s>>>(lat, lon, alt, w.idx, w.count, centers, N, eps, KP, w.Arows));

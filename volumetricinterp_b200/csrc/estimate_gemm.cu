@@ -7,12 +7,14 @@
 //   k_rows_*_idx     (basis.cu)  one thread per compacted point: its basis row -> Arows[j][slot(n)] (full occupancy:
 //                                the special-function work no longer sits in front of the MMAs of a 4-warp CTA)
 //   k_coef_slots     (here)      C -> slot order, zero padded to a multiple of 16 columns
-//   k_fill_nan       (here)      the whole output tile = NaN (the GEMM overwrites the in-hull points)
+//   k_fill_nan       (here)      the whole output tile = NaN (the GEMM overwrites the in-hull points); on a side
+//                                stream, beside the two kernels above
 //   k_est_gemm       (here)      128 compacted points x 32-record chunks per CTA, 8 warps, mma.sync.m16n8k16.f64
 //                                (SASS DMMA.8x8x4), operands staged by 16-byte cp.async, double buffered
 // Both operands are stored with the k index permuted inside each group of 16 (k -> 4 (k % 4) + k / 4) and a row
 // stride = 2 (mod 16) doubles, so that every fragment is two conflict-free 128-bit shared loads.
 #include "common.cuh"
+#include <mutex>
 
 namespace {
 
@@ -137,7 +139,40 @@ k_est_gemm(const double* __restrict__ Arows, const int32_t* __restrict__ idx, co
 
 inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
 
+// One side stream per device for the NaN fill of the output tile: pure HBM writes that run beside the hull test and
+// the basis rows (FP64 ALU work) instead of in front of the GEMM.
+struct Side { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+Side g_side[64];
+std::mutex g_side_mu;
+int side_for_device(Side** out) {
+  int dev = 0;
+  VI_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) { vi_set_error("device index %d out of range", dev); return VI_EINVAL; }
+  std::lock_guard<std::mutex> lk(g_side_mu);
+  Side& sd = g_side[dev];
+  if (!sd.stream) {
+    VI_CUDA(cudaStreamCreateWithFlags(&sd.stream, cudaStreamNonBlocking));
+    VI_CUDA(cudaEventCreateWithFlags(&sd.fork, cudaEventDisableTiming));
+    VI_CUDA(cudaEventCreateWithFlags(&sd.join, cudaEventDisableTiming));
+  }
+  *out = &sd;
+  return VI_OK;
+}
+
 }  // namespace
+
+// first half of vi_estimate_*_many (called before the hull test is launched): out <- NaN on the side stream
+int vi_estimate_fill_begin(double* out, int32_t Rsel, int64_t npts, cudaStream_t s) {
+  Side* sd = nullptr;
+  if (int rc = side_for_device(&sd)) return rc;
+  VI_CUDA(cudaEventRecord(sd->fork, s));                 // out may still be read by earlier work on s
+  VI_CUDA(cudaStreamWaitEvent(sd->stream, sd->fork, 0));
+  const int64_t pairs = ((int64_t)Rsel * npts + 1) / 2;
+  const unsigned grid = blocks(pairs, 256) < 148u * 16u ? blocks(pairs, 256) : 148u * 16u;
+  VI_KERNEL(VI_K_ESTIMATE, sd->stream, k_fill_nan<<<grid, 256, 0, sd->stream>>>(out, (int64_t)Rsel * npts));
+  VI_CUDA(cudaEventRecord(sd->join, sd->stream));
+  return VI_OK;
+}
 
 // workspace layout (shared with basis.cu): [count: 256 B][idx: int32 x npts][Arows: npts x KP][Cs: Rpad x KP]
 extern "C" int vi_estimate_workspace_bytes(int64_t npts, int32_t N, int32_t Rsel, int64_t* bytes) {
@@ -147,7 +182,7 @@ extern "C" int vi_estimate_workspace_bytes(int64_t npts, int32_t N, int32_t Rsel
   return VI_OK;
 }
 
-// second half of vi_estimate_*_many: idx / count / Arows already filled by basis.cu
+// last part of vi_estimate_*_many: idx / count / Arows already filled by basis.cu, vi_estimate_fill_begin called
 int vi_estimate_gemm_launch(const int32_t* count, const int32_t* idx, const double* Arows, double* Cs, const double* C,
                             int32_t Rsel, int32_t N, int64_t npts, double* out, cudaStream_t s) {
   const int KP = (N + 15) / 16 * 16, Rpad = (Rsel + kRC - 1) / kRC * kRC;
@@ -156,8 +191,12 @@ int vi_estimate_gemm_launch(const int32_t* count, const int32_t* idx, const doub
   const size_t smem = ((size_t)kTileP * LD + 2 * (size_t)kRC * LD) * sizeof(double);
   if (smem > 227 * 1024 - 1024) { vi_set_error("nbasis %d too large for the Estimate GEMM tile", N); return VI_EUNSUPPORTED; }
   VI_KERNEL(VI_K_ESTIMATE, s, k_coef_slots<<<blocks((int64_t)Rpad * KP, 256), 256, 0, s>>>(C, Rsel, N, KP, Rpad, Cs));
-  VI_KERNEL(VI_K_ESTIMATE, s, k_fill_nan<<<blocks(((int64_t)Rsel * npts + 1) / 2, 256) < 148 * 16 ? blocks(((int64_t)Rsel * npts + 1) / 2, 256) : 148 * 16, 256, 0, s>>>(out, (int64_t)Rsel * npts));
+  {
+    Side* sd = nullptr;
+    if (int rc = side_for_device(&sd)) return rc;
+    VI_CUDA(cudaStreamWaitEvent(s, sd->join, 0));        // the NaN fill of vi_estimate_fill_begin is complete
+  }
   VI_CUDA(cudaFuncSetAttribute(k_est_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  VI_KERNEL(VI_K_ESTIMATE, s, k_est_gemm<<<blocks(npts, kTileP), kGemmThreads, smem, s>>>(Arows, idx, count, Cs, Rsel, Rpad, KP, LD, npts, out));
+  VI_KERNEL(VI_K_EST_GEMM, s, k_est_gemm<<<blocks(npts, kTileP), kGemmThreads, smem, s>>>(Arows, idx, count, Cs, Rsel, Rpad, KP, LD, npts, out));
   return VI_OK;
 }

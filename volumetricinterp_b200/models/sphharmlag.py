@@ -91,7 +91,7 @@ class Model(object):
             out.data_ptr() if out is not None else None, out_t.data_ptr() if out_t is not None else None, s))
         return out
 
-    def estimate_device(self, lat, lon, alt, Cf, hull_eq, out, stream=None):
+    def estimate_device(self, lat, lon, alt, Cf, hull_eq, out, stream=None, ws_slot=0):
         """out[r, p] = basis(p) . Cf[r], NaN outside the hull (estimate.py:113-121).  With 16 or more records the
         in-hull points are compacted and the contraction runs as an FP64 tensor-core GEMM (vi_estimate_*_many)."""
         import torch
@@ -99,7 +99,7 @@ class Model(object):
         F = 0 if hull_eq is None else hull_eq.shape[0]
         npts, R = lat.numel(), Cf.shape[0]
         if R >= 16 and npts > 0 and self.nbasis <= 144:      # the GEMM tile holds K = nbasis columns in shared memory
-            ws = _native.estimate_workspace(lat.device, npts, self.nbasis, R)
+            ws = _native.estimate_workspace(lat.device, npts, self.nbasis, R, ws_slot)
             _native.check(_native.lib().vi_estimate_sphharmlag_many(
                 lat.data_ptr(), lon.data_ptr(), alt.data_ptr(), npts, C.byref(self.params()),
                 Cf.data_ptr(), R, hull_eq.data_ptr() if F else None, F, out.data_ptr(), ws.data_ptr(), ws.numel(), s))
