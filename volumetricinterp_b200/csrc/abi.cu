@@ -14,6 +14,20 @@ void vi_set_error(const char* fmt, ...) {
 extern "C" const char* vi_last_error(void) { return g_err; }
 extern "C" const char* vi_version(void) { return "volinterp_b200 0.1.0 (sm_100a)"; }
 
+// SMs of the current device (per device ordinal: a process may drive several, possibly different, GPUs)
+int vi_sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = (dev >= 0 && dev < 64) ? dev : 0;
+  if (cache[slot] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[slot] = n;
+  }
+  return cache[slot];
+}
+
 // ---- launch accounting ---------------------------------------------------------------------
 #include <vector>
 namespace {

@@ -42,6 +42,8 @@ static inline int64_t vi_align_up(int64_t x, int64_t a) { return (x + a - 1) / a
 // launch counter of `kind` is always incremented; when vi_profile_enable(1) was called, the launch
 // is bracketed by CUDA events on the launching stream and vi_profile_read() reports the summed
 // device time per kind.  Not thread safe (one profiling client at a time).
+int vi_sm_count();      // abi.cu
+
 enum ViKind { VI_K_BASIS = 0, VI_K_NORMAL_EQ, VI_K_TRIDIAG, VI_K_TQL, VI_K_APPLY, VI_K_CHI2, VI_K_COV, VI_K_ESTIMATE, VI_K_MISC, VI_K_CHASE, VI_K_EST_GEMM, VI_K_COUNT };
 void vi_prof_count_rotations(int64_t rotations, int64_t systems);
 void vi_prof_launch_begin(int kind, cudaStream_t s);

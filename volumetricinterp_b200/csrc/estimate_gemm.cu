@@ -9,7 +9,7 @@
 //   k_coef_slots     (here)      C -> slot order, zero padded to a multiple of 16 columns
 //   k_fill_nan       (here)      the whole output tile = NaN (the GEMM overwrites the in-hull points); on a side
 //                                stream, beside the two kernels above
-//   k_est_gemm       (here)      128 compacted points x 32-record chunks per CTA, 8 warps, mma.sync.m16n8k16.f64
+//   k_est_gemm       (here)      persistent CTAs over (128 compacted points x 32-record chunk) units, 8 warps, mma.sync.m16n8k16.f64
 //                                (SASS DMMA.8x8x4), operands staged by 16-byte cp.async, double buffered
 // Both operands are stored with the k index permuted inside each group of 16 (k -> 4 (k % 4) + k / 4) and a row
 // stride = 2 (mod 16) doubles, so that every fragment is two conflict-free 128-bit shared loads.
@@ -58,7 +58,10 @@ __global__ void k_fill_nan(double* __restrict__ out, int64_t n) {
   }
 }
 
-// out[r][idx[j]] = Arows[j] . Cs[r] for the compacted points j of this CTA's tile, all records
+// out[r][idx[j]] = Arows[j] . Cs[r].  Persistent CTAs (one per SM: the A tile takes 150 KB of shared memory): the work
+// units (128-point tile, 32-record chunk), tile-major, are split evenly into one contiguous range per CTA, so the
+// number of in-hull points -- known only on the device -- never leaves a partial last wave, and a CTA reloads its
+// A tile only when its range crosses into the next tile.
 __global__ void __launch_bounds__(kGemmThreads)
 k_est_gemm(const double* __restrict__ Arows, const int32_t* __restrict__ idx, const int32_t* __restrict__ count,
            const double* __restrict__ Cs, int Rsel, int Rpad, int KP, int LD, int64_t npts, double* __restrict__ out) {
@@ -67,19 +70,13 @@ k_est_gemm(const double* __restrict__ Arows, const int32_t* __restrict__ idx, co
   double* sC = smem + (size_t)kTileP * LD;         // 2 x kRC x LD
   __shared__ int32_t s_idx[kTileP];
   const int nin = *count;
-  const int64_t j0 = (int64_t)blockIdx.x * kTileP;
-  if (j0 >= nin) return;
+  const int nchunk = Rpad / kRC;
+  const int64_t total = (int64_t)((nin + kTileP - 1) / kTileP) * nchunk;
+  const int64_t u0 = total * blockIdx.x / gridDim.x, u1 = total * (blockIdx.x + 1) / gridDim.x;
+  if (u0 >= u1) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int pg = warp & 3, rh = warp >> 2;         // 32-point group, 16-record half of the chunk
-  const int rows = (nin - j0 < kTileP) ? (int)(nin - j0) : kTileP;
-  if (tid < kTileP) s_idx[tid] = (tid < rows) ? idx[j0 + tid] : -1;
   const int kp2 = KP >> 1;                         // 16-byte pieces per row
-  for (int e = tid; e < kTileP * kp2; e += kGemmThreads) {
-    const int rr = e / kp2, q = e - rr * kp2;
-    double* dst = sA + (size_t)rr * LD + 2 * q;
-    if (rr < rows) cpa16(dst, Arows + (j0 + rr) * (int64_t)KP + 2 * q);
-    else { dst[0] = 0.0; dst[1] = 0.0; }
-  }
   auto load_chunk = [&](int chunk, int buf) {
     double* dst = sC + (size_t)buf * kRC * LD;
     const int r0 = chunk * kRC;
@@ -89,12 +86,27 @@ k_est_gemm(const double* __restrict__ Arows, const int32_t* __restrict__ idx, co
     }
     cpa_commit();
   };
-  const int nchunk = Rpad / kRC;
-  load_chunk(0, 0);                                // (this group also carries the A tile)
-  for (int ch = 0; ch < nchunk; ++ch) {
-    if (ch + 1 < nchunk) { load_chunk(ch + 1, (ch + 1) & 1); cpa_wait<1>(); } else cpa_wait<0>();
+  int cur_tile = -1;
+  load_chunk((int)(u0 % nchunk), 0);
+  for (int64_t u = u0; u < u1; ++u) {
+    const int tile = (int)(u / nchunk), ch = (int)(u - (int64_t)tile * nchunk);
+    const int i = (int)(u - u0);
+    if (tile != cur_tile) {                        // (every warp is past the previous tile: barrier at the loop's end)
+      const int64_t j0 = (int64_t)tile * kTileP;
+      const int rows = (nin - j0 < kTileP) ? (int)(nin - j0) : kTileP;
+      if (tid < kTileP) s_idx[tid] = (tid < rows) ? idx[j0 + tid] : -1;
+      for (int e = tid; e < kTileP * kp2; e += kGemmThreads) {
+        const int rr = e / kp2, q = e - rr * kp2;
+        double* dst = sA + (size_t)rr * LD + 2 * q;
+        if (rr < rows) cpa16(dst, Arows + (j0 + rr) * (int64_t)KP + 2 * q);
+        else { dst[0] = 0.0; dst[1] = 0.0; }
+      }
+      cpa_commit();
+      cur_tile = tile;
+    }
+    if (u + 1 < u1) { load_chunk((int)((u + 1) % nchunk), (i + 1) & 1); cpa_wait<1>(); } else cpa_wait<0>();
     __syncthreads();
-    const double* Cb = sC + (size_t)(ch & 1) * kRC * LD;
+    const double* Cb = sC + (size_t)(i & 1) * kRC * LD;
     double acc[2][2][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -168,7 +180,8 @@ int vi_estimate_fill_begin(double* out, int32_t Rsel, int64_t npts, cudaStream_t
   VI_CUDA(cudaEventRecord(sd->fork, s));                 // out may still be read by earlier work on s
   VI_CUDA(cudaStreamWaitEvent(sd->stream, sd->fork, 0));
   const int64_t pairs = ((int64_t)Rsel * npts + 1) / 2;
-  const unsigned grid = blocks(pairs, 256) < 148u * 16u ? blocks(pairs, 256) : 148u * 16u;
+  const unsigned cap = 2u * (unsigned)vi_sm_count();   // two CTAs per SM saturate the HBM writes and leave the
+  const unsigned grid = blocks(pairs, 256) < cap ? blocks(pairs, 256) : cap;      // thread slots to the basis rows
   VI_KERNEL(VI_K_ESTIMATE, sd->stream, k_fill_nan<<<grid, 256, 0, sd->stream>>>(out, (int64_t)Rsel * npts));
   VI_CUDA(cudaEventRecord(sd->join, sd->stream));
   return VI_OK;
@@ -197,6 +210,6 @@ int vi_estimate_gemm_launch(const int32_t* count, const int32_t* idx, const doub
     VI_CUDA(cudaStreamWaitEvent(s, sd->join, 0));        // the NaN fill of vi_estimate_fill_begin is complete
   }
   VI_CUDA(cudaFuncSetAttribute(k_est_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  VI_KERNEL(VI_K_EST_GEMM, s, k_est_gemm<<<blocks(npts, kTileP), kGemmThreads, smem, s>>>(Arows, idx, count, Cs, Rsel, Rpad, KP, LD, npts, out));
+  VI_KERNEL(VI_K_EST_GEMM, s, k_est_gemm<<<(unsigned)vi_sm_count(), kGemmThreads, smem, s>>>(Arows, idx, count, Cs, Rsel, Rpad, KP, LD, npts, out));
   return VI_OK;
 }

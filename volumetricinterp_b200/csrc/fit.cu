@@ -223,18 +223,7 @@ int64_t per_system_bytes(int n, int nreg, int P) {
   return (b.off + 32 * 256) / 32;
 }
 
-int sm_count() {
-  static int cache[64] = {0};          // per device ordinal: a process may drive several (different) GPUs
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const int slot = (dev >= 0 && dev < 64) ? dev : 0;
-  if (cache[slot] == 0) {
-    int n = 0;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    cache[slot] = n;
-  }
-  return cache[slot];
-}
+int sm_count() { return vi_sm_count(); }
 
 // Scratch budget for the in-flight eigen-systems when the caller does not size the batch itself: half of the
 // device memory that is free right now, at most 32 GiB (VI_SCRATCH_GIB overrides the ceiling).
