@@ -33,12 +33,17 @@ for _ in range(3):
     model.estimate_device(la, lo, al, Cm, eq, out)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+lib.vi_profile_reset()
+lib.vi_profile_enable(1)
 e0.record()
 for _ in range(iters):
     model.estimate_device(la, lo, al, Cm, eq, out)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
+kms, kn = _native.profile_read()
+lib.vi_profile_enable(0)
+print({k: round(v / iters, 4) for k, v in kms.items() if kn[k]}, "ms per tile by kind")
 fin = float(torch.isfinite(out[0]).double().mean().item())
 print(f"records {R} tile {tile} inside {fin:.3f}: {ms:.3f} ms per tile, {tile * R / ms / 1e6:.1f} G(point,record)/s, "
       f"{2 * model.nbasis * tile * R * fin / ms / 1e9:.2f} TFLOP/s, {tile * R * 8 / ms / 1e6:.0f} GB/s written")

@@ -297,33 +297,36 @@ k_hull_compact(const double* __restrict__ lat, const double* __restrict__ lon, c
   if (in) idx[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)p;
 }
 
-// basis row of compacted point j in slot order (k -> 4 (k % 4) + k / 4 inside each group of 16), zero padded to KP
+// basis row of compacted point j, stored TRANSPOSED: value n of point j at Arows[slot(n) * ldj + j] (slot order:
+// k -> 4 (k % 4) + k / 4 inside each group of 16; zero padded to KP).  Consecutive threads write consecutive addresses:
+// with the point-major layout every store of a warp touched 32 sectors, and the kernel could not share the memory
+// system with the NaN fill that runs beside it.
 __global__ void __launch_bounds__(kThreads)
 k_rows_shl_idx(const double* __restrict__ lat, const double* __restrict__ lon, const double* __restrict__ alt,
                const int32_t* __restrict__ idx, const int32_t* __restrict__ count, const __grid_constant__ vi_shl_params P,
-               int KP, double* __restrict__ Arows) {
+               int KP, int64_t ldj, double* __restrict__ Arows) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= *count) return;
   const int N = P.maxk * P.maxl * P.maxl;
   const int32_t p = idx[j];
-  double* row = Arows + j * (int64_t)KP;
-  for (int k = N; k < KP; ++k) row[k_slot16(k)] = 0.0;
-  vi_shl_row(P, lat[p], lon[p], alt[p], [&](int n, double v) { row[k_slot16(n)] = v; });
+  double* col = Arows + j;
+  for (int k = N; k < KP; ++k) col[k_slot16(k) * ldj] = 0.0;
+  vi_shl_row(P, lat[p], lon[p], alt[p], [&](int n, double v) { col[k_slot16(n) * ldj] = v; });
 }
 
 __global__ void __launch_bounds__(kThreads)
 k_rows_rbf_idx(const double* __restrict__ lat, const double* __restrict__ lon, const double* __restrict__ alt,
                const int32_t* __restrict__ idx, const int32_t* __restrict__ count, const double* __restrict__ centers,
-               int N, double eps, int KP, double* __restrict__ Arows) {
+               int N, double eps, int KP, int64_t ldj, double* __restrict__ Arows) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= *count) return;
   const int32_t p = idx[j];
   double x, y, z;
   vi_geodetic2ecef(lat[p], lon[p], alt[p], &x, &y, &z);
-  double* row = Arows + j * (int64_t)KP;
-  for (int k = N; k < KP; ++k) row[k_slot16(k)] = 0.0;
+  double* col = Arows + j;
+  for (int k = N; k < KP; ++k) col[k_slot16(k) * ldj] = 0.0;
   for (int n = 0; n < N; ++n)
-    row[k_slot16(n)] = vi_rbf_value(x, y, z, centers[3 * n], centers[3 * n + 1], centers[3 * n + 2], eps);
+    col[k_slot16(n) * ldj] = vi_rbf_value(x, y, z, centers[3 * n], centers[3 * n + 1], centers[3 * n + 2], eps);
 }
 
 int check_shl(const vi_shl_params* P) {
@@ -447,7 +450,7 @@ int est_carve(void* workspace, int64_t workspace_bytes, int64_t npts, int32_t N,
   char* b = reinterpret_cast<char*>(workspace);
   w->count = reinterpret_cast<int32_t*>(b); b += 256;
   w->idx = reinterpret_cast<int32_t*>(b); b += vi_align_up(npts * 4, 256);
-  w->Arows = reinterpret_cast<double*>(b); b += npts * KP * 8;
+  w->Arows = reinterpret_cast<double*>(b); b += (npts + 2) * KP * 8;      // KP x ldj, ldj = npts rounded up to even
   w->Cs = reinterpret_cast<double*>(b);
   return VI_OK;
 }
@@ -469,7 +472,7 @@ extern "C" int vi_estimate_sphharmlag_many(const double* lat, const double* lon,
   if (int rc = vi_estimate_fill_begin(out, Rsel, npts, s)) return rc;
   VI_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int32_t), s));
   VI_KERNEL(VI_K_ESTIMATE, s, k_hull_compact<<<(unsigned)((npts + 255) / 256), 256, 0, s>>>(lat, lon, alt, npts, hull_eq, F, w.idx, w.count));
-  VI_KERNEL(VI_K_ESTIMATE, s, k_rows_shl_idx<<<(unsigned)((npts + kThreads - 1) / kThreads), kThreads, 0, s>>>(lat, lon, alt, w.idx, w.count, *params, KP, w.Arows));
+  VI_KERNEL(VI_K_ESTIMATE, s, k_rows_shl_idx<<<(unsigned)((npts + kThreads - 1) / kThreads), kThreads, 0, s>>>(lat, lon, alt, w.idx, w.count, *params, KP, (npts + 1) & ~(int64_t)1, w.Arows));
   return vi_estimate_gemm_launch(w.count, w.idx, w.Arows, w.Cs, C, Rsel, N, npts, out, s);
 }
 
@@ -487,7 +490,7 @@ extern "C" int vi_estimate_radbasfun_many(const double* lat, const double* lon, 
   if (int rc = vi_estimate_fill_begin(out, Rsel, npts, s)) return rc;
   VI_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int32_t), s));
   VI_KERNEL(VI_K_ESTIMATE, s, k_hull_compact<<<(unsigned)((npts + 255) / 256), 256, 0, s>>>(lat, lon, alt, npts, hull_eq, F, w.idx, w.count));
-  VI_KERNEL(VI_K_ESTIMATE, s, k_rows_rbf_idx<<<(unsigned)((npts + kThreads - 1) / kThreads), kThreads, 0, s>>>(lat, lon, alt, w.idx, w.count, centers, N, eps, KP, w.Arows));
+  VI_KERNEL(VI_K_ESTIMATE, s, k_rows_rbf_idx<<<(unsigned)((npts + kThreads - 1) / kThreads), kThreads, 0, s>>>(lat, lon, alt, w.idx, w.count, centers, N, eps, KP, (npts + 1) & ~(int64_t)1, w.Arows));
   return vi_estimate_gemm_launch(w.count, w.idx, w.Arows, w.Cs, C, Rsel, N, npts, out, s);
 }
 

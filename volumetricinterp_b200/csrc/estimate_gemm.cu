@@ -4,7 +4,7 @@
 //
 // Pipeline of vi_estimate_*_many (host side at the bottom):
 //   k_hull_compact   (basis.cu)  in-hull test per point + compaction: idx[0 .. count) = the points to evaluate
-//   k_rows_*_idx     (basis.cu)  one thread per compacted point: its basis row -> Arows[j][slot(n)] (full occupancy:
+//   k_rows_*_idx     (basis.cu)  one thread per compacted point: its basis row -> Arows[slot(n)][j] (full occupancy:
 //                                the special-function work no longer sits in front of the MMAs of a 4-warp CTA)
 //   k_coef_slots     (here)      C -> slot order, zero padded to a multiple of 16 columns
 //   k_fill_nan       (here)      the whole output tile = NaN (the GEMM overwrites the in-hull points); on a side
@@ -15,6 +15,7 @@
 // stride = 2 (mod 16) doubles, so that every fragment is two conflict-free 128-bit shared loads.
 #include "common.cuh"
 #include <mutex>
+#include <stdlib.h>
 
 namespace {
 
@@ -95,11 +96,17 @@ k_est_gemm(const double* __restrict__ Arows, const int32_t* __restrict__ idx, co
       const int64_t j0 = (int64_t)tile * kTileP;
       const int rows = (nin - j0 < kTileP) ? (int)(nin - j0) : kTileP;
       if (tid < kTileP) s_idx[tid] = (tid < rows) ? idx[j0 + tid] : -1;
-      for (int e = tid; e < kTileP * kp2; e += kGemmThreads) {
-        const int rr = e / kp2, q = e - rr * kp2;
-        double* dst = sA + (size_t)rr * LD + 2 * q;
-        if (rr < rows) cpa16(dst, Arows + (j0 + rr) * (int64_t)KP + 2 * q);
-        else { dst[0] = 0.0; dst[1] = 0.0; }
+      // A tile: Arows is basis-major (k-slot x compacted point); two points per 16-byte load, transposed into the
+      // point-major rows the fragments read.  Columns past `rows` hold whatever the workspace holds: their products
+      // only reach accumulator rows that are never stored (s_idx = -1).
+      const int64_t ldj = (npts + 1) & ~(int64_t)1;
+#pragma unroll 4
+      for (int e = tid; e < KP * (kTileP / 2); e += kGemmThreads) {
+        const int k = e / (kTileP / 2), pp = e - k * (kTileP / 2);
+        double2 v = make_double2(0.0, 0.0);
+        if (j0 + 2 * pp + 1 < ldj) v = __ldg(reinterpret_cast<const double2*>(Arows + (int64_t)k * ldj + j0) + pp);
+        sA[(size_t)(2 * pp) * LD + k] = (2 * pp < rows) ? v.x : 0.0;
+        sA[(size_t)(2 * pp + 1) * LD + k] = (2 * pp + 1 < rows) ? v.y : 0.0;
       }
       cpa_commit();
       cur_tile = tile;
@@ -180,18 +187,20 @@ int vi_estimate_fill_begin(double* out, int32_t Rsel, int64_t npts, cudaStream_t
   VI_CUDA(cudaEventRecord(sd->fork, s));                 // out may still be read by earlier work on s
   VI_CUDA(cudaStreamWaitEvent(sd->stream, sd->fork, 0));
   const int64_t pairs = ((int64_t)Rsel * npts + 1) / 2;
-  const unsigned cap = 2u * (unsigned)vi_sm_count();   // two CTAs per SM saturate the HBM writes and leave the
-  const unsigned grid = blocks(pairs, 256) < cap ? blocks(pairs, 256) : cap;      // thread slots to the basis rows
+  // a few CTAs per SM: enough stores in flight for the HBM writes, most thread slots left to the basis rows
+  static const int per_sm = getenv("VI_FILL_CTAS") ? atoi(getenv("VI_FILL_CTAS")) : 4;
+  const unsigned cap = (unsigned)(per_sm > 0 ? per_sm : 4) * (unsigned)vi_sm_count();
+  const unsigned grid = blocks(pairs, 256) < cap ? blocks(pairs, 256) : cap;
   VI_KERNEL(VI_K_ESTIMATE, sd->stream, k_fill_nan<<<grid, 256, 0, sd->stream>>>(out, (int64_t)Rsel * npts));
   VI_CUDA(cudaEventRecord(sd->join, sd->stream));
   return VI_OK;
 }
 
-// workspace layout (shared with basis.cu): [count: 256 B][idx: int32 x npts][Arows: npts x KP][Cs: Rpad x KP]
+// workspace layout (shared with basis.cu): [count: 256 B][idx: int32 x npts][Arows: KP x ldj, ldj = even(npts)][Cs: Rpad x KP]
 extern "C" int vi_estimate_workspace_bytes(int64_t npts, int32_t N, int32_t Rsel, int64_t* bytes) {
   VI_REQUIRE(bytes != nullptr && npts >= 0 && N >= 1 && Rsel >= 1, "bad arguments");
   const int64_t KP = (N + 15) / 16 * 16, Rpad = (Rsel + kRC - 1) / kRC * kRC;
-  *bytes = 256 + vi_align_up(npts * 4, 256) + npts * KP * 8 + Rpad * KP * 8 + 256;
+  *bytes = 256 + vi_align_up(npts * 4, 256) + (npts + 2) * KP * 8 + Rpad * KP * 8 + 256;
   return VI_OK;
 }
 
