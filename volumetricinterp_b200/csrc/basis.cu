@@ -305,13 +305,17 @@ __global__ void __launch_bounds__(kThreads)
 k_rows_shl_idx(const double* __restrict__ lat, const double* __restrict__ lon, const double* __restrict__ alt,
                const int32_t* __restrict__ idx, const int32_t* __restrict__ count, const __grid_constant__ vi_shl_params P,
                int KP, int64_t ldj, double* __restrict__ Arows) {
+  // one thread per (compacted point, degree l = blockIdx.y): the in-hull points alone are too few threads to hide the
+  // latency of the Legendre series (490 per SM on a 2^17-point tile); the degrees are independent
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= *count) return;
   const int N = P.maxk * P.maxl * P.maxl;
   const int32_t p = idx[j];
+  const int l = blockIdx.y;
   double* col = Arows + j;
-  for (int k = N; k < KP; ++k) col[k_slot16(k) * ldj] = 0.0;
-  vi_shl_row(P, lat[p], lon[p], alt[p], [&](int n, double v) { col[k_slot16(n) * ldj] = v; });
+  if (l == 0)
+    for (int k = N; k < KP; ++k) col[k_slot16(k) * ldj] = 0.0;
+  vi_shl_row(P, lat[p], lon[p], alt[p], [&](int n, double v) { col[k_slot16(n) * ldj] = v; }, l, l + 1);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -472,7 +476,7 @@ extern "C" int vi_estimate_sphharmlag_many(const double* lat, const double* lon,
   if (int rc = vi_estimate_fill_begin(out, Rsel, npts, s)) return rc;
   VI_CUDA(cudaMemsetAsync(w.count, 0, sizeof(int32_t), s));
   VI_KERNEL(VI_K_ESTIMATE, s, k_hull_compact<<<(unsigned)((npts + 255) / 256), 256, 0, s>>>(lat, lon, alt, npts, hull_eq, F, w.idx, w.count));
-  VI_KERNEL(VI_K_ESTIMATE, s, k_rows_shl_idx<<<(unsigned)((npts + kThreads - 1) / kThreads), kThreads, 0, s>>>(lat, lon, alt, w.idx, w.count, *params, KP, (npts + 1) & ~(int64_t)1, w.Arows));
+  VI_KERNEL(VI_K_ESTIMATE, s, k_rows_shl_idx<<<dim3((unsigned)((npts + kThreads - 1) / kThreads), (unsigned)params->maxl), kThreads, 0, s>>>(lat, lon, alt, w.idx, w.count, *params, KP, (npts + 1) & ~(int64_t)1, w.Arows));
   return vi_estimate_gemm_launch(w.count, w.idx, w.Arows, w.Cs, C, Rsel, N, npts, out, s);
 }
 

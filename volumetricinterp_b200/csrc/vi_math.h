@@ -130,8 +130,10 @@ VI_HD double vi_lpmv_pos(double v, int mx, double x) {
 // One row of the sphharmlag design matrix (sphharmlag.py:138-141):
 //   A[n] = exp(-z/2) * L_k(z) * (K_{v|m|} * cos|sin(|m| phi)) * P_v^m(cos theta)
 // n = k*maxl^2 + l*(l+1) + m.  `emit(n, value)` receives every basis value.
+// [l0, l1): the degrees to emit (default all) -- kernels that give every (point, degree) pair its own thread call it
+// with one degree; the values do not depend on the split.
 template <class Emit>
-VI_HD void vi_shl_row(const vi_shl_params& P, double lat, double lon, double alt, Emit emit) {
+VI_HD void vi_shl_row(const vi_shl_params& P, double lat, double lon, double alt, Emit emit, int l0 = 0, int l1 = -1) {
   double z, theta, phi;
   vi_shl_coords(P, lat, lon, alt, &z, &theta, &phi);
   double lag[VI_MAXK_MAX];
@@ -139,7 +141,8 @@ VI_HD void vi_shl_row(const vi_shl_params& P, double lat, double lon, double alt
   double ez = exp(-0.5 * z);
   double x = cos(theta);
   const int L2 = P.maxl * P.maxl;
-  for (int l = 0; l < P.maxl; ++l) {
+  if (l1 < 0 || l1 > P.maxl) l1 = P.maxl;
+  for (int l = l0; l < l1; ++l) {
     double v = P.nu[l];
     for (int am = 0; am <= l; ++am) {
       double ppos = vi_lpmv_pos(v, am, x);
