@@ -272,7 +272,8 @@ int h_trp_octet_of(int n, int warp, int slot, int a) {
   return vi_trp_octet_of(W, warp, slot, a);
 }
 
-static int g_split_p1 = 0, g_split_nw = 0, g_split_qt = 4;
+static int g_split_p1 = 0, g_split_nw = 0, g_split_qt = 4, g_big = 0;
+void h_bnd_set_big(int on) { g_big = on; }
 void h_bnd_set_split(int p1, int nw2, int qt) { g_split_p1 = p1; g_split_nw = nw2; g_split_qt = qt; }
 
 // Two-stage pipeline of kernels k_band + k_chase + QL + back-transformation (csrc/vi_band.h, vi_chase.h), the device
@@ -289,6 +290,21 @@ int h_system_solve_two_stage(int n, const double* G, const double* y, const doub
   double scl = 1.0, badf = 0.0;
   const int p1 = (g_split_p1 > 0 && g_split_p1 < vi_bnd_nbk(n) - 1) ? g_split_p1 : 0;      // split reduction (k_band + k_band_tail)
   std::vector<double> Xt(p1 ? vi_bnd_trailing_doubles(n, p1) + 2 : 2, 0.0);
+  std::vector<double> Xbig(g_big ? vi_bnd_nblk(n) * 64 + 2 : 2, 0.0);
+  if (g_big) {          // k_band_big: blocks in "global" memory, panel QR in shared memory, no look-ahead
+    const int nwb = 6;
+    std::vector<double> smemb(vi_bnd_doubles_big(n, nwb) + 2);
+    double* bb = smemb.data();
+    if (reinterpret_cast<uintptr_t>(bb) & 15) bb += 1;
+    emu::run_cta(0, 32 * nwb, [&]() {
+      vi_bnd_ws S;
+      vi_bnd_carve_big(S, bb, Xbig.data(), n, nwb);
+      vi_bnd_load(S, G, y, regs, lam, nreg, nullptr, 0.0, 0.0);
+      const bool isbad = S.sc[1] != 0.0;
+      if (!isbad) { vi_bnd_reduce_big(S, Vg.data()); vi_bnd_store_band(S, band.data()); }
+      if (vi_tid() == 0) { scl = S.sc[0]; badf = S.sc[1]; }
+    });
+  } else
   emu::run_cta(0, nt, [&]() {
     vi_bnd_ws S;
     vi_bnd_carve(S, base, n);
@@ -306,7 +322,7 @@ int h_system_solve_two_stage(int n, const double* G, const double* y, const doub
     }
     if (vi_tid() == 0) { scl = S.sc[0]; badf = S.sc[1]; }
   });
-  if (p1 && badf == 0.0) {
+  if (p1 && !g_big && badf == 0.0) {
     const int n2 = n - 8 * p1, nw2 = g_split_nw > 0 ? g_split_nw : vi_bnd_nwarp(n2);
     std::vector<double> smem2(vi_bnd_doubles(n2, nw2) + 2);
     double* base2 = smem2.data();

@@ -254,6 +254,47 @@ def test_two_stage_split_reduction(harness, n, p1):
     assert np.allclose(np.linalg.eigvalsh(T2), np.linalg.eigvalsh(T0), rtol=0, atol=1e-13 * np.abs(d0).max())
 
 
+@pytest.mark.parametrize("n", [9, 40, 144, 200])
+def test_two_stage_global_memory_form(harness, n):
+    """k_band_big (orders beyond 168: X in global memory, panel QR on the panel in shared memory, no look-ahead): same
+    reduction as the shared-memory kernel up to summation order, also on a graded indefinite matrix."""
+    rng = np.random.default_rng(700 + n)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    ev = rng.standard_normal(n) * 10.0 ** rng.uniform(-10, 0, n)
+    X = (Q * ev) @ Q.T
+    X = np.ascontiguousarray(0.5 * (X + X.T))
+    y = rng.standard_normal(n)
+    harness.h_bnd_set_big(1)
+    try:
+        b1, c1, d1, e1, r1 = _band_of(harness, X, y, (0, 0, 4))
+    finally:
+        harness.h_bnd_set_big(0)
+    npad = (n + 7) // 8 * 8
+    Bm = np.zeros((n, n))
+    for j in range(n):
+        for d in range(9):
+            if j + d < n:
+                Bm[j + d, j] = Bm[j, j + d] = b1[9 * j + d]
+    scl = 2.0 ** -np.frexp(np.abs(X).max())[1]
+    assert np.allclose(np.sort(np.linalg.eigvalsh(Bm) / scl), np.sort(np.linalg.eigvalsh(X)), rtol=0, atol=1e-13 * np.abs(ev).max())
+    T1 = np.diag(d1) + np.diag(e1[:-1], 1) + np.diag(e1[:-1], -1)
+    assert np.allclose(np.sort(np.linalg.eigvalsh(T1) / scl), np.sort(np.linalg.eigvalsh(X)), rtol=0, atol=1e-13 * np.abs(ev).max())
+    if n <= 168:
+        b0, c0, d0, e0, r0 = _band_of(harness, X, y, (0, 0, 4))
+        assert np.allclose(np.abs(b1), np.abs(b0), rtol=0, atol=1e-13 * np.abs(b0).max())
+    # and the solve through it on a well-conditioned system
+    M = rng.standard_normal((n, n))
+    Xw = np.ascontiguousarray(M @ M.T + n * np.eye(n))
+    harness.h_bnd_set_big(1)
+    try:
+        st, bad, rank, Cq, dd, ee = _system(harness, Xw, y, np.zeros((1, n, n)), [0.0], TWO_STAGE)
+    finally:
+        harness.h_bnd_set_big(0)
+    assert st == 0 and bad == 0 and rank == n
+    ref = np.linalg.solve(Xw, y)
+    assert np.max(np.abs(Cq - ref)) <= 1e-12 * np.abs(ref).max()
+
+
 def test_two_stage_layout(harness):
     """Block layout of vi_band.h: the element map of a block is a bijection, and each of the three fragment access
     patterns touches 16 distinct 8-byte bank pairs per half warp (64-bit accesses) / 8 distinct 16-byte slots per

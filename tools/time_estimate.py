@@ -29,9 +29,6 @@ la, lo, al = gl[p // (G * G)], gn[(p // G) % G], ga[p % G]
 Cm = torch.from_numpy(np.random.default_rng(0).standard_normal((R, model.nbasis))).to(dev)
 out = torch.empty((R, tile), dtype=torch.float64, device=dev)
 lib = _native.lib()
-import os
-if os.environ.get('VI_TE_STREAM'):
-    torch.cuda.set_stream(torch.cuda.Stream(dev))
 for _ in range(3):
     model.estimate_device(la, lo, al, Cm, eq, out)
 torch.cuda.synchronize()

@@ -184,14 +184,6 @@ int side_for_device(Side** out) {
 int vi_estimate_fill_begin(double* out, int32_t Rsel, int64_t npts, cudaStream_t s) {
   Side* sd = nullptr;
   if (int rc = side_for_device(&sd)) return rc;
-  static const int dbg = getenv("VI_FILL_DEBUG") ? atoi(getenv("VI_FILL_DEBUG")) : 0;      // 1: no fill, 2: fill on s
-  if (dbg == 1) { VI_CUDA(cudaEventRecord(sd->join, s)); return VI_OK; }
-  if (dbg == 2) {
-    const int64_t pairs2 = ((int64_t)Rsel * npts + 1) / 2;
-    VI_KERNEL(VI_K_ESTIMATE, s, k_fill_nan<<<blocks(pairs2, 256) < 148u * 16u ? blocks(pairs2, 256) : 148u * 16u, 256, 0, s>>>(out, (int64_t)Rsel * npts));
-    VI_CUDA(cudaEventRecord(sd->join, s));
-    return VI_OK;
-  }
   VI_CUDA(cudaEventRecord(sd->fork, s));                 // out may still be read by earlier work on s
   VI_CUDA(cudaStreamWaitEvent(sd->stream, sd->fork, 0));
   const int64_t pairs = ((int64_t)Rsel * npts + 1) / 2;

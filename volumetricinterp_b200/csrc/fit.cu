@@ -72,9 +72,20 @@ struct Downdate { const double* A; const double* Wm; const double* bm; int P; };
 constexpr int kChiGates = 1024;    // gates per CTA in k_chi2 (partial sums combined in fixed order)
 
 // two-stage reduction: orders whose panel fits the QR warp's registers and whose blocks fit one CTA's shared memory
+// two-stage tridiagonalisation with X in shared memory (n <= 168) ...
+bool two_stage_smem(int n) {
+  return n <= VI_BND_NMAX && (size_t)vi_bnd_doubles(n) * sizeof(double) <= 227 * 1024;
+}
+// ... or with X in global memory (k_band_big: the high-order model of BASELINE configs[2], N = 500)
+constexpr int kBigWarps = 6;
+constexpr int kBigNmax = 1024;
+bool two_stage_big(int n) {
+  return !two_stage_smem(n) && n <= kBigNmax && (size_t)vi_bnd_doubles_big(n, kBigWarps) * sizeof(double) <= 227 * 1024 &&
+         (size_t)vi_chs_doubles(n) * sizeof(double) <= 227 * 1024;
+}
 bool two_stage_ok(int n) {
   static const bool off = getenv("VI_ONE_STAGE") != nullptr;
-  return !off && n <= VI_BND_NMAX && (size_t)vi_bnd_doubles(n) * sizeof(double) <= 227 * 1024;
+  return !off && (two_stage_smem(n) || two_stage_big(n));
 }
 
 // Split of stage 1 (k_band + k_band_tail).  The reduction is a chain of panel steps whose latency barely depends on
@@ -84,7 +95,7 @@ bool two_stage_ok(int n) {
 constexpr int kTailWarps = 4;
 int band_split(int n) {
   static const int env = getenv("VI_BAND_SPLIT") ? atoi(getenv("VI_BAND_SPLIT")) : -1;       // 0: off, > 0: that panel
-  if (!two_stage_ok(n) || env == 0) return 0;
+  if (!two_stage_ok(n) || !two_stage_smem(n) || env == 0) return 0;
   const int nbk = vi_bnd_nbk(n);
   if (vi_bnd_nwarp(n) != VI_BND_NW) return 0;                // small orders: one kernel
   int p1 = 0;
@@ -145,7 +156,7 @@ void sysbuf_carve(Bump& b, SysBuf& S, int64_t cap, int n, int nreg, int P) {
   S.unit = b.take<int32_t>(cap);
   S.kidx = b.take<int32_t>(cap);
   S.gate = b.take<int32_t>(cap);
-  S.Xg = S.use_gx ? b.take<double>(cap * n * S.ld) : nullptr;
+  S.Xg = (S.use_gx || (S.two_stage && !two_stage_smem(n))) ? b.take<double>(cap * n * S.ld) : nullptr;
   S.rot_total = b.take<unsigned long long>(4);
 }
 
@@ -395,6 +406,33 @@ k_band(const double* __restrict__ G, const double* __restrict__ y, const double*
   if (threadIdx.x == 0) { B.scl[s] = W.sc[0]; B.st[s] = bad ? VI_ST_NONFINITE : VI_ST_OK; }
 }
 
+// Stage 1 for orders whose X does not fit shared memory: blocks in global memory (B.Xg), panel factors in shared memory.
+__global__ void __launch_bounds__(kBigWarps * 32, 2)
+k_band_big(const double* __restrict__ G, const double* __restrict__ y, const double* __restrict__ regs, SysBuf B, Downdate dd) {
+  extern __shared__ __align__(16) double sm[];
+  const int64_t s = blockIdx.x;
+  const int r = B.rec[s];
+  if (r < 0) { if (threadIdx.x == 0) B.st[s] = kSkip; return; }
+  const int n = B.n;
+  vi_bnd_ws W;
+  vi_bnd_carve_big(W, sm, B.Xg + s * (int64_t)n * B.ld, n, kBigWarps);
+  const double* arow = nullptr;
+  double wj = 0.0, bj = 0.0;
+  if (dd.A != nullptr) {
+    const int j = B.gate[s];
+    arow = dd.A + (int64_t)j * n;
+    wj = dd.Wm[(int64_t)r * dd.P + j];
+    bj = dd.bm[(int64_t)r * dd.P + j];
+  }
+  vi_bnd_load(W, G + (int64_t)r * n * n, y + (int64_t)r * n, regs, B.lam + s * (B.nreg > 0 ? B.nreg : 1), B.nreg, arow, wj, bj);
+  const bool bad = W.sc[1] != 0.0;
+  if (!bad) {
+    vi_bnd_reduce_big(W, B.V + s * B.vstride);
+    vi_bnd_store_band(W, B.band + s * (int64_t)vi_bnd_band_doubles(n));
+  }
+  if (threadIdx.x == 0) { B.scl[s] = W.sc[0]; B.st[s] = bad ? VI_ST_NONFINITE : VI_ST_OK; }
+}
+
 // Second kernel of the split stage 1: the trailing matrix of order n - 8 p1 as an independent band reduction
 // (panel q of it = panel p1 + q of the system), four CTAs of four warps per SM.
 __global__ void __launch_bounds__(kTailWarps * 32, 4)
@@ -418,7 +456,7 @@ __global__ void __launch_bounds__(kChaseWarps * 32)
 k_chase(int64_t nsys, SysBuf B) {
   extern __shared__ __align__(16) double sm[];
   const int n = B.n, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t s = (int64_t)blockIdx.x * kChaseWarps + warp;
+  const int64_t s = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;       // (high orders: fewer warps per CTA)
   if (s >= nsys || B.st[s] != VI_ST_OK) return;
   const int np = vi_bnd_npad(n);
   double* Bw = sm + (size_t)warp * vi_chs_doubles(n);
@@ -1568,6 +1606,19 @@ inline unsigned blocks(int64_t n, int per) { return (unsigned)((n + per - 1) / p
 int run_tridiag(int64_t cnt, const double* G, const double* y, const double* regs, const SysBuf& B, cudaStream_t s,
                 Downdate dd = Downdate{nullptr, nullptr, nullptr, 0}) {
   if (cnt <= 0) return VI_OK;
+  if (B.two_stage && !two_stage_smem(B.n)) {
+    const size_t smem1 = (size_t)vi_bnd_doubles_big(B.n, kBigWarps) * sizeof(double);
+    VI_CUDA(cudaFuncSetAttribute(k_band_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    VI_KERNEL(VI_K_TRIDIAG, s, k_band_big<<<(unsigned)cnt, kBigWarps * 32, smem1, s>>>(G, y, regs, B, dd));
+    const size_t per = (size_t)vi_chs_doubles(B.n) * sizeof(double);
+    int cw = (int)((227 * 1024) / per);
+    if (cw > kChaseWarps) cw = kChaseWarps;
+    if (cw > 1 && (227 * 1024) / (per * cw) < 2 && (227 * 1024) / per >= 2) cw = 1;      // rather two CTAs of one warp than one of two
+    const size_t smem2 = per * cw;
+    VI_CUDA(cudaFuncSetAttribute(k_chase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    VI_KERNEL(VI_K_CHASE, s, k_chase<<<blocks(cnt, cw), cw * 32, smem2, s>>>(cnt, B));
+    return VI_OK;
+  }
   if (B.two_stage) {
     const size_t smem1 = (size_t)vi_bnd_doubles(B.n) * sizeof(double);
     const int nt = vi_bnd_threads(B.n);

@@ -567,6 +567,138 @@ VI_DEV void vi_bnd_reduce(const vi_bnd_ws& S, double* Vg, int pstop = -1) {
   }
 }
 
+// ---- orders beyond the shared-memory form (n > VI_BND_NMAX): X stays in global memory --------------------------------
+// The same block layout and the same phases; the blocks are read and written through L2 (1 MB per system at n = 500,
+// one CTA's traffic per panel step = the trailing matrix three times), the panel factors V / W, g and the Gram
+// partials stay in shared memory (75 KB at n = 500: three CTAs per SM).  The panel QR works on the panel in shared
+// memory (S.V), one warp, without look-ahead.
+VI_HD int vi_bnd_doubles_big(int n, int nw) {
+  const int nt = 32 * nw;
+  int part = nw * VI_BND_PART;
+  if (part < nt) part = nt;
+  return 2 * 8 * vi_bnd_ldv(n) + vi_bnd_npad(n) + part + 16;
+}
+VI_HD void vi_bnd_carve_big(vi_bnd_ws& S, double* mem, double* Xglobal, int n, int nw) {
+  S.n = n; S.npad = vi_bnd_npad(n); S.nbk = S.npad >> 3; S.ldv = vi_bnd_ldv(n); S.nw = nw;
+  const int nt = 32 * nw;
+  int part = nw * VI_BND_PART;
+  if (part < nt) part = nt;
+  S.X = Xglobal;
+  S.V = mem; mem += 8 * S.ldv;
+  S.W = mem; mem += 8 * S.ldv;
+  S.g = mem; mem += S.npad;
+  S.part = mem; mem += part;
+  S.tau = mem; mem += 8;
+  S.sc = mem; mem += 8;
+}
+
+// Householder QR of panel p by warp 0, the panel in S.V (its final place); same reflector convention and the same
+// results up to summation order as vi_bnd_qr_compute + vi_bnd_qr_store.  Lane l owns the rows r0 + l + 32 t.
+VI_DEV void vi_bnd_qr_big(const vi_bnd_ws& S, int p) {
+  const int lane = vi_tid() & 31;
+  const int r0 = 8 * (p + 1), npad = S.npad, nbk = S.nbk, ldv = S.ldv;
+  for (int i = r0 + lane; i < npad; i += 32) {
+    const double* blk = S.X + vi_bnd_blk(nbk, i >> 3, p) * 64;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 8; ++c) S.V[c * ldv + (i - 8)] = blk[vi_bnd_el(i & 7, c)];
+  }
+  vi_warp_sync();
+  for (int j = 0; j < 8; ++j) {
+    const int piv = r0 + j;
+    double s[8];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 8; ++c) s[c] = 0.0;
+    for (int i = r0 + lane; i < npad; i += 32) {
+      if (i <= piv) continue;
+      const double aj = S.V[j * ldv + (i - 8)];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int c = 0; c < 8; ++c)
+        if (c >= j) s[c] = fma(aj, S.V[c * ldv + (i - 8)], s[c]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+      for (int c = 0; c < 8; ++c) s[c] += vi_shfl_xor(s[c], o);
+    }
+    const double alpha = S.V[j * ldv + (piv - 8)];
+    double beta, tau, scale;
+    vi_reflector_scalars(alpha, s[j], &beta, &tau, &scale);
+    double w[8];
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 8; ++c) w[c] = (c > j) ? tau * (S.V[c * ldv + (piv - 8)] + scale * s[c]) : 0.0;
+    vi_warp_sync();                                             // pivot-row reads above, writes below
+    for (int i = r0 + lane; i < npad; i += 32) {
+      if (i < piv) continue;
+      if (i == piv) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int c = 0; c < 8; ++c)
+          if (c > j) S.V[c * ldv + (i - 8)] -= w[c];            // v = 1 on the pivot row
+        S.V[j * ldv + (i - 8)] = beta;
+      } else {
+        const double v = S.V[j * ldv + (i - 8)] * scale;
+        S.V[j * ldv + (i - 8)] = v;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+        for (int c = 0; c < 8; ++c)
+          if (c > j) S.V[c * ldv + (i - 8)] = fma(-w[c], v, S.V[c * ldv + (i - 8)]);
+      }
+    }
+    if (lane == 0) S.tau[j] = tau;
+    vi_warp_sync();
+  }
+  // R -> block (p + 1, p); V unit lower trapezoidal in place
+  if (lane < 8) {
+    double* blk = S.X + vi_bnd_blk(nbk, p + 1, p) * 64;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 8; ++c) blk[vi_bnd_el(lane, c)] = (lane <= c) ? S.V[c * ldv + (r0 + lane - 8)] : 0.0;
+  }
+  vi_warp_sync();
+  if (lane < 8) {
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 8; ++c)
+      if (lane <= c) S.V[c * ldv + (r0 + lane - 8)] = (lane == c) ? 1.0 : 0.0;
+  }
+}
+
+VI_DEV void vi_bnd_reduce_big(const vi_bnd_ws& S, double* Vg) {
+  const int warp = vi_tid() >> 5;
+  const int npan = S.nbk - 1;
+  if (npan <= 0) return;
+  if (warp == 0) vi_bnd_qr_big(S, 0);
+  vi_cta_sync();
+  for (int p = 0; p < npan; ++p) {
+    vi_bnd_symm(S, p);
+    vi_cta_sync();
+    if (warp == 0) vi_bnd_small(S);
+    vi_cta_sync();
+    vi_bnd_wpanel(S, p, Vg);
+    vi_cta_sync();
+    vi_bnd_update_col(S, p);
+    vi_bnd_update_rest(S, p, 0);
+    vi_cta_sync();
+    if (p + 1 < npan) {
+      if (warp == 0) vi_bnd_qr_big(S, p + 1);
+      vi_cta_sync();
+    }
+  }
+}
+
 // band[j * 9 + d] = X[j + d][j] (d = 0..8, zero beyond the matrix) for the columns j < ncols, g[i] for i < ncols to
 // gout.  The whole system: ncols = npad, gout = band + 9 npad.
 VI_DEV void vi_bnd_store_band(const vi_bnd_ws& S, double* band, double* gout, int ncols) {
