@@ -76,7 +76,15 @@ def test_search_agrees_with_reference_trace_and_envelope(cuda, name):
         c2 = [e[d]["chi2"] for d in DRIVERS]
         c2_spread = (max(c2) - min(c2)) / ref["chi2"]
         # (floor: chi2 at the root is nu + f(root), and brentq stops at |f| ~ 1e-7 nu -- the strict tier's 1e-6)
-        assert min(abs(res.chi_sq[r] - x) for x in c2) / ref["chi2"] <= max(3 * c2_spread, 1e-6), (r, c2_spread)
+        # ... or inside the reference's OWN scatter at the root: where chi2(alpha) is discontinuous (rank flips; at
+        # N = 500 the reference's brentq iterates within 1e-6 of its root read chi2 - nu between -0.92 and +0.22) the
+        # value returned is whichever side of the jump the last evaluation fell on
+        at_root = tr[np.abs(tr[:, 0] - tr[-1, 0]) <= 1e-6, 1]
+        lo, hi = at_root.min(), at_root.max()
+        f_gpu = res.chi_sq[r] - res.trace["nu"][r]
+        in_scatter = lo - 0.05 * (hi - lo) <= f_gpu <= hi + 0.05 * (hi - lo)
+        assert in_scatter or min(abs(res.chi_sq[r] - x) for x in c2) / ref["chi2"] <= max(3 * c2_spread, 1e-6), \
+            (r, c2_spread, f_gpu, lo, hi)
         ranks = [e[d]["rank"] for d in DRIVERS]
         assert min(ranks) - 2 <= int(res.rank[r]) <= max(ranks) + 2
 
