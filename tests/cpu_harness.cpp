@@ -404,6 +404,53 @@ int h_wave_replay_identical(int n, const double* d0, const double* e0, const dou
   return 0;
 }
 
+// The same with 32 / G systems replayed side by side by one warp (lane groups of G = 8 or 16): `nsys` tridiagonals of
+// order n, concatenated.  Returns 0 if every system's Z^T g and Z g are bit-identical to the sequential replay.
+int h_wave_replay_groups(int n, int G, const double* d0, const double* e0, const double* g0) {
+  const int S = 32 / G;
+  const int cap = 2 * n * n + 64, maxsw = vi_wav_maxsweeps(n);
+  std::vector<std::vector<double>> tcs(S), a(S), b(S), wa(S), wb(S);
+  std::vector<std::vector<int32_t>> ti(S), tab(S);
+  std::vector<int32_t> nr(S, 0);
+  std::vector<int> ns(S, 0);
+  for (int q = 0; q < S; ++q) {
+    std::vector<double> d(d0 + q * n, d0 + (q + 1) * n), e(n, 0.0);
+    for (int i = 0; i + 1 < n; ++i) e[i] = e0[q * n + i];
+    tcs[q].assign(2 * (size_t)cap, 0.0); ti[q].assign(cap, 0); tab[q].assign(maxsw + 2, 0);
+    vi_tape tape{{tcs[q].data(), 2}, {tcs[q].data() + 1, 2}, {ti[q].data(), 1}, cap};
+    if (vi_tql_values(n, {d.data(), 1}, {e.data(), 1}, tape, &nr[q]) != 0) return 9;
+    a[q].assign(g0 + q * n, g0 + (q + 1) * n); b[q] = a[q]; wa[q] = a[q]; wb[q] = a[q];
+    vi_tape_apply_zt({a[q].data(), 1}, tape, nr[q]);
+    vi_tape_apply_z({b[q].data(), 1}, tape, nr[q]);
+  }
+  int bad = 0;
+  emu::run_cta(0, 32, [&]() {
+    const int lane = vi_tid() & 31, grp = lane / G;
+    int myns = 0;
+    for (int q = 0; q < S; ++q) {              // the scans: whole warp, one system after the other
+      int tn = 0;
+      const int k = vi_wav_scan(ti[q].data(), 0, nr[q], tab[q].data(), maxsw, &tn);
+      if (tn != nr[q]) { if (lane == 0) bad = 8; }
+      if (q == grp) myns = k;
+      if (lane == 0) ns[q] = k;
+    }
+    if (bad) return;
+    if (G == 8) {
+      vi_wav_pass<true, 8>(wa[grp].data(), tcs[grp].data(), ti[grp].data(), tab[grp].data(), myns);
+      vi_wav_pass<false, 8>(wb[grp].data(), tcs[grp].data(), ti[grp].data(), tab[grp].data(), myns);
+    } else {
+      vi_wav_pass<true, 16>(wa[grp].data(), tcs[grp].data(), ti[grp].data(), tab[grp].data(), myns);
+      vi_wav_pass<false, 16>(wb[grp].data(), tcs[grp].data(), ti[grp].data(), tab[grp].data(), myns);
+    }
+  });
+  if (bad) return bad;
+  for (int q = 0; q < S; ++q) {
+    if (std::memcmp(a[q].data(), wa[q].data(), n * sizeof(double)) != 0) return 10 + q;
+    if (std::memcmp(b[q].data(), wb[q].data(), n * sizeof(double)) != 0) return 20 + q;
+  }
+  return 0;
+}
+
 int h_wav_bytes(int n) { return vi_wav_bytes(n); }
 int h_bnd_threads(int n) { return vi_bnd_threads(n); }
 int h_bnd_smem_bytes(int n) { return vi_bnd_doubles(n) * 8; }

@@ -211,6 +211,26 @@ def test_two_stage_band_is_orthogonally_similar(harness):
     assert np.abs(band.reshape(npad, 9)[n:]).max(initial=0.0) == 0.0
 
 
+@pytest.mark.parametrize("n,G", [(144, 8), (144, 16), (27, 8), (97, 8)])
+def test_wavefront_replay_several_systems_per_warp(harness, n, G):
+    """vi_wav_pass<., G>: 32 / G systems of different spectra (hence different sweep structures and lengths) replayed
+    side by side by the lane groups of one warp, each bit-identical to its sequential replay."""
+    S = 32 // G
+    rng = np.random.default_rng(n + G)
+    d = rng.standard_normal((S, n))
+    e = rng.standard_normal((S, n))
+    for q in range(S):
+        if q % 2 == 0:
+            d[q] *= 10.0 ** rng.uniform(-12, 0, n)
+            e[q] *= 10.0 ** rng.uniform(-12, 0, n)
+        if q == 1:
+            e[q, n // 2] = 0.0
+    g = rng.standard_normal((S, n))
+    fn = harness.h_wave_replay_groups
+    fn.restype = C.c_int
+    assert fn(n, G, dptr(np.ascontiguousarray(d)), dptr(np.ascontiguousarray(e)), dptr(np.ascontiguousarray(g))) == 0
+
+
 def _band_of(harness, X, y, split):
     n = X.shape[0]
     npad = (n + 7) // 8 * 8

@@ -63,6 +63,7 @@ struct SysBuf {
   size_t smem;
   double *V, *d, *e, *g, *tau, *scl, *tcs, *lam, *Csys, *chi2, *chi2p, *Xg, *band;
   int32_t *tix, *st, *rec, *rank, *nrot, *unit, *kidx, *gate;
+  int32_t* wtab;       // sweep tables of k_replay_wave4 (4n + 34 per system)
   unsigned long long* rot_total;   // rotations of all eigen-solves since the call started (profiling; may be null)
 };
 
@@ -156,6 +157,7 @@ void sysbuf_carve(Bump& b, SysBuf& S, int64_t cap, int n, int nreg, int P) {
   S.unit = b.take<int32_t>(cap);
   S.kidx = b.take<int32_t>(cap);
   S.gate = b.take<int32_t>(cap);
+  S.wtab = S.two_stage ? b.take<int32_t>(cap * (int64_t)(vi_wav_maxsweeps(n) + 2)) : nullptr;
   S.Xg = (S.use_gx || (S.two_stage && !two_stage_smem(n))) ? b.take<double>(cap * n * S.ld) : nullptr;
   S.rot_total = b.take<unsigned long long>(4);
 }
@@ -760,6 +762,111 @@ k_replay_wave(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, i
   }
   for (int i = lane; i < n; i += 32) Cs[i] = w[i];
   if (lane == 0) { rank_out[s] = rank; B.rank[s] = rank; }
+}
+
+// The same for FULL batches, four systems per warp (lane groups of 8, vi_wav_pass<., 8>): the sweeps of a QL run are
+// short on average, so with one system per warp ~7 of 32 lanes rotate per step and the kernel is bound by the
+// instruction issue of the idle ones.  The scans, the spectral cut-off and the back-transformations use the whole
+// warp, one system after the other; the sweep tables live in global memory (B.wtab) so that shared memory holds
+// nothing but the four vectors.
+constexpr int kWaveSys = 4;
+__global__ void __launch_bounds__(kWaveWarps * 32)
+k_replay_wave4(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, int32_t* __restrict__ rank_out) {
+  extern __shared__ __align__(16) double smw[];
+  const int n = B.n, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, grp = lane >> 3;
+  const int np = (n + 7) & ~7;
+  const int64_t s0 = ((int64_t)blockIdx.x * kWaveWarps + warp) * kWaveSys;
+  if (s0 >= nsys) return;
+  double* wbase = smw + (size_t)warp * kWaveSys * (np + 8);
+  const int maxsw = vi_wav_maxsweeps(n);
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  int my_ns = 0;                                 // sweeps of this lane group's system (0: nothing to replay in parallel)
+  unsigned okmask = 0, seqmask = 0;              // systems with a solution to compute / whose table overflowed
+  for (int g = 0; g < kWaveSys; ++g) {
+    const int64_t s = s0 + g;
+    if (s >= nsys) break;
+    const int st = B.st[s];
+    if (st == kSkip) continue;
+    double* Cs = Cout + s * (int64_t)n;
+    if (st != VI_ST_OK) {
+      for (int i = lane; i < n; i += 32) Cs[i] = nan;
+      if (lane == 0) rank_out[s] = 0;
+      continue;
+    }
+    okmask |= 1u << g;
+    double* w = wbase + g * (np + 8);
+    const int64_t base = ileave(s, n);
+    for (int i = lane; i < np + 8; i += 32) w[i] = (i < n) ? B.g[base + (int64_t)i * 32] : 0.0;
+    int tnext = 0;
+    const int32_t nrot = B.nrot[s];
+    const int k = vi_wav_scan(B.tix + s * (int64_t)B.tapecap, 0, nrot, B.wtab + s * (int64_t)(maxsw + 2), maxsw, &tnext);
+    if (tnext != nrot) seqmask |= 1u << g;
+    else if (g == grp) my_ns = k;
+  }
+  __syncwarp();
+  const int64_t sg = s0 + grp;                   // this lane group's system
+  const bool mine = ((okmask >> grp) & 1u) != 0;
+  const int64_t sc = mine ? sg : s0;
+  double* wg = wbase + grp * (np + 8);
+  const double* csg = B.tcs + sc * (int64_t)B.tapecap * 2;
+  const int32_t* ixg = B.tix + sc * (int64_t)B.tapecap;
+  const int32_t* tabg = B.wtab + sc * (int64_t)(maxsw + 2);
+  auto sequential = [&](bool fwd) {              // table overflow (never seen on this path's spectra): one lane
+    for (int g = 0; g < kWaveSys; ++g) {
+      if (!((seqmask >> g) & 1u) || lane != 0) continue;
+      const int64_t s = s0 + g;
+      double* cs = B.tcs + s * (int64_t)B.tapecap * 2;
+      vi_tape tp{{cs, 2}, {cs + 1, 2}, {B.tix + s * (int64_t)B.tapecap, 1}, B.tapecap};
+      if (fwd) vi_tape_apply_zt(vi_svec{wbase + g * (np + 8), 1}, tp, B.nrot[s]);
+      else vi_tape_apply_z(vi_svec{wbase + g * (np + 8), 1}, tp, B.nrot[s]);
+    }
+    __syncwarp();
+  };
+  vi_wav_pass<true, 8>(wg, csg, ixg, tabg, mine ? my_ns : 0);
+  if (seqmask) sequential(true);
+  __syncwarp();
+  int ranks[kWaveSys];
+#pragma unroll
+  for (int g = 0; g < kWaveSys; ++g) {
+    ranks[g] = 0;
+    if (!((okmask >> g) & 1u)) continue;
+    const int64_t s = s0 + g;
+    double* w = wbase + g * (np + 8);
+    const int64_t base = ileave(s, n);
+    double lmax = 0.0;
+    for (int i = lane; i < n; i += 32) lmax = fmax(lmax, fabs(B.d[base + (int64_t)i * 32]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    const double cut = rcond * lmax;
+    int rank = 0;
+    for (int i = lane; i < n; i += 32) {
+      const double l = B.d[base + (int64_t)i * 32];
+      if (fabs(l) > cut) { w[i] = w[i] / l; ++rank; }
+      else w[i] = 0.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+    ranks[g] = rank;
+  }
+  __syncwarp();
+  vi_wav_pass<false, 8>(wg, csg, ixg, tabg, mine ? my_ns : 0);
+  if (seqmask) sequential(false);
+  __syncwarp();
+#pragma unroll
+  for (int g = 0; g < kWaveSys; ++g) {
+    if (!((okmask >> g) & 1u)) continue;
+    const int64_t s = s0 + g;
+    double* w = wbase + g * (np + 8);
+    const double scl = B.scl[s];
+    for (int i = lane; i < n; i += 32) w[i] *= scl;
+    __syncwarp();
+    const double* Vg = B.V + s * B.vstride;
+    vi_chs_apply_q(w, n, Vg + vi_bnd_vdoubles(n));
+    vi_bnd_apply_q(w, n, Vg);
+    double* Cs = Cout + s * (int64_t)n;
+    for (int i = lane; i < n; i += 32) Cs[i] = w[i];
+    if (lane == 0) { rank_out[s] = ranks[g]; B.rank[s] = ranks[g]; }
+  }
 }
 
 // ---- covariance: dC = H (A^T W A) H, H = pinv(X)  (interpolate.py:464-467) ---------------------
@@ -1713,6 +1820,16 @@ int run_ql(int64_t cnt, const SysBuf& B, cudaStream_t s, bool* split) {
 int run_apply(int64_t cnt, const SysBuf& B, double rcond, double* Cout, int32_t* rank_out, cudaStream_t s, bool split) {
   if (cnt <= 0) return VI_OK;
   static const bool old_replay = getenv("VI_OLD_REPLAY") != nullptr;
+  // full batches of two-stage systems: four systems per warp
+  static const int wave4_min = env_int("VI_WAVE4_MIN", 8192);
+  if (split && !old_replay && B.two_stage && B.wtab && cnt >= wave4_min) {
+    const size_t smem = (size_t)kWaveWarps * kWaveSys * (((B.n + 7) & ~7) + 8) * sizeof(double);
+    if (smem <= 227 * 1024) {
+      VI_CUDA(cudaFuncSetAttribute(k_replay_wave4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      VI_KERNEL(VI_K_APPLY, s, k_replay_wave4<<<blocks(cnt, kWaveWarps * kWaveSys), kWaveWarps * 32, smem, s>>>(cnt, B, rcond, Cout, rank_out));
+      return VI_OK;
+    }
+  }
   if (split && !old_replay) {
     const size_t smem = (size_t)kWaveWarps * vi_wav_bytes(B.n);
     VI_CUDA(cudaFuncSetAttribute(k_replay_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -108,11 +108,17 @@ VI_DEV int vi_wav_scan(const int32_t* ix, int t0, int nrot, int32_t* tab, int ca
 // predecessor lane that has moved on means "everything before me is finished".  Sweeps whose ranges do not nest
 // (short sweeps on a split-off sub-block followed by a long one) are ordered by the same rule: the frontier is
 // cumulative along the chain, not the predecessor's position alone.
-template <bool FWD>
+//
+// G = lanes per system (32, 16 or 8): a warp replays 32 / G systems side by side, each lane group with its own vector,
+// tape and sweep table (the arguments are per lane, uniform inside a group).  The sweeps of a QL run are short on
+// average (7 of 32 lanes rotate per step with G = 32): at full batches four systems per warp cost a warp little more
+// than one.
+template <bool FWD, int G = 32>
 VI_DEV void vi_wav_pass(double* w, const double* cs, const int32_t* ix, const int32_t* tab, int ns) {
   const int lane = vi_tid() & 31;
+  const int gl = lane & (G - 1), gbase = lane & ~(G - 1);
   const int BIG = 1 << 28;
-  int q = lane;                                  // position in processing order: sweep FWD ? q : ns - 1 - q
+  int q = gl;                                    // position in processing order: sweep FWD ? q : ns - 1 - q
   int k = 0, len = 0, t = 0;                     // progress inside the sweep, its length, current tape entry
   const int dt = FWD ? 1 : -1;
   int pi = 0, u = 1;                             // plane index of the current rotation, its step per rotation
@@ -138,8 +144,8 @@ VI_DEV void vi_wav_pass(double* w, const double* cs, const int32_t* ix, const in
   for (;;) {
     const bool have = q < ns;
     const bool done = !have || k >= len;
-    // predecessor = processing position q - 1, on the previous lane; its values as published last step
-    const int pl = (lane + 31) & 31;
+    // predecessor = processing position q - 1, on the previous lane of the group; its values as published last step
+    const int pl = gbase + ((gl + G - 1) & (G - 1));
     const int pq = vi_shfl_i(q, pl), pu = vi_shfl_i(u, pl), pK = vi_shfl_i(K, pl), pcum = vi_shfl_i(cum, pl);
     int lim;                                     // K_{q-1} as far as I may rely on it
     bool before_done;                            // every sweep < q is finished
@@ -166,7 +172,7 @@ VI_DEV void vi_wav_pass(double* w, const double* cs, const int32_t* ix, const in
       cum = (fin && before_done) ? 1 : 0;
     }
     if (have && fin && before_done) {            // next sweep of this lane
-      q += 32;
+      q += G;
       open();
       if (q < ns) { vi_wav_ld(cs, t, c, s); code = ix[t]; }
       K = -BIG; cum = 0;                         // nothing known yet about the new sweep's chain
