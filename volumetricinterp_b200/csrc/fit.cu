@@ -782,6 +782,7 @@ k_replay_wave4(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, 
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   int my_ns = 0;                                 // sweeps of this lane group's system (0: nothing to replay in parallel)
   unsigned okmask = 0, seqmask = 0;              // systems with a solution to compute / whose table overflowed
+#pragma unroll 1
   for (int g = 0; g < kWaveSys; ++g) {
     const int64_t s = s0 + g;
     if (s >= nsys) break;
@@ -825,10 +826,8 @@ k_replay_wave4(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, 
   vi_wav_pass<true, 8>(wg, csg, ixg, tabg, mine ? my_ns : 0);
   if (seqmask) sequential(true);
   __syncwarp();
-  int ranks[kWaveSys];
-#pragma unroll
+#pragma unroll 1
   for (int g = 0; g < kWaveSys; ++g) {
-    ranks[g] = 0;
     if (!((okmask >> g) & 1u)) continue;
     const int64_t s = s0 + g;
     double* w = wbase + g * (np + 8);
@@ -846,13 +845,13 @@ k_replay_wave4(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, 
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
-    ranks[g] = rank;
+    if (lane == 0) { rank_out[s] = rank; B.rank[s] = rank; }
   }
   __syncwarp();
   vi_wav_pass<false, 8>(wg, csg, ixg, tabg, mine ? my_ns : 0);
   if (seqmask) sequential(false);
   __syncwarp();
-#pragma unroll
+#pragma unroll 1
   for (int g = 0; g < kWaveSys; ++g) {
     if (!((okmask >> g) & 1u)) continue;
     const int64_t s = s0 + g;
@@ -865,7 +864,6 @@ k_replay_wave4(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, 
     vi_bnd_apply_q(w, n, Vg);
     double* Cs = Cout + s * (int64_t)n;
     for (int i = lane; i < n; i += 32) Cs[i] = w[i];
-    if (lane == 0) { rank_out[s] = ranks[g]; B.rank[s] = ranks[g]; }
   }
 }
 
