@@ -118,27 +118,42 @@ VI_DEV void vi_wav_pass(double* w, const double* cs, const int32_t* ix, const in
   const int lane = vi_tid() & 31;
   const int gl = lane & (G - 1), gbase = lane & ~(G - 1);
   const int BIG = 1 << 28;
+  const int dt = FWD ? 1 : -1;
   int q = gl;                                    // position in processing order: sweep FWD ? q : ns - 1 - q
   int k = 0, len = 0, t = 0;                     // progress inside the sweep, its length, current tape entry
-  const int dt = FWD ? 1 : -1;
-  int pi = 0, u = 1;                             // plane index of the current rotation, its step per rotation
-  auto open = [&]() {
+  int pi = 0, u = 1, flag = 0;                   // plane index of the current rotation, its step per rotation, direction flag
+  double c = 1.0, s = 0.0, c1 = 1.0, s1 = 0.0;   // (c, s) of the current entry and of the one after it
+  // Everything a lane needs to OPEN a sweep is fetched one or two sweeps ahead (a sweep open is otherwise two dependent
+  // global loads -- table, then the first tape entry -- in front of every lane of the warp): p1 = next sweep of this
+  // lane (table entries + first tape entry), p2 = the one after (table entries).  Inside a sweep only (c, s) are read:
+  // the plane index moves by u per rotation and the direction flag is constant (that is what defines a sweep).
+  int p1a = 0, p1b = 0, p1code = 0, p2a = 0, p2b = 0;
+  double p1c = 1.0, p1s = 0.0;
+  auto tabld = [&](int pos, int& a, int& b) {
+    if (pos < ns) { const int sw = FWD ? pos : ns - 1 - pos; a = tab[sw]; b = tab[sw + 1]; }
+  };
+  auto firstld = [&](int pos, int a, int b, int& cd, double& cc, double& ss) {
+    if (pos < ns) { const int tt = FWD ? a : b - 1; cd = ix[tt]; vi_wav_ld(cs, tt, cc, ss); }
+  };
+  auto start = [&]() {                           // sweep q from the p1 registers
     k = 0; len = 0;
     if (q < ns) {
-      const int sw = FWD ? q : ns - 1 - q;
-      const int a = tab[sw], b = tab[sw + 1];
-      len = b - a;
-      t = FWD ? a : b - 1;
-      const int code = ix[t];
-      pi = code >> 1;
-      const int along = (code & 1) ? 1 : -1;     // plane index step per rotation in tape order
+      len = p1b - p1a;
+      t = FWD ? p1a : p1b - 1;
+      c = p1c; s = p1s;
+      pi = p1code >> 1;
+      flag = p1code & 1;
+      const int along = flag ? 1 : -1;           // plane index step per rotation in tape order
       u = FWD ? along : -along;
+      if (len > 1) vi_wav_ld(cs, t + dt, c1, s1);
     }
   };
-  open();
-  double c = 1.0, s = 0.0;
-  int code = 0;
-  if (q < ns) { vi_wav_ld(cs, t, c, s); code = ix[t]; }
+  tabld(q, p1a, p1b);
+  firstld(q, p1a, p1b, p1code, p1c, p1s);
+  start();
+  tabld(q + G, p1a, p1b);
+  firstld(q + G, p1a, p1b, p1code, p1c, p1s);
+  tabld(q + 2 * G, p2a, p2b);
   int K = -BIG;                                  // published frontier key of my current sweep (cumulative)
   int cum = 0;                                   // published: my sweep and every earlier one are done
   for (;;) {
@@ -157,12 +172,13 @@ VI_DEV void vi_wav_pass(double* w, const double* cs, const int32_t* ix, const in
       lim = before_done ? BIG : ((pu == u) ? pK : -BIG);
     }
     if (have && !done && u * pi <= lim) {
-      const int pj = (code & 1) ? pi - 1 : pi + 1;
+      const int pj = flag ? pi - 1 : pi + 1;
       const double a = w[pi], b = w[pj];
       if (FWD) { w[pj] = s * a + c * b; w[pi] = c * a - s * b; }
       else { w[pi] = c * a + s * b; w[pj] = c * b - s * a; }
       ++k; t += dt; pi += u;
-      if (k < len) { vi_wav_ld(cs, t, c, s); code = ix[t]; }
+      c = c1; s = s1;
+      if (k + 1 < len) vi_wav_ld(cs, t + dt, c1, s1);
     }
     const bool fin = !have || k >= len;
     // publish; a finished sweep hands the chain's frontier on unchanged
@@ -173,8 +189,10 @@ VI_DEV void vi_wav_pass(double* w, const double* cs, const int32_t* ix, const in
     }
     if (have && fin && before_done) {            // next sweep of this lane
       q += G;
-      open();
-      if (q < ns) { vi_wav_ld(cs, t, c, s); code = ix[t]; }
+      start();
+      p1a = p2a; p1b = p2b;
+      firstld(q + G, p1a, p1b, p1code, p1c, p1s);
+      tabld(q + 2 * G, p2a, p2b);
       K = -BIG; cum = 0;                         // nothing known yet about the new sweep's chain
     }
     vi_warp_sync();
