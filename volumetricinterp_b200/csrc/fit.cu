@@ -1818,9 +1818,10 @@ int run_ql(int64_t cnt, const SysBuf& B, cudaStream_t s, bool* split) {
 int run_apply(int64_t cnt, const SysBuf& B, double rcond, double* Cout, int32_t* rank_out, cudaStream_t s, bool split) {
   if (cnt <= 0) return VI_OK;
   static const bool old_replay = getenv("VI_OLD_REPLAY") != nullptr;
-  // full batches of two-stage systems: four systems per warp
-  static const int wave4_min = env_int("VI_WAVE4_MIN", 8192);
-  if (split && !old_replay && B.two_stage && B.wtab && cnt >= wave4_min) {
+  // four systems per warp: measured SLOWER than one (10.8 vs 8.7 ms per 28 416 systems: with 8 lanes per system the
+  // wavefront needs 3x the steps on these spectra); kept behind VI_WAVE4_MIN=<batch size> for other workloads
+  static const int wave4_min = env_int("VI_WAVE4_MIN", 0);
+  if (split && !old_replay && B.two_stage && B.wtab && wave4_min > 0 && cnt >= wave4_min) {
     const size_t smem = (size_t)kWaveWarps * kWaveSys * (((B.n + 7) & ~7) + 8) * sizeof(double);
     if (smem <= 227 * 1024) {
       VI_CUDA(cudaFuncSetAttribute(k_replay_wave4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
