@@ -157,7 +157,8 @@ void sysbuf_carve(Bump& b, SysBuf& S, int64_t cap, int n, int nreg, int P) {
   S.unit = b.take<int32_t>(cap);
   S.kidx = b.take<int32_t>(cap);
   S.gate = b.take<int32_t>(cap);
-  S.wtab = S.two_stage ? b.take<int32_t>(cap * (int64_t)(vi_wav_maxsweeps(n) + 2)) : nullptr;
+  static const bool tab_smem = getenv("VI_WAVE_TAB_SMEM") != nullptr;      // A/B: sweep tables in shared memory
+  S.wtab = tab_smem ? nullptr : b.take<int32_t>(cap * (int64_t)(vi_wav_maxsweeps(n) + 2));
   S.Xg = (S.use_gx || (S.two_stage && !two_stage_smem(n))) ? b.take<double>(cap * n * S.ld) : nullptr;
   S.rot_total = b.take<unsigned long long>(4);
 }
@@ -707,9 +708,11 @@ k_replay_wave(int64_t nsys, SysBuf B, double rcond, double* __restrict__ Cout, i
     return;
   }
   const int np = (n + 7) & ~7;
-  unsigned char* mine = smraw + (size_t)warp * vi_wav_bytes(n);
+  // the sweep table lives in global memory (B.wtab) when there is one: shared memory then holds only the vector, and
+  // the SM keeps most of its 256 KB as L1 for the 32 tape streams of every warp
+  unsigned char* mine = smraw + (size_t)warp * (B.wtab ? vi_wav_bytes_vec(n) : vi_wav_bytes(n));
   double* w = reinterpret_cast<double*>(mine);
-  int32_t* tab = reinterpret_cast<int32_t*>(mine + np * 8 + 64);
+  int32_t* tab = B.wtab ? B.wtab + s * (int64_t)(vi_wav_maxsweeps(n) + 2) : reinterpret_cast<int32_t*>(mine + np * 8 + 64);
   const int64_t base = ileave(s, n);
   for (int i = lane; i < np + 8; i += 32) w[i] = (i < n) ? B.g[base + (int64_t)i * 32] : 0.0;
   const int32_t nrot = B.nrot[s];
@@ -1830,7 +1833,7 @@ int run_apply(int64_t cnt, const SysBuf& B, double rcond, double* Cout, int32_t*
     }
   }
   if (split && !old_replay) {
-    const size_t smem = (size_t)kWaveWarps * vi_wav_bytes(B.n);
+    const size_t smem = (size_t)kWaveWarps * (B.wtab ? vi_wav_bytes_vec(B.n) : vi_wav_bytes(B.n));
     VI_CUDA(cudaFuncSetAttribute(k_replay_wave, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VI_KERNEL(VI_K_APPLY, s, k_replay_wave<<<blocks(cnt, kWaveWarps), kWaveWarps * 32, smem, s>>>(cnt, B, rcond, Cout, rank_out));
     return VI_OK;
