@@ -93,7 +93,14 @@ if reps:
             wr = float(r[h.index("dram__bytes_write.sum")].replace(",", ""))
             traffic[name] = {"systems_per_launch": 8192, "dram_bytes_read": rd, "dram_bytes_written": wr,
                              "dram_bytes_per_system": (rd + wr) / 8192}
-    json.dump(traffic, open(os.path.join(P, "r02_traffic.json"), "w"), indent=1)
+    kind_of = {"k_band": "tridiag", "k_band_tail": "tridiag", "k_chase": "chase", "k_tql_smem": "tql", "k_replay_wave": "apply"}
+    by_kind = {}
+    for name, v in traffic.items():
+        base = re.sub(r"<.*", "", name)
+        if base in kind_of:
+            by_kind[kind_of[base]] = by_kind.get(kind_of[base], 0.0) + v["dram_bytes_per_system"]
+    json.dump({"capture": "gpurun_out/prof_r02_<kernel>.ncu-rep (tools/time_solver.py 8192 144, ncu --set full, one launch each)",
+               "dram_bytes_per_system": by_kind, "per_kernel": traffic}, open(os.path.join(P, "r02_traffic.json"), "w"), indent=1)
     out += ["", "DRAM traffic per eigen-system (`profiles/r02_traffic.json`): " +
             ", ".join(f"{k}: {v['dram_bytes_per_system'] / 1e3:.0f} KB" for k, v in traffic.items())]
 path = os.path.join(P, "r02_summary.md")
