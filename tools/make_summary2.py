@@ -78,14 +78,13 @@ if os.path.exists(lst):
             "`bench.py --records 2000 --steps 1 --warmup 1 --e2e-steps 1 --no-cpu-baseline`; copy in "
             "`profiles/r02_launches_records2000.csv`)", "",
             "\n".join(l for l in launch_table(lst).split("\n") if not l.startswith("| at::") and "elementwise" not in l)]
-reps = [f"gpurun_out/prof_r02_{k}.ncu-rep" for k in ("k_band", "k_band_tail", "k_chase", "k_tql_smem", "k_replay_wave")]
+reps = [f"gpurun_out/prof_r02_{k}.raw.csv" for k in ("k_band", "k_band_tail", "k_chase", "k_tql_smem", "k_replay_wave")]
 reps = [r for r in reps if os.path.exists(r)]
 if reps:
     out += ["", "## `ncu --set full` of the solver kernels (`tools/time_solver.py 8192 144`, one launch each)", "", full_table(reps)]
     traffic = {}
     for rep in reps:
-        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True, text=True).stdout
-        rows = list(csv.reader(io.StringIO(txt)))
+        rows = list(csv.reader(io.StringIO(open(rep).read())))
         h = rows[0]
         for r in rows[2:]:
             name = re.sub(r"\(.*", "", r[h.index("Kernel Name")]).replace("<unnamed>::", "").replace("void ", "")
@@ -99,7 +98,7 @@ if reps:
         base = re.sub(r"<.*", "", name)
         if base in kind_of:
             by_kind[kind_of[base]] = by_kind.get(kind_of[base], 0.0) + v["dram_bytes_per_system"]
-    json.dump({"capture": "gpurun_out/prof_r02_<kernel>.ncu-rep (tools/time_solver.py 8192 144, ncu --set full, one launch each)",
+    json.dump({"capture": "profiles/r02_ncu_<kernel>.raw.csv (tools/time_solver.py 8192 144, ncu --set full, one launch each)",
                "dram_bytes_per_system": by_kind, "per_kernel": traffic}, open(os.path.join(P, "r02_traffic.json"), "w"), indent=1)
     out += ["", "DRAM traffic per eigen-system (`profiles/r02_traffic.json`): " +
             ", ".join(f"{k}: {v['dram_bytes_per_system'] / 1e3:.0f} KB" for k, v in traffic.items())]

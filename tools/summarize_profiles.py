@@ -44,8 +44,11 @@ WANT = [("gpu__time_duration.sum", "duration ms", 1e-6), ("launch__registers_per
 def full_table(reps):
     out = ["| kernel (grid) | " + " | ".join(w[1] for w in WANT) + " |", "|---|" + "---|" * len(WANT)]
     for rep in reps:
-        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True,
-                             text=True).stdout
+        if rep.endswith(".csv"):      # raw page exported on the GPU box (tools/profile_round2_ncu.sh)
+            txt = open(rep).read()
+        else:
+            txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True,
+                                 text=True).stdout
         rows = list(csv.reader(io.StringIO(txt)))
         hdr = rows[0]
         for r in rows[2:]:
