@@ -58,12 +58,12 @@ if d:
             f"* Estimate block of the default run: single record {d['estimate']['single_record']['value']:.4g} points/s "
             f"({d['estimate']['single_record']['inside_hull_fraction']:.2f} inside the hull)" if d.get("estimate") else ""]
     k = d["kernels"]
-    out += ["", "| kernel kind (CUDA events in the timed region) | ms per step | launches per step | share | TFLOP/s | of FP64 peak |",
+    out += ["", "| kernel kind (CUDA events in the timed region) | ms per step | launches per step | share | algorithmic rate | of its peak (FP64 37.1 TFLOP/s or HBM 6553 GB/s) |",
             "|---|---|---|---|---|---|"]
     for name, v in sorted(k.items(), key=lambda kv: -kv[1]["ms_per_step"]):
-        tf, fr = v.get("tflops"), v.get("frac_of_fp64_peak") or v.get("frac_of_peak")
+        a, u, fr = v.get("achieved"), v.get("unit"), v.get("frac_of_peak")
         out.append(f"| {name} | {v['ms_per_step']:.1f} | {v['launches_per_step']:.0f} | {100 * (v['share'] or 0):.1f} % | "
-                   f"{('%.2f' % tf) if tf else '-'} | {('%.1f %%' % (100 * fr)) if fr else '-'} |")
+                   f"{('%.4g %s' % (a, u)) if a else '-'} | {('%.1f %%' % (100 * fr)) if fr else '-'} |")
     r = d["roofline"]
     out += ["", f"Roofline block of the line: `{json.dumps({k2: r[k2] for k2 in ('kernel', 'bound', 'achieved', 'peak', 'unit', 'frac', 'traffic') if k2 in r})}`",
             f"FP64 peaks measured in the same run: {r.get('fp64_peaks_tflops')} TFLOP/s; HBM {r.get('hbm_peak_gbs')} GB/s ({r.get('hbm_peak_source')})."]
