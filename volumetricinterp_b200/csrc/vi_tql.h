@@ -256,9 +256,14 @@ VI_HD int vi_tql_values(int n, vi_svec d, vi_svec e, vi_tape tape, int32_t* nrot
         double* dp = D + (int64_t)i * sd;          // d[i]; dp[sd] = d[i+1]
         double* ep = E + (int64_t)i * se;          // e[i]; ep[se] = e[i+1]
         double dnext = dp[sd];                     // d[i+1], carried in a register between steps
+        // e[i] and d[i] of the NEXT step are loaded one step ahead (this step writes e[i+1] and d[i+1] only): two
+        // shared-memory latencies less on the dependent chain of every rotation
+        double e_pre = *ep, d_pre = *dp;
         bool early = false;
         for (; i >= l; --i) {
-          const double ei = *ep;
+          const double ei = e_pre;
+          const double di_pre = d_pre;
+          if (i > l) { e_pre = ep[-se]; d_pre = dp[-sd]; }
           const double f = s * ei, b = c * ei;
           const double r2 = f * f + gg * gg;
           if (r2 == 0.0) {
@@ -278,7 +283,7 @@ VI_HD int vi_tql_values(int n, vi_svec d, vi_svec e, vi_tape tape, int32_t* nrot
           s = f * ri;
           c = gg * ri;
           gg = dnext - p;
-          const double di = *dp;
+          const double di = di_pre;
           r = (di - gg) * s + 2.0 * c * b;
           p = s * r;
           dp[sd] = gg + p;
@@ -353,6 +358,7 @@ VI_HD int vi_tql_values_flat(int n, vi_svec d, vi_svec e, vi_tape tape, int32_t*
   int l = 0, mm = 0, cand = 0, mt1 = -1, i = 0;
   bool valid = false, cand_valid = false;
   double s = 1.0, c = 1.0, p = 0.0, gg = 0.0, dnext = 0.0;
+  double e_pre = 0.0, d_pre = 0.0;       // e[i], d[i] of the next rotation, loaded one trip ahead (see vi_tql_values)
   for (;;) {
     // The sweep set-up (shift: two divisions and a square root) is batched: lanes that reach it idle until
     // `iter_batch` of them are waiting or no lane is rotating, so its ~120 instructions are not paid on every trip.
@@ -366,7 +372,9 @@ VI_HD int vi_tql_values_flat(int n, vi_svec d, vi_svec e, vi_tape tape, int32_t*
     if (phase == VI_QL_ROT) {
       double* dp = D + (int64_t)i * sd;
       double* ep = E + (int64_t)i * se;
-      const double ei = *ep;
+      const double ei = e_pre;
+      const double di_pre = d_pre;
+      if (i > l) { e_pre = ep[-se]; d_pre = dp[-sd]; }
       const double f = s * ei, b = c * ei;
       const double r2 = f * f + gg * gg;
       if (r2 == 0.0) {
@@ -386,7 +394,7 @@ VI_HD int vi_tql_values_flat(int n, vi_svec d, vi_svec e, vi_tape tape, int32_t*
         s = f * ri;
         c = gg * ri;
         gg = dnext - p;
-        const double di = *dp;
+        const double di = di_pre;
         r = (di - gg) * s + 2.0 * c * b;
         p = s * r;
         const double dnew = gg + p;          // final d[i+1] of this sweep
@@ -446,6 +454,8 @@ VI_HD int vi_tql_values_flat(int n, vi_svec d, vi_svec e, vi_tape tape, int32_t*
         s = 1.0; c = 1.0; p = 0.0;
         i = mm - 1;
         dnext = D[(int64_t)(i + 1) * sd];
+        e_pre = E[(int64_t)i * se];
+        d_pre = D[(int64_t)i * sd];
         mt1 = -1;
         phase = VI_QL_ROT;
         break;
