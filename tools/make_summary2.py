@@ -51,7 +51,11 @@ one("C5", load("r02_bench_c5.json"), "`--config c5 --records 64`: leave-beam-out
 one("NaN-heavy mix", load("r02_bench_mix.json"), "`--noise-scale 1.0 --signal-terms 5`: the round-1 workload (15 % NaN records)")
 one("2 GPUs weak", load("r02_bench_2gpu_weak.json"), "torchrun, 10 000 records per GPU")
 one("2 GPUs strong", load("r02_bench_2gpu_strong.json"), "torchrun `--scaling strong --records 10000`")
-one("2 GPUs C4", load("r02_bench_2gpu_c4.json"), "torchrun `--config c4`, point-sharded")
+one("2 GPUs C4", load("r02_bench_2gpu_c4.json"), "torchrun `--config c4 --tiles 32`, point-sharded")
+one("4 GPUs weak", load("r02_bench_4gpu_weak.json"), "torchrun, 10 000 records per GPU, `--steps 2`")
+one("4 GPUs C4", load("r02_bench_4gpu_c4.json"), "torchrun `--config c4 --tiles 32`")
+one("8 GPUs weak", load("r02_bench_8gpu_weak.json"), "torchrun, 10 000 records per GPU, `--steps 2`")
+one("8 GPUs C4", load("r02_bench_8gpu_c4.json"), "torchrun `--config c4 --tiles 32`")
 if d:
     out += ["", f"* fit of the default run: {d.get('fit')}",
             f"* CPU baseline inside the default run: {d.get('cpu_baseline')}",
