@@ -87,6 +87,28 @@ def test_normal_equations_strict_bit_exact_and_fast_close(cuda, name):
     assert np.array_equal(Wm.cpu().numpy() != 0, np.isfinite(g["value"]))
 
 
+@pytest.mark.parametrize("N,P", [(161, 300), (343, 700), (500, 1000), (129, 77)])
+def test_normal_equations_blocked_tensor_core_kernel(cuda, N, P):
+    """Orders beyond the one-CTA tensor-core kernel (N > 160: k_ne_dmma_blk, 128 x 128 blocks of the lower triangle):
+    against the bit-exact strict kernel on random data with masked gates, 1e-13 of the scale, exactly symmetric.
+    (N = 129 still takes the one-CTA kernel: same bar.)"""
+    from volumetricinterp_b200 import _native, fit
+    rng = np.random.default_rng(N + P)
+    A = rng.standard_normal((P, N)) * 10.0 ** rng.uniform(-3, 0, N)
+    value = rng.uniform(1e10, 1e12, (3, P))
+    value[0, ::7] = np.nan
+    value[2, : P // 2] = np.nan
+    error = rng.uniform(1e9, 1e11, (3, P))
+    At, v, e = _t(cuda, A), _t(cuda, value), _t(cuda, error)
+    Gs, ys, *_ = fit.normal_equations_device(At, v, e, None, _native.NE_STRICT)
+    Gf, yf, *_ = fit.normal_equations_device(At, v, e, None, _native.NE_FAST)
+    Gs, ys, Gf, yf = (t.cpu().numpy() for t in (Gs, ys, Gf, yf))
+    for r in range(3):
+        assert np.array_equal(Gf[r], Gf[r].T)
+        assert np.max(np.abs(Gf[r] - Gs[r])) <= 1e-13 * np.abs(Gs[r]).max()
+        assert np.max(np.abs(yf[r] - ys[r])) <= 1e-13 * np.abs(ys[r]).max()
+
+
 def test_device_weights_are_correctly_rounded(cuda):
     from fractions import Fraction
     from volumetricinterp_b200 import _native, fit

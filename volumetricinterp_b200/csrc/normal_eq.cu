@@ -339,6 +339,146 @@ k_ne_dmma3(const double* __restrict__ A, const double* __restrict__ Wm, const do
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// fast, orders beyond the one-CTA form (N > 160: the high-order model of BASELINE configs[2], N = 500; radbasfun
+// NUMGRIDPNT = 7, N = 343): the lower triangle of G in 128 x 128 blocks, one CTA per (block, record), 8 warps of
+// 32 x 64 outputs (16 m16n8k16 tiles each), both operands staged k-slot permuted from the rows of A (32 gates per
+// stage, two stages, 8-byte cp.async: the transposition happens in the copy), weights applied to the A fragments,
+// the right-hand side from the fragments of the diagonal blocks.  Diagonal blocks compute their upper half too
+// (4 of 10 blocks at N = 500: 20 % extra tensor work) -- this is the secondary configuration.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBG = 32;          // gates per stage
+constexpr int kBLD = 34;         // doubles per staged column: 34 = 2 (mod 16)
+constexpr int kBB = 128;         // block edge
+__global__ void __launch_bounds__(256)
+k_ne_dmma_blk(const double* __restrict__ A, const double* __restrict__ Wm, const double* __restrict__ bm,
+              int P, int N, int nb, double* __restrict__ G, double* __restrict__ y) {
+  extern __shared__ __align__(16) double sm[];
+  // per stage: Si (kBB x kBLD), Sj (kBB x kBLD), w (kBG), b (kBG)
+  const int stage_doubles = 2 * kBB * kBLD + 2 * kBG;
+  const int r = blockIdx.y;
+  int bi = 0, bj = 0;
+  {                                                            // blockIdx.x -> (bi >= bj)
+    int rem = blockIdx.x;
+    while (rem > bi) { rem -= bi + 1; ++bi; }
+    bj = rem;
+  }
+  const bool diag = bi == bj;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wr = warp & 3, wc = warp >> 2;                     // 32-row group, 64-column half
+  const double* Wr = Wm + (int64_t)r * P;
+  const double* br = bm + (int64_t)r * P;
+  const int nchunk = (P + kBG - 1) / kBG;
+  auto stage_load = [&](int chunk) {
+    double* Si = sm + (size_t)(chunk & 1) * stage_doubles;
+    double* Sj = Si + kBB * kBLD;
+    double* sw = Sj + kBB * kBLD;
+    double* sb = sw + kBG;
+    const int j0 = chunk * kBG;
+#pragma unroll
+    for (int q = 0; q < kBG / 8; ++q) {                        // a warp copies one gate (one row of A) per trip
+      const int jj = warp + 8 * q, j = j0 + jj;
+      const int sl = gate_slot(jj);
+      const double* src = A + (int64_t)j * N;
+#pragma unroll
+      for (int c4 = 0; c4 < kBB / 32; ++c4) {
+        const int c = lane + 32 * c4;
+        const int ci = kBB * bi + c, cj = kBB * bj + c;
+        if (j < P && ci < N) cp_async8(Si + c * kBLD + sl, src + ci); else Si[c * kBLD + sl] = 0.0;
+        if (!diag) { if (j < P && cj < N) cp_async8(Sj + c * kBLD + sl, src + cj); else Sj[c * kBLD + sl] = 0.0; }
+      }
+    }
+    if (tid < kBG) {
+      const int j = j0 + tid, sl = gate_slot(tid);
+      if (j < P) { cp_async8(sw + sl, Wr + j); cp_async8(sb + sl, br + j); }
+      else { sw[sl] = 0.0; sb[sl] = 0.0; }
+    }
+    cp_async_commit();
+  };
+  double acc[2][8][4];
+  double ya[2][2];
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    ya[m][0] = ya[m][1] = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[m][q][0] = acc[m][q][1] = acc[m][q][2] = acc[m][q][3] = 0.0;
+  }
+  stage_load(0);
+  for (int ch = 0; ch < nchunk; ++ch) {
+    if (ch + 1 < nchunk) { stage_load(ch + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+    __syncthreads();
+    const double* Si = sm + (size_t)(ch & 1) * stage_doubles;
+    const double* Sj = diag ? Si : Si + kBB * kBLD;
+    const double* sw = Si + 2 * kBB * kBLD;
+    const double* sb = sw + kBG;
+#pragma unroll
+    for (int ks = 0; ks < kBG / 16; ++ks) {
+      const int kb = 16 * ks + 4 * t;
+      const double2 w01 = *reinterpret_cast<const double2*>(sw + kb);
+      const double2 w23 = *reinterpret_cast<const double2*>(sw + kb + 2);
+      double a[2][8];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const double* p0 = Si + (32 * wr + 16 * m + g) * kBLD + kb;
+        const double* p1 = p0 + 8 * kBLD;
+        const double2 x01 = *reinterpret_cast<const double2*>(p0), x23 = *reinterpret_cast<const double2*>(p0 + 2);
+        const double2 z01 = *reinterpret_cast<const double2*>(p1), z23 = *reinterpret_cast<const double2*>(p1 + 2);
+        a[m][0] = x01.x * w01.x; a[m][2] = x01.y * w01.y; a[m][4] = x23.x * w23.x; a[m][6] = x23.y * w23.y;
+        a[m][1] = z01.x * w01.x; a[m][3] = z01.y * w01.y; a[m][5] = z23.x * w23.x; a[m][7] = z23.y * w23.y;
+      }
+      if (diag && wc == 0) {                                   // rhs: y_i += sum_k (A_ki w_k) b_k
+        const double2 v01 = *reinterpret_cast<const double2*>(sb + kb);
+        const double2 v23 = *reinterpret_cast<const double2*>(sb + kb + 2);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          ya[m][0] = fma(a[m][0], v01.x, ya[m][0]); ya[m][0] = fma(a[m][2], v01.y, ya[m][0]);
+          ya[m][0] = fma(a[m][4], v23.x, ya[m][0]); ya[m][0] = fma(a[m][6], v23.y, ya[m][0]);
+          ya[m][1] = fma(a[m][1], v01.x, ya[m][1]); ya[m][1] = fma(a[m][3], v01.y, ya[m][1]);
+          ya[m][1] = fma(a[m][5], v23.x, ya[m][1]); ya[m][1] = fma(a[m][7], v23.y, ya[m][1]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const double* pb = Sj + (64 * wc + 8 * q + g) * kBLD + kb;
+        const double2 b01 = *reinterpret_cast<const double2*>(pb), b23 = *reinterpret_cast<const double2*>(pb + 2);
+        const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+        dmma_16x8x16(acc[0][q], a[0], b);
+        dmma_16x8x16(acc[1][q], a[1], b);
+      }
+    }
+    __syncthreads();
+  }
+  // c0 (row g, col 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1)
+  double* Gr = G + (int64_t)r * N * N;
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int i = kBB * bi + 32 * wr + 16 * m + g + ((v & 2) ? 8 : 0);
+        const int k = kBB * bj + 64 * wc + 8 * q + 2 * t + (v & 1);
+        if (i < N && k <= i) {
+          Gr[(int64_t)i * N + k] = acc[m][q][v];
+          if (k != i) Gr[(int64_t)k * N + i] = acc[m][q][v];
+        }
+      }
+  if (diag && wc == 0) {
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      double y0 = ya[m][0], y1 = ya[m][1];
+      y0 += __shfl_xor_sync(0xffffffffu, y0, 1); y1 += __shfl_xor_sync(0xffffffffu, y1, 1);
+      y0 += __shfl_xor_sync(0xffffffffu, y0, 2); y1 += __shfl_xor_sync(0xffffffffu, y1, 2);
+      if (t == 0) {
+        const int i = kBB * bi + 32 * wr + 16 * m + g;
+        if (i < N) y[(int64_t)r * N + i] = y0;
+        if (i + 8 < N) y[(int64_t)r * N + i + 8] = y1;
+      }
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int vi_normal_eq_batched(const double* A, const double* value, const double* error, const double* weight,
@@ -369,7 +509,9 @@ extern "C" int vi_normal_eq_batched(const double* A, const double* value, const 
   const int cols3 = 16 * mt;
   const size_t smem3 = ((size_t)kEStages * cols3 * kELD + 2 * kEStages * kEJ) * sizeof(double) + 64;
   NeSplit sp;
-  if (smem3 > 227 * 1024 || !ne3_split(N, mt, 7, sp)) return strict();
+  const bool one_cta = smem3 <= 227 * 1024 && ne3_split(N, mt, 7, sp);
+  static const bool no_blk = getenv("VI_NE_BIG_STRICT") != nullptr;      // A/B: strict kernel for the large orders
+  if (!one_cta && (no_blk || R > 65535)) return strict();
   // masked weights / data: the caller's arrays, else a stream-ordered temporary
   double *Wt = nullptr, *bt = nullptr;
   if (!Wm || !bm) {
@@ -382,14 +524,27 @@ extern "C" int vi_normal_eq_batched(const double* A, const double* value, const 
     VI_KERNEL(VI_K_NORMAL_EQ, s, k_prep<<<R, 256, 0, s>>>(value, error, weight, P, nullptr, nullptr, Wt, bt));
     Wm = Wt; bm = bt;
   }
-  cudaError_t e = cudaFuncSetAttribute(k_ne_dmma3<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
-  if (e == cudaSuccess) {
-    vi_prof_launch_begin(VI_K_NORMAL_EQ, s);
-    k_ne_dmma3<7><<<(unsigned)R, kW3 * 32, smem3, s>>>(A, Wm, bm, P, N, mt, cols3, sp, G, y);
-    vi_prof_launch_end(VI_K_NORMAL_EQ, s);
-    e = cudaGetLastError();
+  cudaError_t e;
+  if (one_cta) {
+    e = cudaFuncSetAttribute(k_ne_dmma3<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+    if (e == cudaSuccess) {
+      vi_prof_launch_begin(VI_K_NORMAL_EQ, s);
+      k_ne_dmma3<7><<<(unsigned)R, kW3 * 32, smem3, s>>>(A, Wm, bm, P, N, mt, cols3, sp, G, y);
+      vi_prof_launch_end(VI_K_NORMAL_EQ, s);
+      e = cudaGetLastError();
+    }
+  } else {
+    const int nb = (N + kBB - 1) / kBB;
+    const size_t smemb = (size_t)2 * (2 * kBB * kBLD + 2 * kBG) * sizeof(double);
+    e = cudaFuncSetAttribute(k_ne_dmma_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemb);
+    if (e == cudaSuccess) {
+      vi_prof_launch_begin(VI_K_NORMAL_EQ, s);
+      k_ne_dmma_blk<<<dim3((unsigned)(nb * (nb + 1) / 2), (unsigned)R), 256, smemb, s>>>(A, Wm, bm, P, N, nb, G, y);
+      vi_prof_launch_end(VI_K_NORMAL_EQ, s);
+      e = cudaGetLastError();
+    }
   }
   if (Wt) { cudaFreeAsync(Wt, s); cudaFreeAsync(bt, s); }
-  if (e != cudaSuccess) { vi_set_error("k_ne_dmma3: %s", cudaGetErrorString(e)); return VI_ECUDA; }
+  if (e != cudaSuccess) { vi_set_error("tensor-core normal equations: %s", cudaGetErrorString(e)); return VI_ECUDA; }
   return VI_OK;
 }
