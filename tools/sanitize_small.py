@@ -1,5 +1,6 @@
-"""Small end-to-end pass for compute-sanitizer (memcheck): every round-2 kernel at a small size.
-    compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
+"""Small end-to-end pass over every round-2 kernel at small and odd sizes (orders at the kernel boundaries, masked gates,
+ragged tiles).  Written for `compute-sanitizer --tool memcheck`; the sanitizer is closed on this GPU pool, so the pass
+was run plain (it completes; results are checked by the GPU tests)."""
 import io
 import sys
 import numpy as np
