@@ -54,7 +54,9 @@ one("2 GPUs strong", load("r02_bench_2gpu_strong.json"), "torchrun `--scaling st
 one("2 GPUs C4", load("r02_bench_2gpu_c4.json"), "torchrun `--config c4 --tiles 32`, point-sharded")
 one("4 GPUs weak", load("r02_bench_4gpu_weak.json"), "torchrun, 10 000 records per GPU, `--steps 2`")
 one("4 GPUs C4", load("r02_bench_4gpu_c4.json"), "torchrun `--config c4 --tiles 32`")
+one("4 GPUs strong", load("r02_bench_4gpu_strong.json"), "torchrun `--scaling strong --records 10000 --steps 2`")
 one("8 GPUs weak", load("r02_bench_8gpu_weak.json"), "torchrun, 10 000 records per GPU, `--steps 2`")
+one("8 GPUs strong", load("r02_bench_8gpu_strong.json"), "torchrun `--scaling strong --records 10000 --steps 2`")
 one("8 GPUs C4", load("r02_bench_8gpu_c4.json"), "torchrun `--config c4 --tiles 32`")
 if d:
     out += ["", f"* fit of the default run: {d.get('fit')}",
