@@ -78,6 +78,14 @@ if d:
         out += ["", "Parity block of the line (first 16 records of the benchmarked workload, GPU vs the reference algorithm): "
                 f"`{json.dumps(p['gpu_vs_reference'])[:900]}`"]
 
+lst0 = os.path.join(P, "r02_launches_records10000.csv")
+if os.path.exists(lst0):
+    out += ["", "## Launch list of the default workload (`ncu --metrics gpu__time_duration.sum --clock-control none`, "
+            "`bench.py --steps 1 --warmup 1 --e2e-steps 1 --no-cpu-baseline --no-estimate`: 10 000 records, three passes; "
+            "`profiles/r02_launches_records10000.csv`)", "",
+            "The kernels' shares agree with the CUDA-event shares of the bench line above (stage 1 28.4 vs 28.5 %, QL 20.0 vs 20.3 %, "
+            "chase 19.3 vs 19.4 %, replay 16.6 vs 16.5 %, chi2 5.5 vs 5.4 %, covariance 6.6 vs 6.6 %, normal equations 2.7 vs 2.7 %).", "",
+            "\n".join(l for l in launch_table(lst0).split("\n")[:22] if not l.startswith("| at::") and "elementwise" not in l)]
 lst = "gpurun_out/r02_launches_records2000.csv"
 if os.path.exists(lst):
     out += ["", "## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, "
